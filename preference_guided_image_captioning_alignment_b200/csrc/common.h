@@ -1,0 +1,44 @@
+// Host-side helpers shared by the C-ABI translation units: thread-local error string,
+// CUDA error mapping, TMA tensor-map construction (driver entry point resolved at run time,
+// so the library links against cudart only).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/pgica.h"
+
+namespace pgica {
+
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define PGICA_CUDA_OK(expr)                                                                    \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      ::pgica::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return PGICA_ERR_CUDA;                                                                   \
+    }                                                                                          \
+  } while (0)
+
+#define PGICA_REQUIRE(cond, ...)          \
+  do {                                    \
+    if (!(cond)) {                        \
+      ::pgica::set_error(__VA_ARGS__);    \
+      return PGICA_ERR_INVALID_ARGUMENT;  \
+    }                                     \
+  } while (0)
+
+// Row-major [rows][cols] bf16 matrix with `row_stride` elements between rows; box = box_rows x 64
+// columns, SWIZZLE_128B, out-of-bounds elements read as zero.
+int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride,
+                   uint32_t box_rows);
+
+int device_sm_count();
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace pgica

@@ -1,0 +1,329 @@
+// K1/K3: z = scale * A B^T on tcgen05 tensor cores with the softmax statistics taken straight out of
+// TMEM — running max / sum-of-exp per row and the target logit — so the (rows x cols) logit matrix is
+// never written anywhere.  Persistent, warp-specialised:
+//   warp 0      TMA producer (A tile 128x64, B tile 256x64 per k-step, SWIZZLE_128B, 4-stage ring)
+//   warp 1      tcgen05.mma issuer (one elected thread), accumulators 128x256 fp32, double-buffered in TMEM
+//   warp 2      TMEM allocator
+//   warps 4..7  epilogue: tcgen05.ld 32 columns at a time, online log-sum-exp in the log2 domain
+// Tiles are linearised row-block-major and cut into equal contiguous ranges, one per CTA, so a CTA keeps
+// a row's (max, sum) in registers across consecutive column tiles; where a range boundary splits a row
+// block the pieces are written as partials and merged by lse_merge_kernel.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace pgica {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockN = 256;
+constexpr int kBlockK = 64;
+constexpr int kUmmaK = 16;
+constexpr int kStages = 4;
+constexpr int kAccStages = 2;
+constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
+constexpr uint32_t kBBytes = kBlockN * kBlockK * 2;
+constexpr int kThreads = 256;
+constexpr int kEpilogueWarp0 = 4;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+struct GemmLseParams {
+  int rows, cols, k;
+  int num_m_blocks, num_n_tiles, tiles_per_cta, rows_pad;
+  float scale;
+  const int* labels;
+  int diag_offset;
+  float* part_max;  // [slots][rows_pad]  running max of scale*log2e*z
+  float* part_sum;  // [slots][rows_pad]  sum of exp2(. - max)
+  float* part_tgt;  // [slots][rows_pad]  scale*z at the label column, -inf if not seen in this piece
+};
+
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + kStages * (kABytes + kBBytes) + 256 /*barriers*/;
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_lse_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                const GemmLseParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * (kABytes + kBBytes));
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;
+  uint64_t* tempty_bar = tfull_bar + kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + kAccStages);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.num_m_blocks * p.num_n_tiles;
+  const int t_begin = blockIdx.x * p.tiles_per_cta;
+  const int t_end = min(t_begin + p.tiles_per_cta, total_tiles);
+  const int num_kb = (p.k + kBlockK - 1) / kBlockK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < kAccStages; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<kAccStages * kBlockN>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int m_blk = t / p.num_n_tiles;
+        const int n_tile = t - m_blk * p.num_n_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], kABytes + kBBytes);
+          tma_load_2d(smem_a + stage * kABytes, &tm_a, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
+          tma_load_2d(smem_b + stage * kBBytes, &tm_b, &full_bar[stage], kb * kBlockK, n_tile * kBlockN);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, kBlockN, 0, 0);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * kBlockN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(smem_a + stage * kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + stage * kBBytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t da = make_smem_desc(a_addr + k * kUmmaK * 2, 16, 1024);
+            const uint64_t db = make_smem_desc(b_addr + k * kUmmaK * 2, 16, 1024);
+            umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);
+        if (++acc == kAccStages) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= kEpilogueWarp0) {
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    const int row_in_blk = quarter * 32 + lane;
+    const float c = p.scale * kLog2e;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int cur_mblk = -1;
+    float run_m = -INFINITY, run_s = 0.f, run_t = -INFINITY;
+    int label = -1;
+
+    auto flush = [&]() {
+      if (cur_mblk < 0) return;
+      const int first_cta = (cur_mblk * p.num_n_tiles) / p.tiles_per_cta;
+      const int slot = blockIdx.x - first_cta;
+      const size_t o = static_cast<size_t>(slot) * p.rows_pad + cur_mblk * kBlockM + row_in_blk;
+      p.part_max[o] = run_m;
+      p.part_sum[o] = run_s;
+      p.part_tgt[o] = run_t;
+    };
+
+    for (int t = t_begin; t < t_end; ++t) {
+      const int m_blk = t / p.num_n_tiles;
+      const int n_tile = t - m_blk * p.num_n_tiles;
+      if (m_blk != cur_mblk) {
+        flush();
+        cur_mblk = m_blk;
+        run_m = -INFINITY;
+        run_s = 0.f;
+        run_t = -INFINITY;
+        const int row = m_blk * kBlockM + row_in_blk;
+        label = -1;
+        if (row < p.rows) label = p.labels ? p.labels[row] : row + p.diag_offset;
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after_sync();
+
+      const int n0 = n_tile * kBlockN;
+      const bool tail = n0 + kBlockN > p.cols;
+      const int rel = label - n0;  // label column relative to this tile
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kBlockN;
+#pragma unroll 1
+      for (int ch = 0; ch < kBlockN / 32; ++ch) {
+        if (tail && n0 + ch * 32 >= p.cols) break;  // warp-uniform: nothing valid from here on
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + ch * 32, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (tail) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + ch * 32 + j >= p.cols) v[j] = -INFINITY;
+        }
+        float cm = v[0];
+#pragma unroll
+        for (int j = 1; j < 32; ++j) cm = fmaxf(cm, v[j]);
+        const float m_new = fmaxf(run_m, cm * c);
+        const float corr = fast_exp2(run_m - m_new);
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          s0 += fast_exp2(fmaf(v[j], c, -m_new));
+          s1 += fast_exp2(fmaf(v[j + 1], c, -m_new));
+        }
+        run_s = fmaf(run_s, corr, s0 + s1);
+        run_m = m_new;
+        if ((rel >> 5) == ch && rel >= 0) {
+          const int jj = rel & 31;
+          float z = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j == jj) z = v[j];
+          run_t = z * p.scale;
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&tempty_bar[acc]);
+      if (++acc == kAccStages) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    flush();
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<kAccStages * kBlockN>(tmem_base);
+}
+
+// One thread per row: fold the per-CTA pieces of that row into lse (natural log) and the target logit.
+__global__ void lse_merge_kernel(const GemmLseParams p, float* __restrict__ lse, float* __restrict__ tgt) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= p.rows) return;
+  const int m_blk = row / kBlockM;
+  const int first_cta = (m_blk * p.num_n_tiles) / p.tiles_per_cta;
+  const int last_cta = ((m_blk + 1) * p.num_n_tiles - 1) / p.tiles_per_cta;
+  float m = -INFINITY, t = -INFINITY;
+  for (int s = 0; s <= last_cta - first_cta; ++s) {
+    const size_t o = static_cast<size_t>(s) * p.rows_pad + row;
+    m = fmaxf(m, p.part_max[o]);
+    t = fmaxf(t, p.part_tgt[o]);
+  }
+  float sum = 0.f;
+  bool bad = false;
+  for (int s = 0; s <= last_cta - first_cta; ++s) {
+    const size_t o = static_cast<size_t>(s) * p.rows_pad + row;
+    const float ps = p.part_sum[o];
+    bad |= (ps != ps);
+    sum += ps * exp2f(p.part_max[o] - m);
+  }
+  float out = (m + log2f(sum)) * kLn2;
+  if (bad) out = NAN;
+  lse[row] = out;
+  if (tgt) tgt[row] = (t == -INFINITY) ? 0.f : t;
+}
+
+int plan(int64_t rows, int64_t cols, int64_t k, GemmLseParams* p, int* grid, size_t* ws_bytes) {
+  PGICA_REQUIRE(rows > 0 && cols > 0 && k > 0, "gemm_lse: empty problem (rows %lld cols %lld k %lld)", (long long)rows,
+                (long long)cols, (long long)k);
+  PGICA_REQUIRE(k % 8 == 0, "gemm_lse: k (%lld) must be a multiple of 8 (16-byte row pitch for TMA)", (long long)k);
+  PGICA_REQUIRE(rows < (1ll << 30) && cols < (1ll << 30), "gemm_lse: dimension too large");
+  p->rows = (int)rows;
+  p->cols = (int)cols;
+  p->k = (int)k;
+  p->num_m_blocks = (int)ceil_div(rows, kBlockM);
+  p->num_n_tiles = (int)ceil_div(cols, kBlockN);
+  p->rows_pad = p->num_m_blocks * kBlockM;
+  const int64_t total = (int64_t)p->num_m_blocks * p->num_n_tiles;
+  PGICA_REQUIRE(total < (1ll << 31), "gemm_lse: too many tiles");
+  const int sms = device_sm_count();
+  const int ctas = (int)(total < sms ? total : sms);
+  p->tiles_per_cta = (int)ceil_div(total, ctas);
+  *grid = (int)ceil_div(total, p->tiles_per_cta);
+  // a row block of num_n_tiles tiles can straddle at most this many CTA ranges
+  const int slots = (p->num_n_tiles + p->tiles_per_cta - 2) / p->tiles_per_cta + 1;
+  *ws_bytes = 3 * align_up((size_t)slots * p->rows_pad * sizeof(float), 256);
+  return PGICA_OK;
+}
+
+}  // namespace
+}  // namespace pgica
+
+extern "C" {
+
+int pgica_gemm_lse_workspace_bytes(int64_t rows, int64_t cols, int64_t k, size_t* bytes_host) {
+  pgica::GemmLseParams p{};
+  int grid = 0;
+  return pgica::plan(rows, cols, k, &p, &grid, bytes_host);
+}
+
+int pgica_gemm_lse(const void* a, const void* b, int64_t rows, int64_t cols, int64_t k, float scale,
+                   const int32_t* labels, int64_t diag_offset, float* lse, float* tgt, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  using namespace pgica;
+  int rc = pgica_device_check();
+  if (rc != PGICA_OK) return rc;
+  GemmLseParams p{};
+  int grid = 0;
+  size_t need = 0;
+  rc = plan(rows, cols, k, &p, &grid, &need);
+  if (rc != PGICA_OK) return rc;
+  PGICA_REQUIRE(a && b && lse, "gemm_lse: null operand");
+  PGICA_REQUIRE(scale > 0.f && scale == scale, "gemm_lse: scale must be positive (got %g)", (double)scale);
+  if (workspace_bytes < need || !workspace) {
+    set_error("gemm_lse: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return PGICA_ERR_WORKSPACE_TOO_SMALL;
+  }
+  const size_t seg = need / 3;
+  p.part_max = reinterpret_cast<float*>(workspace);
+  p.part_sum = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + seg);
+  p.part_tgt = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + 2 * seg);
+  p.scale = scale;
+  p.labels = labels;
+  p.diag_offset = (int)diag_offset;
+
+  CUtensorMap tm_a, tm_b;
+  rc = make_tmap_bf16(&tm_a, a, rows, k, k, kBlockM);
+  if (rc != PGICA_OK) return rc;
+  rc = make_tmap_bf16(&tm_b, b, cols, k, k, kBlockN);
+  if (rc != PGICA_OK) return rc;
+
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PGICA_CUDA_OK(cudaFuncSetAttribute(gemm_lse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  gemm_lse_kernel<<<grid, kThreads, kSmemBytes, st>>>(tm_a, tm_b, p);
+  PGICA_CUDA_OK(cudaGetLastError());
+  lse_merge_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, st>>>(p, lse, tgt);
+  PGICA_CUDA_OK(cudaGetLastError());
+  return PGICA_OK;
+}
+
+}  // extern "C"
