@@ -78,6 +78,113 @@ int pgica_gemm_lse(const void* a, const void* b, int64_t rows, int64_t cols, int
 int pgica_probe_umma(const void* a, const void* b, int64_t n, int64_t k, int b_mn_major, int a_manual,
                      uint32_t b_lbo_bytes, uint32_t b_sbo_bytes, float* d, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K2/K4 core — "softmax-gradient GEMM": the backward of both heads, logits recomputed tile-wise.
+ *
+ *   out[i,:] = sum_j G(i,j) * y[j,:],   z_ij = <x[i,:], y[j,:]>
+ *   G(i,j)   = r_coef[i] * (exp(scale*z_ij - r_lse[i]) - [j == r_tgt[i]])      (row term, if r_lse != NULL)
+ *            + c_coef[j] * (exp(scale*z_ij - c_lse[j]) - [i == c_tgt[j]])      (column term, if c_lse != NULL)
+ *
+ * x: bf16 [mx][k], y: bf16 [my][k], out: [mx][k] fp32 or bf16.  Replaces what autograd derives from
+ * pkg/models/components.py:346-358 / pkg/models/model.py:1074-1083 (log_softmax, gather, mask, sum) chained
+ * into the lm_head matmul, and from F.cross_entropy x2 + matmul in pkg/models/model.py:988-998 /
+ * pkg/models/components.py:131-141 (closed forms: SURVEY.md Appendix A).
+ * ---------------------------------------------------------------------------------------------- */
+int pgica_softmax_grad_gemm(const void* x, const void* y, int64_t mx, int64_t my, int64_t k, float scale,
+                            const float* r_lse, const float* r_coef, const int32_t* r_tgt, const float* c_lse,
+                            const float* c_coef, const int32_t* c_tgt, void* out, int out_is_bf16, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage-2 head, hidden-state level (logits never materialised).
+ *
+ * pgica_lmhead_logprob_fwd: for nseq sequences of seqlen positions, hidden bf16 [nseq*seqlen][d], weight bf16
+ *   [vocab][d] (tied wte / lm_head), labels int64 [nseq][seqlen], mask [nseq][seqlen] of kind `mask_kind`:
+ *     seq_logp[b] = sum_{t<seqlen-1} mask[b][t+1] * log softmax(W h[b][t])[labels[b][t+1]]
+ *   divided by sum_t mask[b][t+1] when length_normalize != 0.
+ *   length_normalize = 0 is compute_sequence_logprobs (pkg/models/components.py:321-362) on
+ *   lm_head(hidden) (modeling_gpt2.py:706); = 1 is PreferenceLoss._compute_log_probs
+ *   (pkg/models/model.py:1052-1085).  Also returns, per row r = b*seqlen + t: lse[r], ztgt[r] (target logit),
+ *   row_label[r] (int32, -1 where nothing is scored) and row_weight[r] — the plumbing the backward reuses —
+ *   and, if nll_sum != NULL, sum over all scored positions of -log p (numerator of the HF causal-LM loss,
+ *   transformers loss_utils.py:45-67 as reached from pkg/models/model.py:604-610).
+ * pgica_lmhead_logprob_bwd: given grad_seq[b] = dLoss/dseq_logp[b], writes dhidden [nseq*seqlen][d] and/or
+ *   dweight [vocab][d] (each may be NULL).
+ * workspace: pgica_lmhead_logprob_workspace_bytes() bytes, scratch only.
+ * ---------------------------------------------------------------------------------------------- */
+int pgica_lmhead_logprob_workspace_bytes(int64_t nseq, int64_t seqlen, int64_t d, int64_t vocab, size_t* bytes_host);
+int pgica_lmhead_logprob_fwd(const void* hidden, const void* weight, const int64_t* labels, const void* mask,
+                             int mask_kind, int64_t nseq, int64_t seqlen, int64_t d, int64_t vocab,
+                             int length_normalize, float* seq_logp, float* lse, float* ztgt, int32_t* row_label,
+                             float* row_weight, float* nll_sum, void* workspace, size_t workspace_bytes,
+                             void* stream);
+int pgica_lmhead_logprob_bwd(const void* hidden, const void* weight, const int32_t* row_label,
+                             const float* row_weight, const float* lse, const float* grad_seq, int64_t nseq,
+                             int64_t seqlen, int64_t d, int64_t vocab, int length_normalize, void* dhidden,
+                             int dhidden_is_bf16, void* dweight, int dweight_is_bf16, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
+/* DPOPreferenceLoss.forward (pkg/models/components.py:192-249) and the tail of PreferenceLoss.forward
+ * (pkg/models/model.py:1046-1048) on n local pairs of an n_global-pair batch (n_global = n on one GPU):
+ *   x = beta*((pc-pr) - (rc-rr)),  loss = sum(-logsigmoid(x))/n_global  (label smoothing: cDPO form)
+ *   metrics[5] = {dpo_loss, reward_margin, reward_accuracy, policy_chosen_logprob, policy_rejected_logprob}
+ *   (local sums / n_global), dpc[i] = dloss/dpc[i]  (= -dloss/dpr = -dloss/drc = dloss/drr).
+ * rc = rr = NULL means reference-free.  All buffers fp32 on the device. */
+int pgica_dpo_loss_fwd(const float* pc, const float* pr, const float* rc, const float* rr, int64_t n,
+                       int64_t n_global, float beta, float label_smoothing, float* loss, float* metrics, float* dpc,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage-1 head: symmetric NT-Xent on a (rows_a x rows_b) slice of the similarity matrix; positives are
+ * (i, i + diag_offset).  a: bf16 [rows_a][dim], b: bf16 [rows_b][dim], inv_tau = 1/temperature.
+ *   fwd: lse_row[i] = logsumexp_j S[i][j], diag[i] = S[i][i+diag_offset], lse_col_part[j] = logsumexp_i S[i][j]
+ *        (complete when rows_a == rows_b; one rank's partial otherwise — merge with pgica_lse_combine).
+ *   bwd: da = dS b / tau, db = dS^T a / tau with dS = grad_loss[0]*grad_mult*(P_row + P_col - 2 I)
+ *        (grad_mult = 1/(2 B_global) for reduction "mean", 1/2 for "sum").
+ * Replaces pkg/models/model.py:970-1000 and pkg/models/components.py:117-145 (and their autograd).
+ * ---------------------------------------------------------------------------------------------- */
+int pgica_ntxent_workspace_bytes(int64_t rows_a, int64_t rows_b, int64_t dim, size_t* bytes_host);
+int pgica_ntxent_fwd(const void* a, const void* b, int64_t rows_a, int64_t rows_b, int64_t dim, float inv_tau,
+                     int64_t diag_offset, float* lse_row, float* diag, float* lse_col_part, void* workspace,
+                     size_t workspace_bytes, void* stream);
+int pgica_ntxent_bwd(const void* a, const void* b, int64_t rows_a, int64_t rows_b, int64_t dim, float inv_tau,
+                     int64_t diag_offset, const float* lse_row, const float* lse_col, const float* grad_loss,
+                     float grad_mult, void* da, int da_is_bf16, void* db, int db_is_bf16, void* workspace,
+                     size_t workspace_bytes, void* stream);
+/* loss = 0.5 * inv_denom * sum_i [(lse_row[i]-diag[i]) + (lse_col_owned[i]-diag[i])]   (model.py:994-998) */
+int pgica_ntxent_loss(const float* lse_row, const float* diag, const float* lse_col_owned, int64_t n,
+                      float inv_denom, float* loss, void* stream);
+/* out[j] = log sum_r exp(parts[r][j]), parts fp32 [nparts][n] (column statistics gathered from all ranks) */
+int pgica_lse_combine(const float* parts, int64_t nparts, int64_t n, float* out, void* stream);
+int pgica_ntxent_coef(const float* grad, float mult, int64_t n, int64_t tgt_offset, int64_t tgt_limit, float* coef,
+                      int32_t* tgt, void* stream);
+
+/* F.normalize(x, p=2, dim=-1) (pkg/models/components.py:74-75, pkg/models/model.py:828-829) and its backward
+ * dx = (g - xh <xh, g>) / max(||x||, eps).  y is bf16 (the tensor-core operand); x fp32 or bf16; dx fp32. */
+int pgica_rownorm_fwd(const void* x, int x_is_bf16, int64_t rows, int64_t dim, float eps, void* y_bf16,
+                      float* inv_norm, void* stream);
+int pgica_rownorm_bwd(const void* x, int x_is_bf16, const float* inv_norm, const void* g, int g_is_bf16, int64_t rows,
+                      int64_t dim, float* dx, void* stream);
+int pgica_cast_f32_to_bf16(const float* x, int64_t n, void* y_bf16, void* stream);
+
+/* Plumbing pieces of the Stage-2 head, exported so the parity tests can pin them bit-exactly:
+ * shift / label / mask layout (components.py:339-344), per-sequence masked sum (components.py:355-360,
+ * model.py:1082-1083), per-row backward coefficients. */
+int pgica_prep_rows(const int64_t* labels, const void* mask, int mask_kind, int64_t nseq, int64_t seqlen,
+                    int64_t vocab, int32_t* row_label, float* row_weight, void* stream);
+int pgica_seq_reduce(const float* lse, const float* ztgt, const float* row_weight, int64_t nseq, int64_t seqlen,
+                     int length_normalize, float* seq_logp, float* nll_sum, void* stream);
+int pgica_row_coef(const float* grad_seq, const float* row_weight, int64_t nseq, int64_t seqlen, int length_normalize,
+                   float sign, float* coef, void* stream);
+int pgica_scale_by_scalar(const float* a, const float* scalar, float mult, int64_t n, float* out, void* stream);
+
+/* Materialised-logits path (strict signature compatibility with PreferenceLoss.forward /
+ * compute_sequence_logprobs, which receive (nseq, seqlen, vocab) logits): streaming log-sum-exp + gather, and
+ * dlogits = coef * (onehot - softmax).  HBM-bound; logits fp32 or bf16. */
+int pgica_logits_lse(const void* logits, int logits_is_bf16, const int32_t* row_label, int64_t nseq, int64_t seqlen,
+                     int64_t vocab, float* lse, float* ztgt, void* stream);
+int pgica_logits_grad(const void* logits, int logits_is_bf16, const int32_t* row_label, const float* lse,
+                      const float* coef, int64_t nseq, int64_t seqlen, int64_t vocab, void* dlogits, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

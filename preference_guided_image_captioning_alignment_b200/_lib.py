@@ -1,36 +1,28 @@
-"""ctypes binding of libpgica.so (the C ABI declared in include/pgica.h).
+"""ctypes binding of libpgica.so — the C ABI declared in include/pgica.h.
 
-The library is the product: if it is missing or fails to load, every op raises — there is no
+The prototypes are parsed from the header itself, so the binding cannot drift from the declared ABI.
+The library is the product: if it is missing or fails to load every op raises — there is no
 PyTorch/CPU fallback behind these calls.
 """
 import ctypes
 import os
+import re
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpgica.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "pgica.h")
 
 _lock = threading.Lock()
 _lib = None
 
-c_void_p = ctypes.c_void_p
-c_int = ctypes.c_int
-c_int64 = ctypes.c_int64
-c_float = ctypes.c_float
-c_size_t = ctypes.c_size_t
-c_uint32 = ctypes.c_uint32
-
-# name -> (restype, argtypes); must list every symbol include/pgica.h declares (tests check this).
-SIGNATURES = {
-    "pgica_abi_version": (c_int, []),
-    "pgica_last_error": (ctypes.c_char_p, []),
-    "pgica_device_check": (c_int, []),
-    "pgica_sm_count": (c_int, []),
-    "pgica_gemm_lse_workspace_bytes": (c_int, [c_int64, c_int64, c_int64, ctypes.POINTER(c_size_t)]),
-    "pgica_gemm_lse": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p, c_int64,
-                               c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "pgica_probe_umma": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_uint32, c_uint32,
-                                 c_void_p, c_void_p]),
+_SCALARS = {
+    "int": ctypes.c_int,
+    "int64_t": ctypes.c_int64,
+    "int32_t": ctypes.c_int32,
+    "uint32_t": ctypes.c_uint32,
+    "float": ctypes.c_float,
+    "size_t": ctypes.c_size_t,
 }
 
 
@@ -38,8 +30,36 @@ class PgicaError(RuntimeError):
     pass
 
 
+def _ctype(decl):
+    decl = decl.strip()
+    if decl == "void":
+        return None
+    if "*" in decl:
+        base = decl.replace("const", "").replace("*", "").split()[0]
+        if base == "size_t":
+            return ctypes.POINTER(ctypes.c_size_t)
+        if base == "char":
+            return ctypes.c_char_p
+        return ctypes.c_void_p
+    base = decl.replace("const", "").split()[0]
+    return _SCALARS[base]
+
+
+def parse_header(path=HEADER_PATH):
+    """-> {name: (restype, [argtypes])} for every function prototype in the header."""
+    text = open(path).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"^\s*#.*$", "", text, flags=re.M)
+    protos = {}
+    for m in re.finditer(r"([A-Za-z_][\w\s\*]*?)\b(pgica_\w+)\s*\(([^)]*)\)\s*;", text):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
+        argtypes = [] if args in ("", "void") else [_ctype(a) for a in args.split(",")]
+        protos[name] = (_ctype(ret) if ret != "const char*" and "char" not in ret else ctypes.c_char_p, argtypes)
+    return protos
+
+
 def load(build_if_missing=True):
-    """Load (building first if the in-tree .so is absent and nvcc is available)."""
+    """Load the library (building it first if the in-tree .so is absent and nvcc is available)."""
     global _lib
     with _lock:
         if _lib is not None:
@@ -50,7 +70,7 @@ def load(build_if_missing=True):
             from . import _build
             _build.build()
         lib = ctypes.CDLL(LIB_PATH)
-        for name, (restype, argtypes) in SIGNATURES.items():
+        for name, (restype, argtypes) in parse_header().items():
             fn = getattr(lib, name)  # AttributeError here == header/library mismatch: fail loudly
             fn.restype = restype
             fn.argtypes = argtypes
@@ -60,8 +80,7 @@ def load(build_if_missing=True):
         return lib
 
 
-def check(rc, lib=None):
+def check(rc):
     if rc != 0:
-        lib = lib or load()
-        msg = lib.pgica_last_error()
+        msg = load().pgica_last_error()
         raise PgicaError(f"pgica error {rc}: {msg.decode() if msg else '?'}")

@@ -1,0 +1,287 @@
+"""Tensor-level wrappers over the C ABI (include/pgica.h): allocate outputs with torch, pass raw device
+pointers and the current CUDA stream.  No arithmetic happens here — PyTorch is only memory and streams.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+MASK_NONE, MASK_I64, MASK_F32, MASK_U8, MASK_I32 = 0, 1, 2, 3, 4
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.PgicaError(
+                "pgica ops run on a B200 only (got a %s tensor); there is no CPU fallback" % t.device.type)
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def as_bf16(x):
+    """bf16 contiguous view/copy of a float tensor; fp32 goes through the library's cast kernel."""
+    _need_cuda(x)
+    if x.dtype == torch.bfloat16:
+        return x.contiguous()
+    if x.dtype != torch.float32:
+        x = x.float()
+    x = x.contiguous()
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    if x.numel():
+        _lib.check(_lib.load().pgica_cast_f32_to_bf16(_p(x), x.numel(), _p(y), _stream()))
+    return y
+
+
+def mask_kind(mask):
+    if mask is None:
+        return MASK_NONE, None
+    if mask.dtype == torch.int64:
+        return MASK_I64, mask.contiguous()
+    if mask.dtype == torch.float32:
+        return MASK_F32, mask.contiguous()
+    if mask.dtype in (torch.bool, torch.uint8):
+        return MASK_U8, mask.contiguous().view(torch.uint8)
+    if mask.dtype == torch.int32:
+        return MASK_I32, mask.contiguous()
+    return MASK_F32, mask.float().contiguous()
+
+
+# ----------------------------------------------------------------------------------------- K1/K3 core
+def gemm_lse(a, b, scale=1.0, labels=None, diag_offset=0, want_tgt=True):
+    """lse[i] = logsumexp_j scale*<a_i, b_j>;  tgt[i] = scale*<a_i, b_label(i)>.  a, b bf16 [*, k]."""
+    _need_cuda(a, b, labels)
+    lib = _lib.load()
+    rows, k = a.shape
+    cols = b.shape[0]
+    need = ctypes.c_size_t(0)
+    _lib.check(lib.pgica_gemm_lse_workspace_bytes(rows, cols, k, ctypes.byref(need)))
+    ws = _ws(need.value, a.device)
+    lse = torch.empty(rows, dtype=torch.float32, device=a.device)
+    tgt = torch.empty(rows, dtype=torch.float32, device=a.device) if want_tgt else None
+    _lib.check(lib.pgica_gemm_lse(_p(a), _p(b), rows, cols, k, float(scale), _p(labels), int(diag_offset), _p(lse),
+                                  _p(tgt), _p(ws), need.value, _stream()))
+    return lse, tgt
+
+
+# ----------------------------------------------------------------------------------------- K2/K4 core
+def softmax_grad_gemm(x, y, scale=1.0, row=None, col=None, out_dtype=torch.float32):
+    """out = G(x y^T) y with G built from row stats (lse, coef, tgt) and/or column stats (see pgica.h)."""
+    _need_cuda(x, y)
+    lib = _lib.load()
+    mx, k = x.shape
+    my = y.shape[0]
+    out = torch.empty(mx, k, dtype=out_dtype, device=x.device)
+    r = row if row is not None else (None, None, None)
+    c = col if col is not None else (None, None, None)
+    _lib.check(lib.pgica_softmax_grad_gemm(_p(x), _p(y), mx, my, k, float(scale), _p(r[0]), _p(r[1]), _p(r[2]),
+                                           _p(c[0]), _p(c[1]), _p(c[2]), _p(out),
+                                           1 if out_dtype == torch.bfloat16 else 0, _stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------------------- Stage-2 head
+def lmhead_logprob_fwd(hidden, weight, labels, mask=None, length_normalize=False, want_nll=False):
+    """hidden bf16 [nseq, T, d], weight bf16 [V, d], labels int64 [nseq, T] -> seq_logp [nseq] + saved ctx."""
+    _need_cuda(hidden, weight, labels, mask)
+    lib = _lib.load()
+    nseq, T, d = hidden.shape
+    V = weight.shape[0]
+    dev = hidden.device
+    kind, mask_c = mask_kind(mask)
+    labels = labels.contiguous()
+    if labels.dtype != torch.int64:
+        labels = labels.long()
+    need = ctypes.c_size_t(0)
+    _lib.check(lib.pgica_lmhead_logprob_workspace_bytes(nseq, T, d, V, ctypes.byref(need)))
+    ws = _ws(need.value, dev)
+    f32 = dict(dtype=torch.float32, device=dev)
+    seq_logp = torch.empty(nseq, **f32)
+    lse = torch.empty(nseq * T, **f32)
+    ztgt = torch.empty(nseq * T, **f32)
+    row_label = torch.empty(nseq * T, dtype=torch.int32, device=dev)
+    row_weight = torch.empty(nseq * T, **f32)
+    nll = torch.empty(1, **f32) if want_nll else None
+    _lib.check(lib.pgica_lmhead_logprob_fwd(_p(hidden), _p(weight), _p(labels), _p(mask_c), kind, nseq, T, d, V,
+                                            1 if length_normalize else 0, _p(seq_logp), _p(lse), _p(ztgt),
+                                            _p(row_label), _p(row_weight), _p(nll), _p(ws), need.value, _stream()))
+    return seq_logp, lse, ztgt, row_label, row_weight, nll
+
+
+def lmhead_logprob_bwd(hidden, weight, row_label, row_weight, lse, grad_seq, length_normalize=False,
+                       need_dhidden=True, need_dweight=True, dhidden_dtype=torch.bfloat16,
+                       dweight_dtype=torch.float32):
+    _need_cuda(hidden, weight, grad_seq)
+    lib = _lib.load()
+    nseq, T, d = hidden.shape
+    V = weight.shape[0]
+    dev = hidden.device
+    dh = torch.empty(nseq, T, d, dtype=dhidden_dtype, device=dev) if need_dhidden else None
+    dw = torch.empty(V, d, dtype=dweight_dtype, device=dev) if need_dweight else None
+    ws = _ws(nseq * T * 4, dev)
+    grad_seq = grad_seq.contiguous().float()
+    _lib.check(lib.pgica_lmhead_logprob_bwd(_p(hidden), _p(weight), _p(row_label), _p(row_weight), _p(lse),
+                                            _p(grad_seq), nseq, T, d, V, 1 if length_normalize else 0, _p(dh),
+                                            1 if dhidden_dtype == torch.bfloat16 else 0, _p(dw),
+                                            1 if dweight_dtype == torch.bfloat16 else 0, _p(ws), ws.numel(),
+                                            _stream()))
+    return dh, dw
+
+
+def dpo_loss_fwd(pc, pr, rc=None, rr=None, beta=0.1, label_smoothing=0.0, n_global=None):
+    _need_cuda(pc, pr, rc, rr)
+    lib = _lib.load()
+    n = pc.numel()
+    f32 = dict(dtype=torch.float32, device=pc.device)
+    loss = torch.empty((), **f32)
+    metrics = torch.empty(5, **f32)
+    dpc = torch.empty(n, **f32)
+    _lib.check(lib.pgica_dpo_loss_fwd(_p(pc), _p(pr), _p(rc), _p(rr), n, int(n_global or n), float(beta),
+                                      float(label_smoothing), _p(loss), _p(metrics), _p(dpc), _stream()))
+    return loss, metrics, dpc
+
+
+def scale_by_scalar(a, scalar, mult=1.0):
+    lib = _lib.load()
+    out = torch.empty_like(a)
+    _lib.check(lib.pgica_scale_by_scalar(_p(a), _p(scalar), float(mult), a.numel(), _p(out), _stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------------------- Stage-1 head
+def ntxent_fwd(a, b, inv_tau, diag_offset=0):
+    _need_cuda(a, b)
+    lib = _lib.load()
+    ra, dim = a.shape
+    rb = b.shape[0]
+    need = ctypes.c_size_t(0)
+    _lib.check(lib.pgica_ntxent_workspace_bytes(ra, rb, dim, ctypes.byref(need)))
+    ws = _ws(need.value, a.device)
+    f32 = dict(dtype=torch.float32, device=a.device)
+    lse_row, diag, lse_col = torch.empty(ra, **f32), torch.empty(ra, **f32), torch.empty(rb, **f32)
+    _lib.check(lib.pgica_ntxent_fwd(_p(a), _p(b), ra, rb, dim, float(inv_tau), int(diag_offset), _p(lse_row),
+                                    _p(diag), _p(lse_col), _p(ws), need.value, _stream()))
+    return lse_row, diag, lse_col
+
+
+def ntxent_loss(lse_row, diag, lse_col_owned, inv_denom):
+    lib = _lib.load()
+    loss = torch.empty((), dtype=torch.float32, device=lse_row.device)
+    _lib.check(lib.pgica_ntxent_loss(_p(lse_row), _p(diag), _p(lse_col_owned), lse_row.numel(), float(inv_denom),
+                                     _p(loss), _stream()))
+    return loss
+
+
+def lse_combine(parts):
+    """parts fp32 [nparts, n] -> logsumexp over dim 0."""
+    lib = _lib.load()
+    parts = parts.contiguous()
+    out = torch.empty(parts.shape[1], dtype=torch.float32, device=parts.device)
+    _lib.check(lib.pgica_lse_combine(_p(parts), parts.shape[0], parts.shape[1], _p(out), _stream()))
+    return out
+
+
+def ntxent_bwd(a, b, inv_tau, diag_offset, lse_row, lse_col, grad_loss, grad_mult, need_da=True, need_db=True,
+               da_dtype=torch.float32, db_dtype=torch.float32):
+    _need_cuda(a, b, grad_loss)
+    lib = _lib.load()
+    ra, dim = a.shape
+    rb = b.shape[0]
+    need = ctypes.c_size_t(0)
+    _lib.check(lib.pgica_ntxent_workspace_bytes(ra, rb, dim, ctypes.byref(need)))
+    ws = _ws(need.value, a.device)
+    da = torch.empty(ra, dim, dtype=da_dtype, device=a.device) if need_da else None
+    db = torch.empty(rb, dim, dtype=db_dtype, device=a.device) if need_db else None
+    grad_loss = grad_loss.reshape(1).float().contiguous()
+    _lib.check(lib.pgica_ntxent_bwd(_p(a), _p(b), ra, rb, dim, float(inv_tau), int(diag_offset), _p(lse_row),
+                                    _p(lse_col), _p(grad_loss), float(grad_mult), _p(da),
+                                    1 if da_dtype == torch.bfloat16 else 0, _p(db),
+                                    1 if db_dtype == torch.bfloat16 else 0, _p(ws), need.value, _stream()))
+    return da, db
+
+
+def rownorm_fwd(x, eps=1e-12):
+    _need_cuda(x)
+    lib = _lib.load()
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    x = x.contiguous()
+    rows, dim = x.shape
+    y = torch.empty(rows, dim, dtype=torch.bfloat16, device=x.device)
+    inv = torch.empty(rows, dtype=torch.float32, device=x.device)
+    _lib.check(lib.pgica_rownorm_fwd(_p(x), 1 if x.dtype == torch.bfloat16 else 0, rows, dim, float(eps), _p(y),
+                                     _p(inv), _stream()))
+    return y, inv, x
+
+
+def rownorm_bwd(x, inv_norm, g):
+    lib = _lib.load()
+    g = g.contiguous()
+    rows, dim = x.shape
+    dx = torch.empty(rows, dim, dtype=torch.float32, device=x.device)
+    _lib.check(lib.pgica_rownorm_bwd(_p(x), 1 if x.dtype == torch.bfloat16 else 0, _p(inv_norm), _p(g),
+                                     1 if g.dtype == torch.bfloat16 else 0, rows, dim, _p(dx), _stream()))
+    return dx
+
+
+# ----------------------------------------------------------------------------------------- logits path
+def prep_rows(labels, mask, vocab):
+    _need_cuda(labels, mask)
+    lib = _lib.load()
+    nseq, T = labels.shape
+    kind, mask_c = mask_kind(mask)
+    labels = labels.contiguous()
+    if labels.dtype != torch.int64:
+        labels = labels.long()
+    row_label = torch.empty(nseq * T, dtype=torch.int32, device=labels.device)
+    row_weight = torch.empty(nseq * T, dtype=torch.float32, device=labels.device)
+    _lib.check(lib.pgica_prep_rows(_p(labels), _p(mask_c), kind, nseq, T, int(vocab), _p(row_label), _p(row_weight),
+                                   _stream()))
+    return row_label, row_weight
+
+
+def seq_reduce(lse, ztgt, row_weight, nseq, T, length_normalize=False):
+    lib = _lib.load()
+    out = torch.empty(nseq, dtype=torch.float32, device=lse.device)
+    _lib.check(lib.pgica_seq_reduce(_p(lse), _p(ztgt), _p(row_weight), nseq, T, 1 if length_normalize else 0, _p(out),
+                                    None, _stream()))
+    return out
+
+
+def row_coef(grad_seq, row_weight, nseq, T, length_normalize=False, sign=1.0):
+    lib = _lib.load()
+    coef = torch.empty(nseq * T, dtype=torch.float32, device=row_weight.device)
+    grad_seq = grad_seq.contiguous().float()
+    _lib.check(lib.pgica_row_coef(_p(grad_seq), _p(row_weight), nseq, T, 1 if length_normalize else 0, float(sign),
+                                  _p(coef), _stream()))
+    return coef
+
+
+def logits_lse(logits, row_label):
+    _need_cuda(logits)
+    lib = _lib.load()
+    nseq, T, V = logits.shape
+    lse = torch.empty(nseq * T, dtype=torch.float32, device=logits.device)
+    ztgt = torch.empty(nseq * T, dtype=torch.float32, device=logits.device)
+    _lib.check(lib.pgica_logits_lse(_p(logits), 1 if logits.dtype == torch.bfloat16 else 0, _p(row_label), nseq, T, V,
+                                    _p(lse), _p(ztgt), _stream()))
+    return lse, ztgt
+
+
+def logits_grad(logits, row_label, lse, coef):
+    lib = _lib.load()
+    nseq, T, V = logits.shape
+    dlogits = torch.empty_like(logits)
+    _lib.check(lib.pgica_logits_grad(_p(logits), 1 if logits.dtype == torch.bfloat16 else 0, _p(row_label), _p(lse),
+                                     _p(coef), nseq, T, V, _p(dlogits), _stream()))
+    return dlogits
