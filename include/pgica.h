@@ -69,6 +69,12 @@ int pgica_gemm_lse(const void* a, const void* b, int64_t rows, int64_t cols, int
                    const int32_t* labels, int64_t diag_offset, float* lse, float* tgt, void* workspace,
                    size_t workspace_bytes, void* stream);
 
+/* Dense scaled similarity sim[i][j] = scale*<a_i, b_j> (fp32 [rows][cols]) for retrieval-style scoring —
+ * TemperatureScaledSimilarity.forward, pkg/models/components.py:61-83 after normalisation — plus the row
+ * log-sum-exp.  Same kernel as pgica_gemm_lse with the store epilogue enabled; workspace as for gemm_lse. */
+int pgica_similarity(const void* a, const void* b, int64_t rows, int64_t cols, int64_t k, float scale, float* sim,
+                     float* lse, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Debug / self-test: one CTA, one 128 x n x k tcgen05 product, D written to `d` (fp32 [128][n]).
  *   b_mn_major = 0: b is [n][k] (K-major);  1: b is [k][n] (MN-major, the layout the backward's second

@@ -1,1 +1,22 @@
-"""B200-native fused alignment loss heads (NT-Xent + DPO)."""
+"""B200-native (sm_100a) fused alignment loss heads: Stage-1 NT-Xent and Stage-2 DPO.
+
+Drop-in for the loss-head hot path of A-SHOJAEI/preference-guided-image-captioning-alignment:
+
+    losses.ContrastiveLoss / losses.PreferenceLoss         <- pkg/models/model.py:957-1085 (what the trainer uses)
+    components.ContrastiveLoss / DPOPreferenceLoss /
+        TemperatureScaledSimilarity / compute_sequence_logprobs   <- pkg/models/components.py
+    components.FusedDPOHead / lmhead_sequence_logprobs      hidden-state level: logits never materialised
+    distributed.global_ntxent / GlobalContrastiveLoss       NT-Xent with negatives from every rank
+    install()                                               rebinds the reference's names to the above
+
+Everything computes in hand-written CUDA (csrc/, exported through the C ABI in include/pgica.h).  There is no
+CPU or PyTorch fallback: on a machine without a B200 the ops raise.
+"""
+from . import _lib  # noqa: F401  (ctypes binding; the library itself is loaded on first use)
+from .components import (DPOPreferenceLoss, FusedDPOHead, TemperatureScaledSimilarity,  # noqa: F401
+                         compute_sequence_logprobs, lmhead_sequence_logprobs)
+from .install import install, uninstall  # noqa: F401
+from .losses import ContrastiveLoss, LazyLogits, PreferenceLoss  # noqa: F401
+
+__all__ = ["ContrastiveLoss", "PreferenceLoss", "DPOPreferenceLoss", "FusedDPOHead", "TemperatureScaledSimilarity",
+           "compute_sequence_logprobs", "lmhead_sequence_logprobs", "LazyLogits", "install", "uninstall"]

@@ -1,0 +1,157 @@
+"""Mirror of the reference's stand-alone loss components (pkg/models/components.py): same class / function
+names, constructor arguments, forward signatures and return types, computed by the fused sm_100a kernels.
+
+    TemperatureScaledSimilarity   components.py:24-83
+    ContrastiveLoss               components.py:86-145   (normalises inside, clamps tau to [0.1, 2.0])
+    DPOPreferenceLoss             components.py:148-249  -> (loss, metrics dict)
+    compute_sequence_logprobs     components.py:321-362  (masked SUM of target log-probs)
+
+plus the hidden-state-level entry points that avoid materialising logits altogether
+(`lmhead_sequence_logprobs`, `FusedDPOHead`).
+"""
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .losses import LazyLogits
+
+_METRIC_KEYS = ("dpo_loss", "reward_margin", "reward_accuracy", "policy_chosen_logprob", "policy_rejected_logprob")
+
+
+class TemperatureScaledSimilarity(nn.Module):
+    """normalize(v) · normalize(t)ᵀ / clamp(τ, min_temp, max_temp) as a dense (B, B) matrix.
+
+    The fused ContrastiveLoss below never forms this matrix; this module exists for callers that want it
+    (retrieval-style scoring).  τ is a buffer, or a Parameter when `learnable` — like the reference, so it
+    shows up in state_dict() under the same key."""
+
+    def __init__(self, temperature: float = 0.5, learnable: bool = False, min_temp: float = 0.1,
+                 max_temp: float = 2.0):
+        super().__init__()
+        self.min_temp = min_temp
+        self.max_temp = max_temp
+        if learnable:
+            self.temperature = nn.Parameter(torch.tensor(temperature))
+        else:
+            self.register_buffer("temperature", torch.tensor(temperature))
+
+    def effective_temperature(self) -> float:
+        return float(min(max(float(self.temperature), self.min_temp), self.max_temp))
+
+    def forward(self, vision_embeds: torch.Tensor, text_embeds: torch.Tensor) -> torch.Tensor:
+        from . import functional as F
+        if torch.is_grad_enabled() and (vision_embeds.requires_grad or text_embeds.requires_grad
+                                        or self.temperature.requires_grad):
+            raise NotImplementedError(
+                "TemperatureScaledSimilarity returns the dense similarity matrix for scoring only; for training use "
+                "ContrastiveLoss, whose fused kernels never materialise it")
+        v, _ = ops.l2_normalize(vision_embeds, 1e-12)
+        t, _ = ops.l2_normalize(text_embeds, 1e-12)
+        return F.similarity(v, t, 1.0 / self.effective_temperature())
+
+
+class ContrastiveLoss(nn.Module):
+    """NT-Xent / InfoNCE, components flavour (components.py:86-145): L2-normalise both inputs (eps 1e-12),
+    clamp τ to [0.1, 2.0], symmetric cross-entropy with reduction 'mean' or 'sum', halved."""
+
+    def __init__(self, temperature: float = 0.5, reduction: str = "mean"):
+        super().__init__()
+        self.similarity = TemperatureScaledSimilarity(temperature=temperature)
+        self.reduction = reduction
+
+    def forward(self, vision_embeds: torch.Tensor, text_embeds: torch.Tensor) -> torch.Tensor:
+        if self.reduction not in ("mean", "sum"):
+            # F.cross_entropy would raise on an unknown reduction string as well
+            raise ValueError(f"{self.reduction} is not a valid value for reduction")
+        v, _ = ops.l2_normalize(vision_embeds, 1e-12)
+        t, _ = ops.l2_normalize(text_embeds, 1e-12)
+        loss, _, _ = ops.ntxent(v, t, 1.0 / self.similarity.effective_temperature(), self.reduction == "mean")
+        return loss
+
+
+class DPOPreferenceLoss(nn.Module):
+    """Direct Preference Optimisation loss on per-sequence log-probs (components.py:148-249)."""
+
+    def __init__(self, beta: float = 0.1, reference_free: bool = False, label_smoothing: float = 0.0):
+        super().__init__()
+        self.beta = beta
+        self.reference_free = reference_free
+        self.label_smoothing = label_smoothing
+
+    def forward(self, policy_chosen_logprobs: torch.Tensor, policy_rejected_logprobs: torch.Tensor,
+                reference_chosen_logprobs: Optional[torch.Tensor] = None,
+                reference_rejected_logprobs: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, dict]:
+        loss, metrics = self.forward_tensors(policy_chosen_logprobs, policy_rejected_logprobs,
+                                             reference_chosen_logprobs, reference_rejected_logprobs)
+        vals = metrics.tolist()  # ONE device->host read (the reference does five .item() calls, :241-247)
+        return loss, dict(zip(_METRIC_KEYS, vals))
+
+    def forward_tensors(self, pc, pr, rc=None, rr=None, n_global: Optional[int] = None):
+        """Same computation, metrics left on the device as a (5,) tensor (no host sync)."""
+        if self.reference_free or rc is None:
+            rc = rr = None
+        loss, metrics, _ = ops.dpo_loss(pc, pr, rc, rr, float(self.beta), float(self.label_smoothing),
+                                        int(n_global or pc.numel()))
+        return loss, metrics
+
+
+def compute_sequence_logprobs(logits, labels: torch.Tensor,
+                              attention_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(B, T, V) logits (or LazyLogits), (B, T) labels, optional (B, T) mask -> (B,) masked sum of
+    log p(labels[t+1] | position t)  (components.py:321-362)."""
+    if isinstance(logits, LazyLogits):
+        return logits.seq_logprobs(labels, attention_mask, False)
+    return ops.logits_seq_logprob(logits, labels, attention_mask, False)[0]
+
+
+def lmhead_sequence_logprobs(hidden: torch.Tensor, weight: torch.Tensor, labels: torch.Tensor,
+                             attention_mask: Optional[torch.Tensor] = None,
+                             length_normalize: bool = False) -> torch.Tensor:
+    """compute_sequence_logprobs(lm_head(hidden), labels, mask) without the logits: hidden (B, T, d), tied
+    LM-head / wte weight (V, d).  Differentiable w.r.t. hidden and weight."""
+    return ops.lmhead_seq_logprob(hidden, weight, labels, attention_mask, length_normalize)[0]
+
+
+class FusedDPOHead(nn.Module):
+    """The whole Stage-2 head at the hidden-state level: policy log-probs (with grad) for chosen and rejected,
+    frozen-reference log-probs (no grad), DPO loss and metrics.  Equivalent to
+
+        DPOPreferenceLoss(beta, ...)(csl(lm_head(hc)), csl(lm_head(hr)), csl(ref_lm_head(rhc)), csl(ref_lm_head(rhr)))
+
+    with csl = compute_sequence_logprobs, and logits never materialised."""
+
+    def __init__(self, beta: float = 0.1, reference_free: bool = False, label_smoothing: float = 0.0,
+                 length_normalize: bool = False):
+        super().__init__()
+        self.loss = DPOPreferenceLoss(beta, reference_free, label_smoothing)
+        self.length_normalize = length_normalize
+
+    def forward(self, hidden_chosen, hidden_rejected, weight, labels_chosen, labels_rejected, mask_chosen=None,
+                mask_rejected=None, ref_hidden_chosen=None, ref_hidden_rejected=None, ref_weight=None,
+                n_global: Optional[int] = None):
+        ln = self.length_normalize
+        B = hidden_chosen.shape[0]
+        same_shape = hidden_chosen.shape == hidden_rejected.shape and (mask_chosen is None) == (mask_rejected is None)
+        if same_shape:
+            # one launch over chosen ++ rejected rows: twice the row blocks per wave, one dW accumulation
+            hidden = torch.cat([hidden_chosen, hidden_rejected], 0)
+            labels = torch.cat([labels_chosen, labels_rejected], 0)
+            mask = None if mask_chosen is None else torch.cat([mask_chosen, mask_rejected], 0)
+            seq = lmhead_sequence_logprobs(hidden, weight, labels, mask, ln)
+            pc, pr = seq[:B], seq[B:]
+        else:
+            pc = lmhead_sequence_logprobs(hidden_chosen, weight, labels_chosen, mask_chosen, ln)
+            pr = lmhead_sequence_logprobs(hidden_rejected, weight, labels_rejected, mask_rejected, ln)
+        rc = rr = None
+        if ref_weight is not None and not self.loss.reference_free:
+            with torch.no_grad():
+                if same_shape and ref_hidden_chosen.shape == ref_hidden_rejected.shape:
+                    rseq = lmhead_sequence_logprobs(torch.cat([ref_hidden_chosen, ref_hidden_rejected], 0), ref_weight,
+                                                    labels, mask, ln)
+                    rc, rr = rseq[:B], rseq[B:]
+                else:
+                    rc = lmhead_sequence_logprobs(ref_hidden_chosen, ref_weight, labels_chosen, mask_chosen, ln)
+                    rr = lmhead_sequence_logprobs(ref_hidden_rejected, ref_weight, labels_rejected, mask_rejected, ln)
+        return self.loss.forward_tensors(pc, pr, rc, rr, n_global)

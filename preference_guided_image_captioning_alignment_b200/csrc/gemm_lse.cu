@@ -37,6 +37,7 @@ struct GemmLseParams {
   float* part_max;  // [slots][rows_pad]  running max of scale*log2e*z
   float* part_sum;  // [slots][rows_pad]  sum of exp2(. - max)
   float* part_tgt;  // [slots][rows_pad]  scale*z at the label column, -inf if not seen in this piece
+  float* z_out;     // optional dense [rows][cols] copy of scale*z (similarity-matrix API only)
 };
 
 constexpr size_t kSmemBytes = 1024 /*align slack*/ + kStages * (kABytes + kBBytes) + 256 /*barriers*/;
@@ -188,6 +189,15 @@ gemm_lse_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           for (int j = 0; j < 32; ++j)
             if (n0 + ch * 32 + j >= p.cols) v[j] = -INFINITY;
         }
+        if (p.z_out != nullptr) {
+          const int row = m_blk * kBlockM + row_in_blk;
+          if (row < p.rows) {
+            float* dst = p.z_out + static_cast<size_t>(row) * p.cols + n0 + ch * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + ch * 32 + j < p.cols) dst[j] = v[j] * p.scale;
+          }
+        }
         float cm = v[0];
 #pragma unroll
         for (int j = 1; j < 32; ++j) cm = fmaxf(cm, v[j]);
@@ -286,9 +296,9 @@ int pgica_gemm_lse_workspace_bytes(int64_t rows, int64_t cols, int64_t k, size_t
   return pgica::plan(rows, cols, k, &p, &grid, bytes_host);
 }
 
-int pgica_gemm_lse(const void* a, const void* b, int64_t rows, int64_t cols, int64_t k, float scale,
-                   const int32_t* labels, int64_t diag_offset, float* lse, float* tgt, void* workspace,
-                   size_t workspace_bytes, void* stream) {
+static int gemm_lse_impl(const void* a, const void* b, int64_t rows, int64_t cols, int64_t k, float scale,
+                         const int32_t* labels, int64_t diag_offset, float* lse, float* tgt, float* z_out,
+                         void* workspace, size_t workspace_bytes, void* stream) {
   using namespace pgica;
   int rc = pgica_device_check();
   if (rc != PGICA_OK) return rc;
@@ -310,6 +320,7 @@ int pgica_gemm_lse(const void* a, const void* b, int64_t rows, int64_t cols, int
   p.scale = scale;
   p.labels = labels;
   p.diag_offset = (int)diag_offset;
+  p.z_out = z_out;
 
   CUtensorMap tm_a, tm_b;
   rc = make_tmap_bf16(&tm_a, a, rows, k, k, kBlockM);
@@ -324,6 +335,19 @@ int pgica_gemm_lse(const void* a, const void* b, int64_t rows, int64_t cols, int
   lse_merge_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, st>>>(p, lse, tgt);
   PGICA_CUDA_OK(cudaGetLastError());
   return PGICA_OK;
+}
+
+int pgica_gemm_lse(const void* a, const void* b, int64_t rows, int64_t cols, int64_t k, float scale,
+                   const int32_t* labels, int64_t diag_offset, float* lse, float* tgt, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  return gemm_lse_impl(a, b, rows, cols, k, scale, labels, diag_offset, lse, tgt, nullptr, workspace,
+                       workspace_bytes, stream);
+}
+
+int pgica_similarity(const void* a, const void* b, int64_t rows, int64_t cols, int64_t k, float scale, float* sim,
+                     float* lse, void* workspace, size_t workspace_bytes, void* stream) {
+  PGICA_REQUIRE(sim && lse, "similarity: null output");
+  return gemm_lse_impl(a, b, rows, cols, k, scale, nullptr, 0, lse, nullptr, sim, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

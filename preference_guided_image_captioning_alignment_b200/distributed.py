@@ -1,0 +1,141 @@
+"""Multi-GPU forms of the two heads — only where they shard naturally.
+
+NT-Xent with global negatives: rank r owns rows [r*b, (r+1)*b) of both embedding matrices.
+    forward : all-gather text rows -> local (b x B) slice on the tensor cores -> row LSE is complete, column
+              LSE is a partial over b rows -> all-gather the W partial vectors (B floats each) and merge ->
+              local loss terms -> all-reduce of one scalar.
+    backward: dA_r is final locally; dB is a (B x D) partial -> reduce-scatter to the owners.
+    The result equals the reference module applied to the concatenated global batch on one device (the
+    reference itself, under DDP, only ever sees local negatives).  Gradients are those of ONE copy of the
+    global loss (no extra 1/world factor): averaging across replicas is the caller's / DDP's business.
+
+DPO: preference pairs are independent -> shard pairs, replicate W; the loss is a mean over the GLOBAL batch
+    (1/B_global inside the kernel), scalars are all-reduced, and dW is all-reduced by `allreduce_dweight`
+    (stand-alone use) or by DDP's bucket reducer when the head sits inside a DDP-wrapped model.
+
+The collective plumbing is written against a small `compute` interface so that the CPU test-suite can drive
+it under gloo with the oracle standing in for the kernels; the product always uses CudaCompute.
+"""
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import functional as F
+
+
+class CudaCompute:
+    """The kernels (functional.py -> C ABI).  No CPU implementation exists."""
+
+    name = "cuda"
+
+    def to_operand(self, x):
+        return F.as_bf16(x)
+
+    def ntxent_fwd(self, a, b_all, inv_tau, diag_offset):
+        return F.ntxent_fwd(a, b_all, inv_tau, diag_offset)
+
+    def lse_combine(self, parts):
+        return F.lse_combine(parts)
+
+    def ntxent_loss(self, lse_row, diag, lse_col_owned, inv_denom):
+        return F.ntxent_loss(lse_row, diag, lse_col_owned, inv_denom)
+
+    def ntxent_bwd(self, a, b_all, inv_tau, diag_offset, lse_row, lse_col, grad_loss, mult):
+        return F.ntxent_bwd(a, b_all, inv_tau, diag_offset, lse_row, lse_col, grad_loss, mult,
+                            da_dtype=torch.float32, db_dtype=torch.float32)
+
+
+def _world(group):
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+def all_gather_rows(x: torch.Tensor, group=None) -> torch.Tensor:
+    """(b, D) per rank -> (W*b, D), rank-major."""
+    world, _ = _world(group)
+    out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+    return out
+
+
+def reduce_scatter_rows(x: torch.Tensor, group=None) -> torch.Tensor:
+    """(W*b, D) partial sums per rank -> (b, D) owned rows, summed over ranks."""
+    world, rank = _world(group)
+    b = x.shape[0] // world
+    out = torch.empty((b,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    if dist.get_backend(group) == "gloo":  # gloo has no reduce_scatter: all-reduce and keep the owned slice
+        full = x.contiguous().clone()
+        dist.all_reduce(full, group=group)
+        out.copy_(full[rank * b:(rank + 1) * b])
+    else:
+        dist.reduce_scatter_tensor(out, x.contiguous(), group=group)
+    return out
+
+
+class _GlobalNTXent(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, inv_tau, reduce_mean, group, compute):
+        world, rank = _world(group)
+        nb = a.shape[0]
+        B = nb * world
+        a_op = compute.to_operand(a)
+        b_all = all_gather_rows(compute.to_operand(b), group)
+        off = rank * nb
+        lse_row, diag, lse_col_part = compute.ntxent_fwd(a_op, b_all, inv_tau, off)
+        parts = all_gather_rows(lse_col_part.reshape(1, B), group)  # (W, B)
+        lse_col = compute.lse_combine(parts)
+        loss = compute.ntxent_loss(lse_row, diag, lse_col[off:off + nb].contiguous(), (1.0 / B) if reduce_mean else 1.0)
+        loss = loss.clone()
+        dist.all_reduce(loss, group=group)
+        ctx.save_for_backward(a_op, b_all, lse_row, lse_col)
+        ctx.meta = (inv_tau, off, (1.0 / (2.0 * B)) if reduce_mean else 0.5, group, compute, a.dtype, b.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        a_op, b_all, lse_row, lse_col = ctx.saved_tensors
+        inv_tau, off, mult, group, compute, a_dtype, b_dtype = ctx.meta
+        da, db_part = compute.ntxent_bwd(a_op, b_all, inv_tau, off, lse_row, lse_col, grad_loss.contiguous(), mult)
+        db = reduce_scatter_rows(db_part, group)
+        return da.to(a_dtype), db.to(b_dtype), None, None, None, None
+
+
+def global_ntxent(a: torch.Tensor, b: torch.Tensor, temperature: float, reduce_mean: bool = True, group=None,
+                  compute=None) -> torch.Tensor:
+    """NT-Xent over the GLOBAL batch; a, b are this rank's (b, D) rows, used as given (normalise first if needed).
+    Returns the global loss (identical on every rank)."""
+    return _GlobalNTXent.apply(a, b, 1.0 / float(temperature), reduce_mean, group, compute or CudaCompute())
+
+
+class GlobalContrastiveLoss(torch.nn.Module):
+    """ContrastiveLoss (pkg/models/model.py:957-1000 semantics) with negatives from every rank."""
+
+    def __init__(self, temperature: float = 0.07, group=None, compute=None):
+        super().__init__()
+        self.temperature = temperature
+        self.group = group
+        self.compute = compute
+
+    def forward(self, image_embeddings, text_embeddings):
+        return global_ntxent(image_embeddings, text_embeddings, self.temperature, True, self.group, self.compute)
+
+
+# ------------------------------------------------------------------------------------------------ DPO
+def shard_pairs(n_global: int, rank: int, world: int):
+    """Contiguous, balanced slice of the global pair batch owned by `rank`."""
+    base, rem = divmod(n_global, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def allreduce_scalars(loss: torch.Tensor, metrics: Optional[torch.Tensor], group=None):
+    """Local sums / B_global -> global mean (the kernel already divides by n_global)."""
+    packed = torch.cat([loss.detach().reshape(1), metrics.detach()]) if metrics is not None else loss.detach().reshape(1)
+    dist.all_reduce(packed, group=group)
+    return packed[0], (packed[1:] if metrics is not None else None)
+
+
+def allreduce_dweight(dweight: torch.Tensor, group=None, async_op: bool = False):
+    """Sum the LM-head weight gradient over the data-parallel ranks (206 MB fp32 for GPT-2 Medium).
+    Skip inside a DDP-wrapped model: DDP's reducer already owns the tied wte / lm_head Parameter."""
+    return dist.all_reduce(dweight, group=group, async_op=async_op)

@@ -74,6 +74,22 @@ def gemm_lse(a, b, scale=1.0, labels=None, diag_offset=0, want_tgt=True):
     return lse, tgt
 
 
+def similarity(a, b, scale=1.0):
+    """Dense fp32 (rows, cols) matrix scale*<a_i, b_j> (scoring API; the loss path never calls this)."""
+    _need_cuda(a, b)
+    lib = _lib.load()
+    rows, k = a.shape
+    cols = b.shape[0]
+    need = ctypes.c_size_t(0)
+    _lib.check(lib.pgica_gemm_lse_workspace_bytes(rows, cols, k, ctypes.byref(need)))
+    ws = _ws(need.value, a.device)
+    sim = torch.empty(rows, cols, dtype=torch.float32, device=a.device)
+    lse = torch.empty(rows, dtype=torch.float32, device=a.device)
+    _lib.check(lib.pgica_similarity(_p(a), _p(b), rows, cols, k, float(scale), _p(sim), _p(lse), _p(ws), need.value,
+                                    _stream()))
+    return sim
+
+
 # ----------------------------------------------------------------------------------------- K2/K4 core
 def softmax_grad_gemm(x, y, scale=1.0, row=None, col=None, out_dtype=torch.float32):
     """out = G(x y^T) y with G built from row stats (lse, coef, tgt) and/or column stats (see pgica.h)."""

@@ -1,0 +1,273 @@
+"""torch.library registration of the fused loss-head ops (namespace `pgica`).
+
+Each op is a thin shim over functional.py (-> C ABI -> CUDA kernels); autograd formulas call the backward
+kernels.  Fake (meta) implementations make the ops traceable; there is deliberately no CPU implementation:
+calling an op on CPU tensors raises.
+"""
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import functional as F
+
+_lib_def = torch.library.Library("pgica", "DEF")  # noqa: F841  (keeps the namespace alive)
+
+
+def _f32(n, like):
+    return torch.empty(n, dtype=torch.float32, device=like.device)
+
+
+def _grad_dtype(t):
+    return torch.bfloat16 if t.dtype == torch.bfloat16 else torch.float32
+
+
+# ============================================================================================ NT-Xent
+@torch.library.custom_op("pgica::ntxent", mutates_args=())
+def ntxent(a: Tensor, b: Tensor, inv_tau: float, reduce_mean: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """Symmetric NT-Xent on (B, D) x (B, D) embeddings as given (no normalisation here).
+    Returns (loss[], lse_row[B], lse_col[B])."""
+    if a.shape != b.shape or a.dim() != 2:
+        raise ValueError(f"ntxent expects two (B, D) tensors of equal shape, got {tuple(a.shape)} {tuple(b.shape)}")
+    ab, bb = F.as_bf16(a), F.as_bf16(b)
+    lse_row, diag, lse_col = F.ntxent_fwd(ab, bb, inv_tau, 0)
+    n = a.shape[0]
+    loss = F.ntxent_loss(lse_row, diag, lse_col, 1.0 / n if reduce_mean else 1.0)
+    return loss, lse_row, lse_col
+
+
+@ntxent.register_fake
+def _(a, b, inv_tau, reduce_mean):
+    return a.new_empty((), dtype=torch.float32), _f32(a.shape[0], a), _f32(b.shape[0], a)
+
+
+@torch.library.custom_op("pgica::ntxent_bwd", mutates_args=())
+def ntxent_bwd(a: Tensor, b: Tensor, lse_row: Tensor, lse_col: Tensor, grad_loss: Tensor, inv_tau: float,
+               reduce_mean: bool) -> Tuple[Tensor, Tensor]:
+    ab, bb = F.as_bf16(a), F.as_bf16(b)
+    n = a.shape[0]
+    mult = 1.0 / (2.0 * n) if reduce_mean else 0.5
+    da, db = F.ntxent_bwd(ab, bb, inv_tau, 0, lse_row, lse_col, grad_loss, mult, da_dtype=_grad_dtype(a),
+                          db_dtype=_grad_dtype(b))
+    return da, db
+
+
+@ntxent_bwd.register_fake
+def _(a, b, lse_row, lse_col, grad_loss, inv_tau, reduce_mean):
+    return torch.empty_like(a, dtype=_grad_dtype(a)), torch.empty_like(b, dtype=_grad_dtype(b))
+
+
+def _ntxent_setup(ctx, inputs, output):
+    a, b, inv_tau, reduce_mean = inputs
+    _, lse_row, lse_col = output
+    ctx.save_for_backward(a, b, lse_row, lse_col)
+    ctx.inv_tau, ctx.reduce_mean = inv_tau, reduce_mean
+
+
+def _ntxent_backward(ctx, g_loss, g_lr, g_lc):
+    a, b, lse_row, lse_col = ctx.saved_tensors
+    da, db = ntxent_bwd(a, b, lse_row, lse_col, g_loss.contiguous(), ctx.inv_tau, ctx.reduce_mean)
+    return da.to(a.dtype), db.to(b.dtype), None, None
+
+
+ntxent.register_autograd(_ntxent_backward, setup_context=_ntxent_setup)
+
+
+# ------------------------------------------------------------------------------------- L2 normalisation
+@torch.library.custom_op("pgica::l2_normalize", mutates_args=())
+def l2_normalize(x: Tensor, eps: float) -> Tuple[Tensor, Tensor]:
+    """F.normalize(x, dim=-1) -> (bf16 unit rows, 1/max(||x||, eps))."""
+    y, inv, _ = F.rownorm_fwd(x, eps)
+    return y, inv
+
+
+@l2_normalize.register_fake
+def _(x, eps):
+    return torch.empty_like(x, dtype=torch.bfloat16), _f32(x.shape[0], x)
+
+
+@torch.library.custom_op("pgica::l2_normalize_bwd", mutates_args=())
+def l2_normalize_bwd(x: Tensor, inv_norm: Tensor, g: Tensor) -> Tensor:
+    xx = x if x.dtype in (torch.float32, torch.bfloat16) else x.float()
+    gg = g if g.dtype in (torch.float32, torch.bfloat16) else g.float()
+    return F.rownorm_bwd(xx.contiguous(), inv_norm, gg)
+
+
+@l2_normalize_bwd.register_fake
+def _(x, inv_norm, g):
+    return torch.empty_like(x, dtype=torch.float32)
+
+
+def _l2_setup(ctx, inputs, output):
+    x, _ = inputs
+    ctx.save_for_backward(x, output[1])
+
+
+def _l2_backward(ctx, g_y, g_inv):
+    x, inv = ctx.saved_tensors
+    return l2_normalize_bwd(x, inv, g_y).to(x.dtype), None
+
+
+l2_normalize.register_autograd(_l2_backward, setup_context=_l2_setup)
+
+
+# ============================================================================================ LM head
+@torch.library.custom_op("pgica::lmhead_seq_logprob", mutates_args=())
+def lmhead_seq_logprob(hidden: Tensor, weight: Tensor, labels: Tensor, mask: Optional[Tensor],
+                       length_normalize: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """hidden (nseq, T, d), weight (V, d), labels (nseq, T) -> (seq_logp[nseq], lse[nseq*T], ztgt[nseq*T],
+    row_label[nseq*T] int32, row_weight[nseq*T]).  The (nseq, T, V) logits are never formed."""
+    if hidden.dim() != 3 or weight.dim() != 2 or hidden.shape[-1] != weight.shape[-1]:
+        raise ValueError("lmhead_seq_logprob: hidden (nseq,T,d) and weight (V,d) expected")
+    if tuple(labels.shape) != tuple(hidden.shape[:2]):
+        raise ValueError("lmhead_seq_logprob: labels must be (nseq, T)")
+    hb, wb = F.as_bf16(hidden), F.as_bf16(weight)
+    seq, lse, ztgt, rl, rw, _ = F.lmhead_logprob_fwd(hb, wb, labels, mask, length_normalize)
+    return seq, lse, ztgt, rl, rw
+
+
+@lmhead_seq_logprob.register_fake
+def _(hidden, weight, labels, mask, length_normalize):
+    n = hidden.shape[0] * hidden.shape[1]
+    return (_f32(hidden.shape[0], hidden), _f32(n, hidden), _f32(n, hidden),
+            torch.empty(n, dtype=torch.int32, device=hidden.device), _f32(n, hidden))
+
+
+@torch.library.custom_op("pgica::lmhead_seq_logprob_bwd", mutates_args=())
+def lmhead_seq_logprob_bwd(hidden: Tensor, weight: Tensor, row_label: Tensor, row_weight: Tensor, lse: Tensor,
+                           grad_seq: Tensor, length_normalize: bool, need_dhidden: bool,
+                           need_dweight: bool) -> Tuple[Tensor, Tensor]:
+    hb, wb = F.as_bf16(hidden), F.as_bf16(weight)
+    dh, dw = F.lmhead_logprob_bwd(hb, wb, row_label, row_weight, lse, grad_seq, length_normalize,
+                                  need_dhidden=need_dhidden, need_dweight=need_dweight,
+                                  dhidden_dtype=_grad_dtype(hidden), dweight_dtype=_grad_dtype(weight))
+    if dh is None:
+        dh = hidden.new_empty(0)
+    if dw is None:
+        dw = weight.new_empty(0)
+    return dh, dw
+
+
+@lmhead_seq_logprob_bwd.register_fake
+def _(hidden, weight, row_label, row_weight, lse, grad_seq, length_normalize, need_dhidden, need_dweight):
+    dh = torch.empty_like(hidden, dtype=_grad_dtype(hidden)) if need_dhidden else hidden.new_empty(0)
+    dw = torch.empty_like(weight, dtype=_grad_dtype(weight)) if need_dweight else weight.new_empty(0)
+    return dh, dw
+
+
+def _lm_setup(ctx, inputs, output):
+    hidden, weight, labels, mask, length_normalize = inputs
+    _, lse, _, row_label, row_weight = output
+    ctx.save_for_backward(hidden, weight, row_label, row_weight, lse)
+    ctx.length_normalize = length_normalize
+
+
+def _lm_backward(ctx, g_seq, g_lse, g_zt, g_rl, g_rw):
+    hidden, weight, row_label, row_weight, lse = ctx.saved_tensors
+    need_h, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+    dh, dw = lmhead_seq_logprob_bwd(hidden, weight, row_label, row_weight, lse, g_seq.contiguous(),
+                                    ctx.length_normalize, need_h, need_w)
+    return (dh.to(hidden.dtype) if need_h else None, dw.to(weight.dtype) if need_w else None, None, None, None)
+
+
+lmhead_seq_logprob.register_autograd(_lm_backward, setup_context=_lm_setup)
+
+
+# ==================================================================================== materialised logits
+@torch.library.custom_op("pgica::logits_seq_logprob", mutates_args=())
+def logits_seq_logprob(logits: Tensor, labels: Tensor, mask: Optional[Tensor],
+                       length_normalize: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """(nseq, T, V) logits -> (seq_logp[nseq], lse[nseq*T], row_label, row_weight); streaming, HBM-bound."""
+    if logits.dim() != 3:
+        raise ValueError("logits_seq_logprob: logits must be (nseq, T, V)")
+    lg = logits if logits.dtype in (torch.float32, torch.bfloat16) else logits.float()
+    lg = lg.contiguous()
+    nseq, T, V = lg.shape
+    rl, rw = F.prep_rows(labels, mask, V)
+    lse, zt = F.logits_lse(lg, rl)
+    seq = F.seq_reduce(lse, zt, rw, nseq, T, length_normalize)
+    return seq, lse, rl, rw
+
+
+@logits_seq_logprob.register_fake
+def _(logits, labels, mask, length_normalize):
+    n = logits.shape[0] * logits.shape[1]
+    return (_f32(logits.shape[0], logits), _f32(n, logits),
+            torch.empty(n, dtype=torch.int32, device=logits.device), _f32(n, logits))
+
+
+@torch.library.custom_op("pgica::logits_seq_logprob_bwd", mutates_args=())
+def logits_seq_logprob_bwd(logits: Tensor, row_label: Tensor, row_weight: Tensor, lse: Tensor, grad_seq: Tensor,
+                           length_normalize: bool) -> Tensor:
+    lg = logits if logits.dtype in (torch.float32, torch.bfloat16) else logits.float()
+    lg = lg.contiguous()
+    nseq, T, _ = lg.shape
+    coef = F.row_coef(grad_seq, row_weight, nseq, T, length_normalize, 1.0)
+    return F.logits_grad(lg, row_label, lse, coef)
+
+
+@logits_seq_logprob_bwd.register_fake
+def _(logits, row_label, row_weight, lse, grad_seq, length_normalize):
+    return torch.empty_like(logits, dtype=logits.dtype if logits.dtype == torch.bfloat16 else torch.float32)
+
+
+def _lg_setup(ctx, inputs, output):
+    logits, labels, mask, length_normalize = inputs
+    _, lse, row_label, row_weight = output
+    ctx.save_for_backward(logits, row_label, row_weight, lse)
+    ctx.length_normalize = length_normalize
+
+
+def _lg_backward(ctx, g_seq, g_lse, g_rl, g_rw):
+    logits, row_label, row_weight, lse = ctx.saved_tensors
+    d = logits_seq_logprob_bwd(logits, row_label, row_weight, lse, g_seq.contiguous(), ctx.length_normalize)
+    return d.to(logits.dtype), None, None, None
+
+
+logits_seq_logprob.register_autograd(_lg_backward, setup_context=_lg_setup)
+
+
+# ============================================================================================ DPO scalar
+@torch.library.custom_op("pgica::dpo_loss", mutates_args=())
+def dpo_loss(pc: Tensor, pr: Tensor, rc: Optional[Tensor], rr: Optional[Tensor], beta: float,
+             label_smoothing: float, n_global: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """-> (loss[], metrics[5], dloss/dpc[n]).  metrics = (dpo_loss, reward_margin, reward_accuracy,
+    mean policy chosen log-prob, mean policy rejected log-prob)."""
+    f = lambda t: None if t is None else t.contiguous().float()
+    return F.dpo_loss_fwd(f(pc), f(pr), f(rc), f(rr), beta, label_smoothing, n_global)
+
+
+@dpo_loss.register_fake
+def _(pc, pr, rc, rr, beta, label_smoothing, n_global):
+    return pc.new_empty((), dtype=torch.float32), _f32(5, pc), _f32(pc.numel(), pc)
+
+
+@torch.library.custom_op("pgica::scale_by_scalar", mutates_args=())
+def scale_by_scalar(a: Tensor, scalar: Tensor, mult: float) -> Tensor:
+    return F.scale_by_scalar(a.contiguous().float(), scalar.reshape(1).contiguous().float(), mult)
+
+
+@scale_by_scalar.register_fake
+def _(a, scalar, mult):
+    return torch.empty_like(a, dtype=torch.float32)
+
+
+def _dpo_setup(ctx, inputs, output):
+    pc, pr, rc, rr = inputs[:4]
+    ctx.save_for_backward(output[2])
+    ctx.has_ref = rc is not None
+    ctx.dtypes = (pc.dtype, pr.dtype, rc.dtype if rc is not None else None, rr.dtype if rr is not None else None)
+
+
+def _dpo_backward(ctx, g_loss, g_metrics, g_dpc):
+    (dpc,) = ctx.saved_tensors
+    need = ctx.needs_input_grad
+    pos = scale_by_scalar(dpc, g_loss, 1.0)
+    neg = scale_by_scalar(dpc, g_loss, -1.0)
+    dt = ctx.dtypes
+    return (pos.to(dt[0]) if need[0] else None, neg.to(dt[1]) if need[1] else None,
+            neg.to(dt[2]) if ctx.has_ref and need[2] else None, pos.to(dt[3]) if ctx.has_ref and need[3] else None,
+            None, None, None)
+
+
+dpo_loss.register_autograd(_dpo_backward, setup_context=_dpo_setup)

@@ -1,0 +1,189 @@
+"""CPU tests (no GPU, no compute calls): the C-ABI library builds, loads and exports every symbol that
+include/pgica.h declares; host-side argument validation; the Python mirror of the reference interface."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+import types
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from preference_guided_image_captioning_alignment_b200 import _build, _lib
+    _build.build()
+    return _lib.load()
+
+
+def test_header_symbols_exported(lib):
+    from preference_guided_image_captioning_alignment_b200 import _lib
+    protos = _lib.parse_header()
+    text = open(_lib.HEADER_PATH).read()
+    declared = set(re.findall(r"\b(pgica_\w+)\s*\(", text))
+    assert declared == set(protos), "header parser missed a prototype"
+    assert len(declared) >= 25
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT (pgica_\w+)", out))
+    assert declared <= exported, f"declared but not exported: {sorted(declared - exported)}"
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.pgica_abi_version() == 1
+
+
+def test_every_entry_point_cites_the_reference():
+    text = open(os.path.join(ROOT, "include", "pgica.h")).read()
+    for needle in ("pkg/models/components.py:321-362", "pkg/models/model.py:1052-1085", "pkg/models/components.py:192-249",
+                   "pkg/models/model.py:970-1000", "pkg/models/components.py:117-145", "modeling_gpt2.py:706"):
+        assert needle in text
+
+
+def test_library_is_sm100a_only(lib):
+    from preference_guided_image_captioning_alignment_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_host_side_validation_without_gpu(lib):
+    need = ctypes.c_size_t(0)
+    assert lib.pgica_gemm_lse_workspace_bytes(4064, 50257, 1024, ctypes.byref(need)) == 0
+    assert 0 < need.value < (1 << 28)
+    assert lib.pgica_gemm_lse_workspace_bytes(128, 256, 1001, ctypes.byref(need)) == -1
+    assert b"multiple of 8" in lib.pgica_last_error()
+    assert lib.pgica_gemm_lse_workspace_bytes(0, 256, 64, ctypes.byref(need)) == -1
+    assert lib.pgica_lmhead_logprob_workspace_bytes(32, 128, 1024, 50257, ctypes.byref(need)) == 0
+    assert need.value >= 32 * 128 * 4
+    assert lib.pgica_ntxent_workspace_bytes(4096, 32768, 512, ctypes.byref(need)) == 0
+    if not torch.cuda.is_available():
+        # the product path fails loudly without a B200; it never computes on the host
+        assert lib.pgica_device_check() != 0
+        assert lib.pgica_last_error()
+        assert lib.pgica_gemm_lse(None, None, 128, 128, 64, 1.0, None, 0, None, None, None, 0, None) != 0
+
+
+def test_no_cpu_fallback_in_python_layer():
+    import preference_guided_image_captioning_alignment_b200 as pg
+    from preference_guided_image_captioning_alignment_b200._lib import PgicaError
+    a, b = torch.randn(4, 64), torch.randn(4, 64)
+    with pytest.raises(PgicaError):
+        pg.ContrastiveLoss(0.07)(a, b)
+    with pytest.raises(PgicaError):
+        pg.PreferenceLoss(0.1)(torch.randn(2, 5, 11), torch.randn(2, 5, 11), torch.zeros(2, 5, dtype=torch.long),
+                               torch.zeros(2, 5, dtype=torch.long), torch.ones(2, 5), torch.ones(2, 5))
+    with pytest.raises(PgicaError):
+        pg.DPOPreferenceLoss()(torch.zeros(3), torch.zeros(3))
+    # nothing in the product package imports the oracle
+    pkg_dir = os.path.dirname(pg.__file__)
+    for f in os.listdir(pkg_dir):
+        if f.endswith(".py"):
+            src = open(os.path.join(pkg_dir, f)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b|import_module\([\"']oracle", src, flags=re.M), f
+
+
+def test_module_interface_mirrors_reference():
+    import inspect
+
+    import preference_guided_image_captioning_alignment_b200 as pg
+    from preference_guided_image_captioning_alignment_b200 import components, losses
+    sig = lambda f: list(inspect.signature(f).parameters)
+    assert sig(losses.ContrastiveLoss.__init__) == ["self", "temperature"]
+    assert sig(losses.ContrastiveLoss.forward) == ["self", "image_embeddings", "text_embeddings"]
+    assert inspect.signature(losses.ContrastiveLoss.__init__).parameters["temperature"].default == 0.07
+    assert sig(losses.PreferenceLoss.forward) == ["self", "preferred_logits", "rejected_logits", "preferred_labels",
+                                                  "rejected_labels", "preferred_mask", "rejected_mask"]
+    assert sig(losses.PreferenceLoss._compute_log_probs) == ["self", "logits", "labels", "mask"]
+    assert sig(components.ContrastiveLoss.__init__) == ["self", "temperature", "reduction"]
+    assert sig(components.ContrastiveLoss.forward) == ["self", "vision_embeds", "text_embeds"]
+    assert sig(components.DPOPreferenceLoss.__init__) == ["self", "beta", "reference_free", "label_smoothing"]
+    assert sig(components.DPOPreferenceLoss.forward) == ["self", "policy_chosen_logprobs", "policy_rejected_logprobs",
+                                                         "reference_chosen_logprobs", "reference_rejected_logprobs"]
+    assert sig(components.compute_sequence_logprobs) == ["logits", "labels", "attention_mask"]
+    assert sig(components.TemperatureScaledSimilarity.__init__) == ["self", "temperature", "learnable", "min_temp",
+                                                                    "max_temp"]
+    # state: trainer-variant losses hold plain floats; the similarity module owns a `temperature` buffer
+    assert list(pg.ContrastiveLoss(0.3).state_dict()) == [] and pg.ContrastiveLoss(0.3).temperature == 0.3
+    assert list(pg.PreferenceLoss(0.2).state_dict()) == [] and pg.PreferenceLoss(0.2).beta == 0.2
+    assert list(components.ContrastiveLoss(0.5).state_dict()) == ["similarity.temperature"]
+    sim = components.TemperatureScaledSimilarity(0.07)
+    assert sim.effective_temperature() == pytest.approx(0.1)       # clamp, components.py:78
+    assert components.TemperatureScaledSimilarity(5.0).effective_temperature() == 2.0
+    assert isinstance(components.TemperatureScaledSimilarity(0.5, learnable=True).temperature, torch.nn.Parameter)
+
+
+def test_mask_kind_and_lazy_logits():
+    from preference_guided_image_captioning_alignment_b200 import functional as F
+    from preference_guided_image_captioning_alignment_b200.losses import LazyLogits
+    assert F.mask_kind(None) == (0, None)
+    assert F.mask_kind(torch.ones(2, 3, dtype=torch.long))[0] == F.MASK_I64
+    assert F.mask_kind(torch.ones(2, 3))[0] == F.MASK_F32
+    assert F.mask_kind(torch.ones(2, 3, dtype=torch.bool))[0] == F.MASK_U8
+    assert F.mask_kind(torch.ones(2, 3, dtype=torch.int32))[0] == F.MASK_I32
+    assert F.mask_kind(torch.ones(2, 3, dtype=torch.float64))[0] == F.MASK_F32
+    h, w = torch.randn(2, 5, 8), torch.randn(11, 8)
+    z = LazyLogits(h, w)
+    assert z.shape == (2, 5, 11) and z.size(-1) == 11 and z.dim() == 3
+    torch.testing.assert_close(z.materialize(), h @ w.T)
+
+
+def test_fake_tensor_propagation():
+    """The custom ops carry meta kernels (shape/dtype inference without a device)."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+
+    from preference_guided_image_captioning_alignment_b200 import ops
+    with FakeTensorMode():
+        a, b = torch.empty(64, 512), torch.empty(64, 512)
+        loss, lr, lc = ops.ntxent(a, b, 2.0, True)
+        assert loss.shape == () and lr.shape == (64,) and lc.shape == (64,)
+        h, w = torch.empty(4, 16, 128), torch.empty(1000, 128)
+        out = ops.lmhead_seq_logprob(h, w, torch.empty(4, 16, dtype=torch.long), None, True)
+        assert out[0].shape == (4,) and out[1].shape == (64,) and out[3].dtype == torch.int32
+        loss, met, dpc = ops.dpo_loss(torch.empty(8), torch.empty(8), None, None, 0.1, 0.0, 8)
+        assert met.shape == (5,) and dpc.shape == (8,)
+
+
+def test_install_rebinds_reference_names():
+    import importlib
+
+    from preference_guided_image_captioning_alignment_b200 import components, losses
+    install = importlib.import_module("preference_guided_image_captioning_alignment_b200.install")
+    pkg = types.ModuleType("fake_ref")
+    models = types.ModuleType("fake_ref.models")
+    model = types.ModuleType("fake_ref.models.model")
+    comp = types.ModuleType("fake_ref.models.components")
+    training = types.ModuleType("fake_ref.training")
+    trainer = types.ModuleType("fake_ref.training.trainer")
+    sentinel = object()
+    for m in (model, models, trainer):
+        m.ContrastiveLoss = sentinel
+        m.PreferenceLoss = sentinel
+    for n in ("ContrastiveLoss", "DPOPreferenceLoss", "TemperatureScaledSimilarity", "compute_sequence_logprobs"):
+        setattr(comp, n, sentinel)
+    mods = {"fake_ref": pkg, "fake_ref.models": models, "fake_ref.models.model": model,
+            "fake_ref.models.components": comp, "fake_ref.training": training, "fake_ref.training.trainer": trainer}
+    sys.modules.update(mods)
+    try:
+        done = install.install("fake_ref", fuse_lm_head=False)
+        assert trainer.ContrastiveLoss is losses.ContrastiveLoss and trainer.PreferenceLoss is losses.PreferenceLoss
+        assert model.ContrastiveLoss is losses.ContrastiveLoss and models.PreferenceLoss is losses.PreferenceLoss
+        assert comp.DPOPreferenceLoss is components.DPOPreferenceLoss
+        assert ("fake_ref.training.trainer", "PreferenceLoss") in done
+        install.uninstall()
+        assert trainer.ContrastiveLoss is sentinel and comp.compute_sequence_logprobs is sentinel
+    finally:
+        for k in mods:
+            sys.modules.pop(k, None)
+
+
+def test_shard_pairs():
+    from preference_guided_image_captioning_alignment_b200.distributed import shard_pairs
+    for n, w in [(256, 8), (16, 1), (10, 4), (3, 8)]:
+        spans = [shard_pairs(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1

@@ -1,0 +1,402 @@
+"""GPU parity tests (`-m gpu`, B200): the CUDA path — module -> torch.library op -> C ABI -> kernels — against
+(1) golden vectors minted from the real reference, (2) the float64 oracle on seeded inputs at sizes it finishes
+in seconds, (3) size-independent properties at BASELINE.json's full sizes.
+
+Tolerances are the ones BASELINE.json states: bf16 inputs with fp32 accumulation -> loss within 1e-4 relative,
+gradients within 1e-2 relative (||delta|| / ||ref||), index / mask plumbing bit-exact."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import closed_form as cf
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-4
+GRAD_RTOL = 1e-2
+METRIC_KEYS = ("dpo_loss", "reward_margin", "reward_accuracy", "policy_chosen_logprob", "policy_rejected_logprob")
+
+
+def bits_to_f32(u16, dev):
+    return torch.from_numpy(u16.astype(np.int16)).view(torch.bfloat16).float().to(dev)
+
+
+def rel(a, b):
+    a = torch.as_tensor(a, dtype=torch.float64).cpu()
+    b = torch.as_tensor(b, dtype=torch.float64).cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-300)).item()
+
+
+def bf16r(t):
+    return t.to(torch.bfloat16).float()
+
+
+@pytest.fixture(scope="module")
+def pg(cuda_device):
+    import preference_guided_image_captioning_alignment_b200 as pkg
+    from preference_guided_image_captioning_alignment_b200 import _lib
+    lib = _lib.load()
+    assert lib.pgica_device_check() == 0, lib.pgica_last_error()
+    return pkg
+
+
+# ================================================================================================ NT-Xent
+@pytest.mark.parametrize("seed", [1234, 1, 2])
+@pytest.mark.parametrize("tau,red", [(0.5, "mean"), (0.5, "sum"), (0.07, "mean")])
+def test_ntxent_components_golden(pg, cuda_device, golden_dir, seed, tau, red):
+    from preference_guided_image_captioning_alignment_b200 import components
+    g = np.load(os.path.join(golden_dir, "ntxent.npz"))
+    v = bits_to_f32(g[f"s{seed}_v_bf16"], cuda_device).requires_grad_(True)
+    t = bits_to_f32(g[f"s{seed}_t_bf16"], cuda_device).requires_grad_(True)
+    loss = components.ContrastiveLoss(temperature=tau, reduction=red)(v, t)
+    k = f"s{seed}_comp_tau{tau}_{red}"
+    assert loss.dim() == 0
+    assert loss.item() == pytest.approx(float(g[k + "_loss"]), rel=LOSS_RTOL)
+    loss.backward()
+    if k + "_dv" in g:
+        assert rel(v.grad, g[k + "_dv"]) < GRAD_RTOL
+        assert rel(t.grad, g[k + "_dt"]) < GRAD_RTOL
+
+
+@pytest.mark.parametrize("seed", [1234, 1, 2])
+@pytest.mark.parametrize("tau", [0.5, 0.07])
+def test_ntxent_trainer_golden(pg, cuda_device, golden_dir, seed, tau):
+    g = np.load(os.path.join(golden_dir, "ntxent.npz"))
+    v = bits_to_f32(g[f"s{seed}_vn_bf16"], cuda_device).requires_grad_(True)
+    t = bits_to_f32(g[f"s{seed}_tn_bf16"], cuda_device).requires_grad_(True)
+    loss = pg.ContrastiveLoss(temperature=tau)(v, t)
+    k = f"s{seed}_trainer_tau{tau}"
+    assert loss.item() == pytest.approx(float(g[k + "_loss"]), rel=LOSS_RTOL)
+    loss.backward()
+    if k + "_dv" in g:
+        assert rel(v.grad, g[k + "_dv"]) < GRAD_RTOL
+        assert rel(t.grad, g[k + "_dt"]) < GRAD_RTOL
+
+
+def test_ntxent_bf16_inputs_and_no_grad(pg, cuda_device):
+    torch.manual_seed(0)
+    a = torch.nn.functional.normalize(torch.randn(200, 512, device=cuda_device), dim=-1).to(torch.bfloat16)
+    b = torch.nn.functional.normalize(torch.randn(200, 512, device=cuda_device), dim=-1).to(torch.bfloat16)
+    ref = cf.ntxent(a.double().cpu().numpy(), b.double().cpu().numpy(), 0.2)
+    with torch.no_grad():
+        l0 = pg.ContrastiveLoss(0.2)(a, b)
+    assert l0.item() == pytest.approx(ref["loss"], rel=LOSS_RTOL)
+    a.requires_grad_(True)
+    b.requires_grad_(True)
+    loss = pg.ContrastiveLoss(0.2)(a, b)
+    loss.backward()
+    assert a.grad.dtype == torch.bfloat16
+    assert rel(a.grad.float(), ref["dx"]) < GRAD_RTOL and rel(b.grad.float(), ref["dy"]) < GRAD_RTOL
+
+
+def test_ntxent_known_answers(pg, cuda_device):
+    from preference_guided_image_captioning_alignment_b200 import components
+    dev = cuda_device
+    B, D = 48, 64
+    x = torch.randn(1, D, device=dev).repeat(B, 1)
+    assert components.ContrastiveLoss(0.5)(x, x).item() == pytest.approx(math.log(B), rel=LOSS_RTOL)      # KA3
+    e = torch.eye(B, D, device=dev)
+    for tau in (0.5, 0.2):                                                                                # KA4
+        assert pg.ContrastiveLoss(tau)(e, e).item() == pytest.approx(math.log(1 + (B - 1) * math.exp(-1 / tau)),
+                                                                     rel=LOSS_RTOL)
+    u = torch.nn.functional.normalize(torch.randn(4, 256, device=dev), dim=-1)                            # KA5
+    lo, hi = pg.ContrastiveLoss(0.01)(u, u).item(), pg.ContrastiveLoss(1.0)(u, u).item()
+    assert lo < hi and lo >= 0.0
+    v, t = torch.randn(B, D, device=dev), torch.randn(B, D, device=dev)                                   # KA6
+    assert components.ContrastiveLoss(0.07)(v, t).item() == components.ContrastiveLoss(0.1)(v, t).item()
+
+
+def test_reference_test_suite_properties(pg, cuda_device):
+    """The reference's own TestLossFunctions (tests/test_model.py:383-499) re-run against the fused modules."""
+    dev = cuda_device
+    ie = torch.nn.functional.normalize(torch.randn(4, 256, device=dev), dim=-1)
+    te = torch.nn.functional.normalize(torch.randn(4, 256, device=dev), dim=-1)
+    loss = pg.ContrastiveLoss(temperature=0.07)(ie, te)
+    assert isinstance(loss, torch.Tensor) and loss.dim() == 0 and loss.item() >= 0.0
+    lf = pg.PreferenceLoss(beta=0.1)
+    pl, rl = torch.randn(2, 20, 1000, device=dev), torch.randn(2, 20, 1000, device=dev)
+    py, ry = torch.randint(0, 1000, (2, 20), device=dev), torch.randint(0, 1000, (2, 20), device=dev)
+    m = torch.ones(2, 20, device=dev)
+    loss = lf(preferred_logits=pl, rejected_logits=rl, preferred_labels=py, rejected_labels=ry, preferred_mask=m,
+              rejected_mask=m)
+    assert loss.dim() == 0 and loss.item() >= 0.0
+    lp = lf._compute_log_probs(torch.randn(2, 10, 100, device=dev), torch.randint(0, 100, (2, 10), device=dev),
+                               torch.ones(2, 10, device=dev))
+    assert lp.shape == (2,)
+    a = torch.randn(2, 256, device=dev, requires_grad=True)
+    b = torch.randn(2, 256, device=dev, requires_grad=True)
+    pg.ContrastiveLoss()(torch.nn.functional.normalize(a, dim=-1), torch.nn.functional.normalize(b, dim=-1)).backward()
+    assert a.grad is not None and b.grad is not None
+    pl = torch.randn(2, 10, 100, device=dev, requires_grad=True)
+    rl = torch.randn(2, 10, 100, device=dev, requires_grad=True)
+    y = torch.randint(0, 100, (2, 10), device=dev)
+    m = torch.ones(2, 10, device=dev)
+    pg.PreferenceLoss()(pl, rl, y, y, m, m).backward()
+    assert pl.grad is not None and rl.grad is not None
+
+
+def test_ntxent_rank_emulation(pg, cuda_device):
+    """All ranks' shards through the same kernels on one device == the global batch."""
+    from preference_guided_image_captioning_alignment_b200 import functional as F
+    dev = cuda_device
+    W, nb, D, tau = 4, 96, 512, 0.5
+    B = W * nb
+    torch.manual_seed(1)
+    a = torch.nn.functional.normalize(torch.randn(B, D, device=dev), dim=-1).to(torch.bfloat16)
+    b = torch.nn.functional.normalize(a.float() + 0.3 * torch.randn(B, D, device=dev), dim=-1).to(torch.bfloat16)
+    ref = cf.ntxent(a.double().cpu().numpy(), b.double().cpu().numpy(), tau)
+    fw = [F.ntxent_fwd(a[r * nb:(r + 1) * nb].contiguous(), b, 1 / tau, r * nb) for r in range(W)]
+    lse_col = F.lse_combine(torch.stack([f[2] for f in fw]))
+    assert rel(lse_col, ref["lse_col"]) < 1e-5
+    loss = sum(F.ntxent_loss(f[0], f[1], lse_col[r * nb:(r + 1) * nb].contiguous(), 1.0 / B).item()
+               for r, f in enumerate(fw))
+    assert loss == pytest.approx(ref["loss"], rel=LOSS_RTOL)
+    one = torch.ones((), device=dev)
+    db = torch.zeros(B, D, device=dev)
+    for r, f in enumerate(fw):
+        da, dbp = F.ntxent_bwd(a[r * nb:(r + 1) * nb].contiguous(), b, 1 / tau, r * nb, f[0], lse_col, one, 1 / (2 * B))
+        assert rel(da, ref["dx"][r * nb:(r + 1) * nb]) < GRAD_RTOL
+        db += dbp
+    assert rel(db, ref["dy"]) < GRAD_RTOL
+
+
+# ================================================================================================ logits path
+@pytest.mark.parametrize("name", ["none", "i64", "f64"])
+def test_sequence_logprobs_golden(pg, cuda_device, golden_dir, name):
+    g = np.load(os.path.join(golden_dir, "seq_logprobs.npz"))
+    dev = cuda_device
+    logits = torch.tensor(g["logits"], dtype=torch.float32, device=dev, requires_grad=True)
+    labels = torch.tensor(g["labels"], device=dev)
+    mask = {"none": None, "i64": torch.tensor(g["mask_i"], device=dev),
+            "f64": torch.tensor(g["mask_f"], dtype=torch.float32, device=dev)}[name]
+    s = pg.compute_sequence_logprobs(logits, labels, mask)
+    np.testing.assert_allclose(s.detach().cpu().numpy(), g[f"sum_{name}"], rtol=2e-6)
+    (s * torch.arange(1, 4, device=dev).float()).sum().backward()
+    assert rel(logits.grad, g[f"sum_{name}_dlogits"]) < 1e-5
+    if name != "none":
+        lg2 = torch.tensor(g["logits"], dtype=torch.float32, device=dev, requires_grad=True)
+        s2 = pg.PreferenceLoss(0.1)._compute_log_probs(lg2, labels, mask)
+        np.testing.assert_allclose(s2.detach().cpu().numpy(), g[f"mean_{name}"], rtol=2e-6)
+        (s2 * torch.arange(1, 4, device=dev).float()).sum().backward()
+        assert rel(lg2.grad, g[f"mean_{name}_dlogits"]) < 1e-5
+
+
+def test_preference_loss_golden(pg, cuda_device, golden_dir):
+    g = np.load(os.path.join(golden_dir, "seq_logprobs.npz"))
+    dev = cuda_device
+    a = torch.tensor(g["logits"], dtype=torch.float32, device=dev, requires_grad=True)
+    b = torch.tensor(g["logits2"], dtype=torch.float32, device=dev, requires_grad=True)
+    t = lambda k: torch.tensor(g[k], device=dev)
+    loss = pg.PreferenceLoss(beta=0.1)(a, b, t("labels"), t("labels2"), t("mask_i"), t("mask2"))
+    assert loss.item() == pytest.approx(float(g["pref_loss"]), rel=1e-5)
+    loss.backward()
+    assert rel(a.grad, g["pref_dlogits"]) < 1e-4 and rel(b.grad, g["pref_dlogits2"]) < 1e-4
+
+
+@pytest.mark.parametrize("tag,kw,use_ref", [("std", dict(beta=0.1), True),
+                                            ("ls", dict(beta=0.1, label_smoothing=0.1), True),
+                                            ("free", dict(beta=0.1, reference_free=True), True),
+                                            ("noref", dict(beta=0.25), False)])
+def test_dpo_loss_golden(pg, cuda_device, golden_dir, tag, kw, use_ref):
+    g = np.load(os.path.join(golden_dir, "dpo_loss.npz"))
+    xs = [torch.tensor(g[k], dtype=torch.float32, device=cuda_device, requires_grad=True)
+          for k in ("pc", "pr", "rc", "rr")]
+    mod = pg.DPOPreferenceLoss(**kw)
+    loss, metrics = mod(*xs) if use_ref else mod(xs[0], xs[1])
+    assert loss.item() == pytest.approx(float(g[tag + "_loss"]), rel=1e-5)
+    assert tuple(metrics.keys()) == METRIC_KEYS
+    np.testing.assert_allclose([metrics[k] for k in METRIC_KEYS], g[tag + "_metrics"], rtol=1e-5, atol=1e-6)
+    loss.backward()
+    assert rel(xs[0].grad, g[tag + "_dpc"]) < 1e-5 and rel(xs[1].grad, g[tag + "_dpr"]) < 1e-5
+    if use_ref and not kw.get("reference_free"):
+        assert rel(xs[2].grad, g[tag + "_drc"]) < 1e-5 and rel(xs[3].grad, g[tag + "_drr"]) < 1e-5
+    else:
+        assert xs[2].grad is None
+
+
+# ================================================================================================ fused LM head
+def test_dpo_head_golden(pg, cuda_device, golden_dir):
+    g = np.load(os.path.join(golden_dir, "dpo_head.npz"))
+    dev = cuda_device
+    f = lambda k, rg=False: torch.tensor(g[k], dtype=torch.float32, device=dev, requires_grad=rg)
+    i = lambda k: torch.tensor(g[k], device=dev)
+    W, hc, hr = f("W", True), f("hc", True), f("hr", True)
+    head = pg.FusedDPOHead(beta=0.1)
+    loss, metrics = head(hc, hr, W, i("yc"), i("yr"), i("mc"), i("mr"), f("rhc"), f("rhr"), f("Wr"))
+    assert loss.item() == pytest.approx(float(g["loss"]), rel=LOSS_RTOL)
+    np.testing.assert_allclose(metrics.cpu().numpy(), g["metrics"], rtol=1e-4, atol=1e-4)
+    loss.backward()
+    assert rel(W.grad, g["dW"]) < GRAD_RTOL
+    assert rel(hc.grad, g["dhc"]) < GRAD_RTOL and rel(hr.grad, g["dhr"]) < GRAD_RTOL
+    # per-sequence log-probs, sum and mean flavours
+    for ln in (False, True):
+        got = pg.lmhead_sequence_logprobs(hc.detach(), W.detach(), i("yc"), i("mc"), ln)
+        want = cf.lmhead_sequence_logprobs(g["hc"], g["W"], g["yc"], g["mc"], ln)["seq_logp"]
+        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-5)
+
+
+def _cfg2_inputs(dev, B, T=128, d=1024, V=50257, seed=1234):
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    W = (torch.randn(V, d, generator=gen) * 0.02).to(torch.bfloat16)
+    h = torch.randn(2 * B, T, d, generator=gen).to(torch.bfloat16)
+    y = torch.randint(0, V, (2 * B, T), generator=gen)
+    lens = torch.randint(T // 2, T + 1, (2 * B,), generator=gen)
+    m = (torch.arange(T)[None, :] < lens[:, None]).long()
+    return W.to(dev), h.to(dev), y.to(dev), m.to(dev)
+
+
+def test_lmhead_full_vocab_vs_oracle(pg, cuda_device):
+    """GPT-2 Medium head shape (d=1024, V=50257, T=128) on 2 pairs: everything against the float64 oracle."""
+    dev = cuda_device
+    B = 2
+    W, h, y, m = _cfg2_inputs(dev, B)
+    Wg, hg = W.clone().requires_grad_(True), h.clone().requires_grad_(True)
+    seq = pg.lmhead_sequence_logprobs(hg, Wg, y, m)
+    gseq = torch.tensor([0.3, -1.1, 0.7, 2.0], device=dev)
+    (seq * gseq).sum().backward()
+    o = cf.lmhead_sequence_logprobs(h.double().cpu().numpy(), W.double().cpu().numpy(), y.cpu().numpy(),
+                                    m.cpu().numpy(), False, grad_seq=gseq.double().cpu().numpy())
+    np.testing.assert_allclose(seq.detach().cpu().numpy(), o["seq_logp"], rtol=LOSS_RTOL)
+    assert rel(hg.grad.float(), o["dhidden"]) < GRAD_RTOL
+    assert rel(Wg.grad.float(), o["dweight"]) < GRAD_RTOL
+    assert torch.count_nonzero(hg.grad[:, -1]).item() == 0  # nothing is scored at the last position
+
+
+def test_plumbing_bit_exact(pg, cuda_device):
+    """KA10: the index / mask plumbing equals labels[:, 1:], mask[:, 1:] exactly; ids >= V at masked slots are inert."""
+    from preference_guided_image_captioning_alignment_b200 import functional as F
+    dev = cuda_device
+    nseq, T, V = 5, 17, 50257
+    gen = torch.Generator().manual_seed(3)
+    labels = torch.randint(0, V, (nseq, T), generator=gen)
+    lens = torch.tensor([17, 9, 1, 12, 2])
+    mask = (torch.arange(T)[None, :] < lens[:, None]).long()
+    labels[mask == 0] = 50257  # pad id, outside the V=50257 vocabulary
+    for mk in (mask, mask.float(), mask.bool(), mask.int()):
+        rl, rw = F.prep_rows(labels.to(dev), mk.to(dev), V)
+        rl, rw = rl.view(nseq, T).cpu(), rw.view(nseq, T).cpu()
+        want_l = torch.where(mask[:, 1:] == 1, labels[:, 1:], torch.full_like(labels[:, 1:], -1))
+        assert torch.equal(rl[:, :-1].long(), want_l)
+        assert torch.equal(rw[:, :-1], mask[:, 1:].float())
+        assert (rl[:, -1] == -1).all() and (rw[:, -1] == 0).all()
+    rl, rw = F.prep_rows(labels.clamp(max=V - 1).to(dev), None, V)
+    assert torch.equal(rw.view(nseq, T)[:, :-1].cpu(), torch.ones(nseq, T - 1))
+
+
+def test_lmhead_edge_cases(pg, cuda_device):
+    dev = cuda_device
+    torch.manual_seed(5)
+    # ragged shapes: rows not a multiple of 128, V smaller than a tile, d not a multiple of 64
+    for (nseq, T, d, V) in [(1, 2, 64, 50), (3, 7, 72, 300), (2, 130, 256, 1000)]:
+        h = torch.randn(nseq, T, d, device=dev).to(torch.bfloat16).requires_grad_(True)
+        W = (torch.randn(V, d, device=dev) * 0.3).to(torch.bfloat16).requires_grad_(True)
+        y = torch.randint(0, V, (nseq, T), device=dev)
+        seq = pg.lmhead_sequence_logprobs(h, W, y, None, True)
+        seq.sum().backward()
+        o = cf.lmhead_sequence_logprobs(h.detach().double().cpu().numpy(), W.detach().double().cpu().numpy(),
+                                        y.cpu().numpy(), None, True, grad_seq=np.ones(nseq))
+        np.testing.assert_allclose(seq.detach().cpu().numpy(), o["seq_logp"], rtol=LOSS_RTOL)
+        assert rel(h.grad.float(), o["dhidden"]) < GRAD_RTOL and rel(W.grad.float(), o["dweight"]) < GRAD_RTOL
+    # all-zero mask row: 0 in sum mode, NaN in length-normalised mode (like the reference)
+    h = torch.randn(2, 6, 64, device=dev).to(torch.bfloat16)
+    W = torch.randn(40, 64, device=dev).to(torch.bfloat16)
+    y = torch.randint(0, 40, (2, 6), device=dev)
+    m = torch.ones(2, 6, dtype=torch.long, device=dev)
+    m[1] = 0
+    assert pg.lmhead_sequence_logprobs(h, W, y, m, False)[1].item() == 0.0
+    assert math.isnan(pg.lmhead_sequence_logprobs(h, W, y, m, True)[1].item())
+    # NaN in -> NaN out (the trainer's NaN-skip logic relies on it, trainer.py:482,607)
+    hn = h.clone()
+    hn[0, 2, 5] = float("nan")
+    assert math.isnan(pg.lmhead_sequence_logprobs(hn, W, y, None, False)[0].item())
+    # CPU tensors: loud failure, no fallback
+    with pytest.raises(Exception):
+        pg.lmhead_sequence_logprobs(h.cpu(), W.cpu(), y.cpu())
+
+
+def test_cfg2_properties_full_size(pg, cuda_device):
+    """BASELINE config 2 (B=16, T=128, d=1024, V=50257): size-independent properties."""
+    dev = cuda_device
+    B = 16
+    W, h, y, m = _cfg2_inputs(dev, B)
+    head = pg.FusedDPOHead(beta=0.1)
+    # KA1: policy == reference -> ln 2, margin 0, accuracy 0
+    loss, met = head(h[:B], h[B:], W, y[:B], y[B:], m[:B], m[B:], h[:B], h[B:], W)
+    assert loss.item() == pytest.approx(math.log(2), rel=1e-6)
+    assert met[1].item() == 0.0 and met[2].item() == 0.0
+    # KA2: W = 0 -> every token log-prob is -ln V
+    seq = pg.lmhead_sequence_logprobs(h, torch.zeros_like(W), y, m, True)
+    np.testing.assert_allclose(seq.cpu().numpy(), -math.log(50257), rtol=1e-6)
+    # KA9: all-ones mask == no mask, bit for bit
+    ones = torch.ones_like(m)
+    assert torch.equal(pg.lmhead_sequence_logprobs(h, W, y, ones), pg.lmhead_sequence_logprobs(h, W, y, None))
+    # determinism and linearity of the backward in the upstream gradient
+    Wg = W.clone().requires_grad_(True)
+    hg = h.clone().requires_grad_(True)
+    seq = pg.lmhead_sequence_logprobs(hg, Wg, y, m)
+    g1 = torch.autograd.grad(seq.sum(), (hg, Wg), retain_graph=True)
+    g1b = torch.autograd.grad(seq.sum(), (hg, Wg), retain_graph=True)
+    g2 = torch.autograd.grad((2.0 * seq).sum(), (hg, Wg))
+    assert torch.equal(g1[0], g1b[0]) and torch.equal(g1[1], g1b[1])
+    assert rel(g2[1].float(), 2.0 * g1[1].float()) < 1e-2
+    # masked rows receive exactly zero gradient
+    assert torch.count_nonzero(g1[0][(m[:, 1:] == 0).nonzero(as_tuple=True)]).item() == 0
+    # sequence sums against the oracle on a slice of the batch
+    sl = [0, B, 2 * B - 1]
+    o = cf.lmhead_sequence_logprobs(h[sl].double().cpu().numpy(), W.double().cpu().numpy(), y[sl].cpu().numpy(),
+                                    m[sl].cpu().numpy())
+    np.testing.assert_allclose(seq.detach()[sl].cpu().numpy(), o["seq_logp"], rtol=LOSS_RTOL)
+
+
+def test_ntxent_cfg1_and_large(pg, cuda_device):
+    """cfg1 (B=64, D=512, tau=0.5) against the oracle; a 4096-row slice of cfg3 via symmetry properties."""
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(1234)
+    v = torch.randn(64, 512, generator=gen).to(torch.bfloat16).float()
+    t = torch.randn(64, 512, generator=gen).to(torch.bfloat16).float()
+    from preference_guided_image_captioning_alignment_b200 import components
+    vg, tg = v.to(dev).requires_grad_(True), t.to(dev).requires_grad_(True)
+    loss = components.ContrastiveLoss(0.5)(vg, tg)
+    loss.backward()
+    o = cf.ntxent(v.double().numpy(), t.double().numpy(), 0.5, True, True)
+    assert loss.item() == pytest.approx(o["loss"], rel=LOSS_RTOL)
+    assert rel(vg.grad, o["dx"]) < GRAD_RTOL and rel(tg.grad, o["dy"]) < GRAD_RTOL
+    # symmetry: swapping the two sides swaps the gradients and keeps the loss
+    a = torch.nn.functional.normalize(torch.randn(4096, 512, device=dev), dim=-1).requires_grad_(True)
+    b = torch.nn.functional.normalize(torch.randn(4096, 512, device=dev), dim=-1).requires_grad_(True)
+    l1 = pg.ContrastiveLoss(0.5)(a, b)
+    ga, gb = torch.autograd.grad(l1, (a, b))
+    l2 = pg.ContrastiveLoss(0.5)(b, a)
+    hb, ha = torch.autograd.grad(l2, (b, a))
+    assert l1.item() == pytest.approx(l2.item(), rel=1e-6)
+    assert rel(ga, ha) < 1e-3 and rel(gb, hb) < 1e-3
+    o = cf.ntxent(a.detach().to(torch.bfloat16).double().cpu().numpy(),
+                  b.detach().to(torch.bfloat16).double().cpu().numpy(), 0.5)
+    assert l1.item() == pytest.approx(o["loss"], rel=LOSS_RTOL)
+    assert rel(ga, o["dx"]) < GRAD_RTOL
+
+
+def test_similarity_matrix(pg, cuda_device):
+    dev = cuda_device
+    v, t = torch.randn(70, 96, device=dev), torch.randn(50, 96, device=dev)
+    sim = pg.TemperatureScaledSimilarity(temperature=0.07)(v, t)  # clamped to 0.1
+    vn = torch.nn.functional.normalize(v, dim=-1).to(torch.bfloat16).double()
+    tn = torch.nn.functional.normalize(t, dim=-1).to(torch.bfloat16).double()
+    assert sim.shape == (70, 50)
+    assert rel(sim, vn @ tn.T / 0.1) < 1e-5
+    assert "temperature" in pg.TemperatureScaledSimilarity().state_dict()
+
+
+def test_opcheck(pg, cuda_device):
+    from preference_guided_image_captioning_alignment_b200 import ops
+    dev = cuda_device
+    a = torch.randn(32, 64, device=dev, requires_grad=True)
+    b = torch.randn(32, 64, device=dev, requires_grad=True)
+    torch.library.opcheck(ops.ntxent, (a, b, 2.0, True), test_utils=("test_schema", "test_faketensor"))
+    h = torch.randn(2, 5, 64, device=dev, requires_grad=True)
+    W = torch.randn(30, 64, device=dev, requires_grad=True)
+    y = torch.randint(0, 30, (2, 5), device=dev)
+    torch.library.opcheck(ops.lmhead_seq_logprob, (h, W, y, None, False), test_utils=("test_schema", "test_faketensor"))
