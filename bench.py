@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""Benchmark of the loss-head hot path (BASELINE.json metric: DPO pair-tokens/s fwd+bwd; NT-Xent pairs/s as extras).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload at every N (weak scaling, one process per GPU): BASELINE config 2 — Stage-2 DPO head, GPT-2 Medium LM head
+(d=1024, V=50257), 16 preference pairs per GPU, seq 128, beta=0.1, random-init weights, synthetic hidden states.
+One step = policy forward + backward (dH, dW) + frozen-reference forward + DPO loss (+ dW all-reduce when N>1).
+A pair-token is one scored position of one (chosen, rejected) pair: B*(T-1) = 2032 per GPU per step.
+
+`value`   inputs resident in HBM, CUDA events around K steps, max over ranks.
+`e2e`     the same step through the public module API (FusedDPOHead.forward_stacked + backward), inputs copied
+          from pinned host memory every step, loss read back every step.
+`roofline` the dominant kernel of the step against the measured bf16 tensor-core peak (MEASURED_PEAKS.json).
+`cpu_baseline` the reference's CPU path (oracle/torch_port.py) timed on this box's host cores, bounded sample.
+`--impl reference` times that CPU path alone, on all host threads, in the same JSON shape.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CFG = dict(pairs=16, seq_len=128, d=1024, vocab=50257, beta=0.1)
+METRIC = "dpo_pair_tokens_per_s"
+UNIT = "pair-tokens/s"
+WORKLOAD = ("cfg2: Stage-2 DPO loss head, GPT-2 Medium LM head d=1024 V=50257, chosen/rejected seq 128, 16 pairs per "
+            "GPU, beta=0.1, policy fwd+bwd + frozen-reference fwd, random-init, all-ones masks")
+FLOP_PER_PAIR_TOKEN = 16 * CFG["d"] * CFG["vocab"]  # policy fwd 4dV + ref fwd 4dV + policy bwd 8dV
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(burst=p["bf16_tflops"], sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    hbm=p["hbm_gbs"], source="measured")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback")
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}",
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 6]
+        os.unlink(self.f.name)
+        if not rows:
+            return out
+        sm = [float(r[0]) for r in rows if r[0].strip().replace(".", "").isdigit()]
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+            out["sm_max_mhz"] = float(rows[0][1])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for i, n in enumerate(names):
+            if any(r[3 + i].strip().lower().startswith("active") for r in rows):
+                out["reasons"].append(n)
+        out["samples"] = len(rows)
+        return out
+
+
+# ----------------------------------------------------------------------------------------------- CPU reference
+def cpu_reference_step_inputs(pairs, seed=1234):
+    import torch
+    T, d, V = CFG["seq_len"], CFG["d"], CFG["vocab"]
+    g = torch.Generator().manual_seed(seed)
+    W = torch.randn(V, d, generator=g) * 0.02
+    Wr = torch.randn(V, d, generator=g) * 0.02
+    hs = [torch.randn(pairs, T, d, generator=g) for _ in range(4)]
+    yc, yr = torch.randint(0, V, (pairs, T), generator=g), torch.randint(0, V, (pairs, T), generator=g)
+    m = torch.ones(pairs, T, dtype=torch.long)
+    return W, Wr, hs, yc, yr, m
+
+
+def time_cpu_reference(pairs, steps, warmup):
+    """The reference's CPU path: fp32 torch ops on the host cores (oracle/torch_port.dpo_head_step)."""
+    import torch
+
+    from oracle import torch_port as tp
+    torch.set_num_threads(os.cpu_count() or 1)
+    W, Wr, hs, yc, yr, m = cpu_reference_step_inputs(pairs)
+    W.requires_grad_(True)
+    hs[0].requires_grad_(True)
+    hs[1].requires_grad_(True)
+
+    def step():
+        W.grad = hs[0].grad = hs[1].grad = None
+        return tp.dpo_head_step(hs[0], hs[1], W, yc, yr, m, m, hs[2], hs[3], Wr, CFG["beta"])
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    tokens = pairs * (CFG["seq_len"] - 1) * steps
+    return tokens / dt, dt / steps, torch.get_num_threads()
+
+
+def cpu_model_name():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    pairs = 4  # bounded sample: 4 of the 16 pairs per step (throughput is linear in pairs); ~1-2 s of CPU work
+    value, sec, threads = time_cpu_reference(pairs, max(args.steps, 1), max(min(args.warmup, 2), 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3 * CFG["pairs"] / pairs, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "parallelism": f"dp{args.gpus}"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{pairs} of 16 pairs per step (linear in pairs), fp32 torch ops, {cpu_model_name()}"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    import preference_guided_image_captioning_alignment_b200 as pg
+    from preference_guided_image_captioning_alignment_b200 import _lib
+    from preference_guided_image_captioning_alignment_b200 import functional as F
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    _lib.check(lib.pgica_device_check())
+    B, T, d, V, beta = CFG["pairs"], CFG["seq_len"], CFG["d"], CFG["vocab"], CFG["beta"]
+    n_global = B * world
+    gen = torch.Generator().manual_seed(1234 + rank)
+    gw = torch.Generator().manual_seed(1234)  # weights are replicated
+    W = (torch.randn(V, d, generator=gw) * 0.02).to(torch.bfloat16).to(dev)
+    Wr = (torch.randn(V, d, generator=gw) * 0.02).to(torch.bfloat16).to(dev)
+    H_host = torch.randn(2 * B, T, d, generator=gen).to(torch.bfloat16).pin_memory()
+    Hr_host = torch.randn(2 * B, T, d, generator=gen).to(torch.bfloat16).pin_memory()
+    y_host = torch.randint(0, V, (2 * B, T), generator=gen).pin_memory()
+    m_host = torch.ones(2 * B, T, dtype=torch.long).pin_memory()
+    H, Hr, y, m = H_host.to(dev), Hr_host.to(dev), y_host.to(dev), m_host.to(dev)
+    one = torch.ones((), device=dev)
+    phases = ["fwd_policy", "fwd_reference", "dpo_scalar", "bwd_dH", "bwd_dW"] + (["allreduce_dW"] if world > 1 else [])
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ resident step (functional API + events)
+    def resident_step(ev=None):
+        def mark(i):
+            if ev is not None:
+                ev[i].record()
+        mark(0)
+        seq_p, lse_p, _, rl, rw, _ = F.lmhead_logprob_fwd(H, W, y, m, False)
+        mark(1)
+        seq_r = F.lmhead_logprob_fwd(Hr, Wr, y, m, False)[0]
+        mark(2)
+        loss, metrics, dpc = F.dpo_loss_fwd(seq_p[:B], seq_p[B:], seq_r[:B], seq_r[B:], beta, 0.0, n_global)
+        gseq = F.dpo_grad_seq(dpc, one)
+        mark(3)
+        # dW first so that its all-reduce overlaps the dH kernel
+        _, dw = F.lmhead_logprob_bwd(H, W, rl, rw, lse_p, gseq, False, need_dhidden=False)
+        mark(4)
+        work = None
+        if world > 1:
+            comm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(comm):
+                work = dist.all_reduce(dw, async_op=True)
+        dh, _ = F.lmhead_logprob_bwd(H, W, rl, rw, lse_p, gseq, False, need_dweight=False)
+        mark(5)
+        if world > 1:
+            work.wait()
+            torch.cuda.current_stream().wait_stream(comm)
+            packed = torch.cat([loss.reshape(1), metrics])
+            dist.all_reduce(packed)
+            mark(6)
+        return loss, dh, dw
+
+    for _ in range(max(args.warmup, 3)):
+        resident_step()
+    barrier()
+    n_marks = 7 if world > 1 else 6
+    events = [[torch.cuda.Event(enable_timing=True) for _ in range(n_marks)] for _ in range(args.steps)]
+    launches0 = lib.pgica_kernel_launches()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_begin.record()
+    for k in range(args.steps):
+        resident_step(events[k])
+    t_end.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = lib.pgica_kernel_launches() - launches0
+    elapsed_ms = t_begin.elapsed_time(t_end)
+    # order of marks: 0 start,1 after fwd_policy,2 after fwd_ref,3 after dpo,4 after dW,5 after dH,(6 after all-reduce)
+    names_in_order = ["fwd_policy", "fwd_reference", "dpo_scalar", "bwd_dW", "bwd_dH"] + (["allreduce_dW"] if world > 1 else [])
+    phase_ms = {n: statistics.mean(events[k][i].elapsed_time(events[k][i + 1]) for k in range(args.steps))
+                for i, n in enumerate(names_in_order)}
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = t.item()
+    pair_tokens_step = B * (T - 1)
+    value = pair_tokens_step * world * args.steps / (elapsed_ms * 1e-3)
+
+    # ------------------------------------------------------------------ end-to-end step (public module API)
+    head = pg.FusedDPOHead(beta=beta)
+    Wp = W.clone().requires_grad_(True)
+    Hd, Hrd = torch.empty_like(H), torch.empty_like(Hr)
+    yd, md = torch.empty_like(y), torch.empty_like(m)
+    h2d = sum(t.numel() * t.element_size() for t in (H_host, Hr_host, y_host, m_host))
+
+    def e2e_step():
+        Hd.copy_(H_host, non_blocking=True)
+        Hrd.copy_(Hr_host, non_blocking=True)
+        yd.copy_(y_host, non_blocking=True)
+        md.copy_(m_host, non_blocking=True)
+        hin = Hd.requires_grad_(True)
+        Wp.grad = None
+        loss, metrics = head.forward_stacked(hin, Wp, yd, md, Hrd, Wr, n_global)
+        loss.backward()
+        if world > 1:
+            dist.all_reduce(Wp.grad)
+        hin.requires_grad_(False)
+        return loss.item()  # device -> host read of the step's result
+
+    for _ in range(max(args.warmup, 3)):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        last_loss = e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = t.item()
+    e2e_value = pair_tokens_step * world * args.steps / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        return
+    pk = peaks()
+    rows = 2 * B * T  # rows the GEMMs actually run over (the unscored last position included)
+    flops = {"fwd_policy": 2.0 * rows * d * V, "fwd_reference": 2.0 * rows * d * V, "bwd_dH": 2.0 * rows * d * V,
+             "bwd_dW": 2.0 * rows * d * V}
+    kernels = {n: {"ms": phase_ms[n], "tflops": flops[n] / phase_ms[n] / 1e9, "algorithmic_flops": flops[n]}
+               for n in flops}
+    dom = max(flops, key=lambda n: phase_ms[n])
+    roofline = {"bound": "tensor", "kernel": {"fwd_policy": "gemm_lse_kernel", "fwd_reference": "gemm_lse_kernel",
+                                               "bwd_dH": "sgg_kernel<row>", "bwd_dW": "sgg_kernel<col>"}[dom],
+                "phase": dom, "achieved": kernels[dom]["tflops"], "peak": pk["burst"], "unit": "TFLOP/s",
+                "frac": kernels[dom]["tflops"] / pk["burst"], "peak_source": pk["source"] + " bf16 dense, burst",
+                "traffic": None,
+                "step_achieved": FLOP_PER_PAIR_TOKEN * pair_tokens_step / (elapsed_ms / args.steps) / 1e9,
+                "step_frac": FLOP_PER_PAIR_TOKEN * pair_tokens_step / (elapsed_ms / args.steps) / 1e9 / pk["burst"]}
+    cpu_val, cpu_sec, cpu_threads = time_cpu_reference(4, 2, 1)
+    extras = ntxent_extras(torch, F, dev)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "pairs_per_gpu": B, "global_pairs": n_global, "seq_len": T, "d": d, "vocab": V,
+                   "parallelism": f"dp{world}", "pair_tokens_per_step_per_gpu": pair_tokens_step,
+                   "l2": "inputs larger than L2: the step streams 2x103 MB of bf16 LM-head weights and writes a "
+                         "206 MB fp32 dW (L2 = 126 MB)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": e2e_ms / args.steps, "last_loss": last_loss},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "kernels": kernels,
+        "phase_ms": phase_ms,
+        "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cpu_threads, "kind": "port",
+                         "sample": f"2 steps of 4 pairs (of 16; linear in pairs), fp32 torch ops, {cpu_model_name()}"},
+        "ntxent": extras,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def ntxent_extras(torch, F, dev):
+    """NT-Xent pairs/s fwd+bwd: cfg1 (B=64, latency-bound) and a 4096 x 4096 single-GPU batch (D=512, tau=0.5)."""
+    out = {}
+    one = torch.ones((), device=dev)
+    for name, B in (("cfg1_B64", 64), ("B4096", 4096), ("B16384", 16384)):
+        a = torch.nn.functional.normalize(torch.randn(B, 512, device=dev), dim=-1).to(torch.bfloat16)
+        b = torch.nn.functional.normalize(torch.randn(B, 512, device=dev), dim=-1).to(torch.bfloat16)
+
+        def step():
+            lr, dg, lc = F.ntxent_fwd(a, b, 2.0)
+            loss = F.ntxent_loss(lr, dg, lc, 1.0 / B)
+            F.ntxent_bwd(a, b, 2.0, 0, lr, lc, one, 1.0 / (2 * B))
+            return loss
+
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        iters = 20 if B <= 4096 else 5
+        e0.record()
+        for _ in range(iters):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        out[name] = {"pairs_per_s": B / (ms * 1e-3), "us_per_step": ms * 1e3,
+                     "algorithmic_tflops": 6.0 * B * B * 512 / ms / 1e9}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

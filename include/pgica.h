@@ -47,6 +47,8 @@ const char* pgica_last_error(void);
 /* 0 when the current CUDA device is sm_100 (B200); PGICA_ERR_UNSUPPORTED_DEVICE otherwise. */
 int pgica_device_check(void);
 int pgica_sm_count(void);
+/* number of CUDA kernels this library has launched in this process so far */
+int64_t pgica_kernel_launches(void);
 
 /* ------------------------------------------------------------------------------------------------
  * K1/K3 core — tensor-core GEMM with a fused online log-sum-exp + target-gather epilogue.
@@ -165,9 +167,12 @@ int pgica_ntxent_coef(const float* grad, float mult, int64_t n, int64_t tgt_offs
                       int32_t* tgt, void* stream);
 
 /* F.normalize(x, p=2, dim=-1) (pkg/models/components.py:74-75, pkg/models/model.py:828-829) and its backward
- * dx = (g - xh <xh, g>) / max(||x||, eps).  y is bf16 (the tensor-core operand); x fp32 or bf16; dx fp32. */
+ * dx = (g - xh <xh, g>) / max(||x||, eps).  y is bf16 (the tensor-core operand); x fp32 or bf16; dx fp32.
+ * left3 / right3 (optional, both or neither; bf16 [rows][3*dim]) receive the two-term split of the unit rows,
+ * [hi|lo|hi] and [hi|hi|lo], so that <left3_i, right3_j> = a_hi.b_hi + a_lo.b_hi + a_hi.b_lo: the forward
+ * similarity at ~fp32 accuracy from a single bf16 tensor-core GEMM of depth 3*dim. */
 int pgica_rownorm_fwd(const void* x, int x_is_bf16, int64_t rows, int64_t dim, float eps, void* y_bf16,
-                      float* inv_norm, void* stream);
+                      float* inv_norm, void* left3_bf16, void* right3_bf16, void* stream);
 int pgica_rownorm_bwd(const void* x, int x_is_bf16, const float* inv_norm, const void* g, int g_is_bf16, int64_t rows,
                       int64_t dim, float* dx, void* stream);
 int pgica_cast_f32_to_bf16(const float* x, int64_t n, void* y_bf16, void* stream);

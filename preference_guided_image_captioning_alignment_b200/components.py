@@ -65,10 +65,9 @@ class ContrastiveLoss(nn.Module):
         if self.reduction not in ("mean", "sum"):
             # F.cross_entropy would raise on an unknown reduction string as well
             raise ValueError(f"{self.reduction} is not a valid value for reduction")
-        v, _ = ops.l2_normalize(vision_embeds, 1e-12)
-        t, _ = ops.l2_normalize(text_embeds, 1e-12)
-        loss, _, _ = ops.ntxent(v, t, 1.0 / self.similarity.effective_temperature(), self.reduction == "mean")
-        return loss
+        out = ops.ntxent_cosine(vision_embeds, text_embeds, 1.0 / self.similarity.effective_temperature(),
+                                self.reduction == "mean", 1e-12)
+        return out[0]
 
 
 class DPOPreferenceLoss(nn.Module):
@@ -94,7 +93,7 @@ class DPOPreferenceLoss(nn.Module):
             rc = rr = None
         loss, metrics, _ = ops.dpo_loss(pc, pr, rc, rr, float(self.beta), float(self.label_smoothing),
                                         int(n_global or pc.numel()))
-        return loss, metrics
+        return loss, metrics.detach()  # metrics are computed under no_grad in the reference (components.py:234)
 
 
 def compute_sequence_logprobs(logits, labels: torch.Tensor,
@@ -127,6 +126,20 @@ class FusedDPOHead(nn.Module):
         super().__init__()
         self.loss = DPOPreferenceLoss(beta, reference_free, label_smoothing)
         self.length_normalize = length_normalize
+
+    def forward_stacked(self, hidden, weight, labels, mask=None, ref_hidden=None, ref_weight=None,
+                        n_global: Optional[int] = None):
+        """Same head on pre-stacked inputs: rows [0, B) are the chosen captions, rows [B, 2B) the rejected ones
+        (the layout a concatenated policy forward produces) — no concatenation copy."""
+        ln = self.length_normalize
+        B = hidden.shape[0] // 2
+        seq = lmhead_sequence_logprobs(hidden, weight, labels, mask, ln)
+        rc = rr = None
+        if ref_weight is not None and not self.loss.reference_free:
+            with torch.no_grad():
+                rseq = lmhead_sequence_logprobs(ref_hidden, ref_weight, labels, mask, ln)
+            rc, rr = rseq[:B], rseq[B:]
+        return self.loss.forward_tensors(seq[:B], seq[B:], rc, rr, n_global)
 
     def forward(self, hidden_chosen, hidden_rejected, weight, labels_chosen, labels_rejected, mask_chosen=None,
                 mask_rejected=None, ref_hidden_chosen=None, ref_hidden_rejected=None, ref_weight=None,

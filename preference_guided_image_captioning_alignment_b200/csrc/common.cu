@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <atomic>
 #include <mutex>
 
 namespace pgica {
@@ -58,6 +59,10 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t c
   return PGICA_OK;
 }
 
+static std::atomic<unsigned long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+unsigned long long launches_so_far() { return g_launches.load(std::memory_order_relaxed); }
+
 int device_sm_count() {
   static int cached[64] = {0};
   int dev = 0;
@@ -77,6 +82,7 @@ extern "C" {
 int pgica_abi_version(void) { return PGICA_ABI_VERSION; }
 const char* pgica_last_error(void) { return pgica::get_error(); }
 int pgica_sm_count(void) { return pgica::device_sm_count(); }
+int64_t pgica_kernel_launches(void) { return (int64_t)pgica::launches_so_far(); }
 
 int pgica_device_check(void) {
   int dev = 0, major = 0, minor = 0;

@@ -38,6 +38,9 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t c
 
 int device_sm_count();
 
+// process-wide count of kernels this library has launched (bench.py reports it as `gpu_launches`)
+void count_launches(int n);
+
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -119,5 +119,6 @@ extern "C" int pgica_probe_umma(const void* a, const void* b, int64_t n, int64_t
   PGICA_CUDA_OK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kProbeSmem));
   probe_kernel<<<1, 128, kProbeSmem, static_cast<cudaStream_t>(stream)>>>(tm_a, tm_b, p);
   PGICA_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return PGICA_OK;
 }

@@ -399,5 +399,6 @@ extern "C" int pgica_softmax_grad_gemm(const void* x, const void* y, int64_t mx,
     PGICA_LAUNCH_SGG(false, true);
 #undef PGICA_LAUNCH_SGG
   PGICA_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return PGICA_OK;
 }

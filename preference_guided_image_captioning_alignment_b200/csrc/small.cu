@@ -198,7 +198,8 @@ __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p, size
 
 template <typename T>
 __global__ void rownorm_fwd_kernel(const T* __restrict__ x, int rows, int dim, float eps,
-                                   __nv_bfloat16* __restrict__ y, float* __restrict__ inv_norm) {
+                                   __nv_bfloat16* __restrict__ y, float* __restrict__ inv_norm,
+                                   __nv_bfloat16* __restrict__ left3, __nv_bfloat16* __restrict__ right3) {
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= rows) return;
@@ -209,7 +210,22 @@ __global__ void rownorm_fwd_kernel(const T* __restrict__ x, int rows, int dim, f
   }
   ss = warp_sum(ss);
   const float inv = 1.f / fmaxf(sqrtf(ss), eps);
-  for (int k = lane; k < dim; k += 32) y[(size_t)r * dim + k] = __float2bfloat16(ldf(x, (size_t)r * dim + k) * inv);
+  for (int k = lane; k < dim; k += 32) {
+    const float v = ldf(x, (size_t)r * dim + k) * inv;
+    const __nv_bfloat16 hi = __float2bfloat16(v);
+    y[(size_t)r * dim + k] = hi;
+    if (left3) {
+      // two-term bf16 split of the unit vector: <a, b> ~= a_hi.b_hi + a_lo.b_hi + a_hi.b_lo as ONE bf16 GEMM over 3*dim
+      const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
+      const size_t o = (size_t)r * 3 * dim + k;
+      left3[o] = hi;
+      left3[o + dim] = lo;
+      left3[o + 2 * dim] = hi;
+      right3[o] = hi;
+      right3[o + dim] = hi;
+      right3[o + 2 * dim] = lo;
+    }
+  }
   if (lane == 0) inv_norm[r] = inv;
 }
 
@@ -337,6 +353,7 @@ int pgica_prep_rows(const int64_t* labels, const void* mask, int mask_kind, int6
       reinterpret_cast<const long long*>(labels), mask, mask_kind, (int)nseq, (int)seqlen, (int)vocab, row_label,
       row_weight);
   PGICA_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return PGICA_OK;
 }
 
@@ -348,6 +365,7 @@ int pgica_seq_reduce(const float* lse, const float* ztgt, const float* row_weigh
   seq_reduce_kernel<<<(unsigned)ceil_div(nseq, 4), 128, 0, (cudaStream_t)stream>>>(
       lse, ztgt, row_weight, (int)nseq, (int)seqlen, length_normalize, seq_logp, nll_sum);
   PGICA_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return PGICA_OK;
 }
 
@@ -357,6 +375,7 @@ int pgica_row_coef(const float* grad_seq, const float* row_weight, int64_t nseq,
   row_coef_kernel<<<(unsigned)ceil_div(nseq, 4), 128, 0, (cudaStream_t)stream>>>(
       grad_seq, row_weight, (int)nseq, (int)seqlen, length_normalize, sign, coef);
   PGICA_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return PGICA_OK;
 }
 
@@ -370,6 +389,7 @@ int pgica_dpo_loss_fwd(const float* pc, const float* pr, const float* rc, const 
   dpo_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(pc, pr, rc, rr, (int)n, beta, label_smoothing,
                                                        1.f / (float)n_global, loss, metrics, dpc);
   PGICA_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return PGICA_OK;
 }
 
@@ -377,6 +397,7 @@ int pgica_scale_by_scalar(const float* a, const float* scalar, float mult, int64
   PGICA_REQUIRE(a && scalar && out && n > 0, "scale_by_scalar: bad argument");
   scale_by_scalar_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(a, scalar, mult, (int)n, out);
   PGICA_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return PGICA_OK;
 }
 
@@ -385,6 +406,7 @@ int pgica_ntxent_loss(const float* lse_row, const float* diag, const float* lse_
   PGICA_REQUIRE(lse_row && diag && lse_col_owned && loss && n > 0, "ntxent_loss: bad argument");
   ntxent_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(lse_row, diag, lse_col_owned, (int)n, inv_denom, loss);
   PGICA_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return PGICA_OK;
 }
 
@@ -392,6 +414,7 @@ int pgica_lse_combine(const float* parts, int64_t nparts, int64_t n, float* out,
   PGICA_REQUIRE(parts && out && nparts > 0 && n > 0, "lse_combine: bad argument");
   lse_combine_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(parts, (int)nparts, (int)n, out);
   PGICA_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return PGICA_OK;
 }
 
@@ -401,21 +424,27 @@ int pgica_ntxent_coef(const float* grad, float mult, int64_t n, int64_t tgt_offs
   ntxent_coef_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(grad, mult, (int)n, (int)tgt_offset,
                                                                                   (int)tgt_limit, coef, tgt);
   PGICA_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return PGICA_OK;
 }
 
 int pgica_rownorm_fwd(const void* x, int x_is_bf16, int64_t rows, int64_t dim, float eps, void* y_bf16,
-                      float* inv_norm, void* stream) {
+                      float* inv_norm, void* left3_bf16, void* right3_bf16, void* stream) {
   PGICA_REQUIRE(x && y_bf16 && inv_norm && rows > 0 && dim > 0, "rownorm_fwd: bad argument");
+  PGICA_REQUIRE((left3_bf16 == nullptr) == (right3_bf16 == nullptr), "rownorm_fwd: split outputs come as a pair");
+  __nv_bfloat16* l3 = static_cast<__nv_bfloat16*>(left3_bf16);
+  __nv_bfloat16* r3 = static_cast<__nv_bfloat16*>(right3_bf16);
   const unsigned grid = (unsigned)ceil_div(rows, 8);
   if (x_is_bf16)
     rownorm_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(
-        static_cast<const __nv_bfloat16*>(x), (int)rows, (int)dim, eps, static_cast<__nv_bfloat16*>(y_bf16), inv_norm);
+        static_cast<const __nv_bfloat16*>(x), (int)rows, (int)dim, eps, static_cast<__nv_bfloat16*>(y_bf16), inv_norm,
+        l3, r3);
   else
     rownorm_fwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const float*>(x), (int)rows, (int)dim,
                                                                       eps, static_cast<__nv_bfloat16*>(y_bf16),
-                                                                      inv_norm);
+                                                                      inv_norm, l3, r3);
   PGICA_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return PGICA_OK;
 }
 
@@ -438,6 +467,7 @@ int pgica_rownorm_bwd(const void* x, int x_is_bf16, const float* inv_norm, const
     rownorm_bwd_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(x), inv_norm, static_cast<const float*>(g), r, d,
                                              dx);
   PGICA_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return PGICA_OK;
 }
 
@@ -448,6 +478,7 @@ int pgica_cast_f32_to_bf16(const float* x, int64_t n, void* y_bf16, void* stream
   cast_f32_bf16_kernel<<<(unsigned)ceil_div(ceil_div(n, 4), 256), 256, 0, (cudaStream_t)stream>>>(
       x, (size_t)n, static_cast<__nv_bfloat16*>(y_bf16));
   PGICA_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return PGICA_OK;
 }
 
@@ -463,6 +494,7 @@ int pgica_logits_lse(const void* logits, int logits_is_bf16, const int32_t* row_
     logits_lse_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const float*>(logits), row_label,
                                                                      (int)seqlen, (int)vocab, lse, ztgt);
   PGICA_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return PGICA_OK;
 }
 
@@ -479,6 +511,7 @@ int pgica_logits_grad(const void* logits, int logits_is_bf16, const int32_t* row
     logits_grad_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const float*>(logits), row_label, lse,
                                                                       coef, (int)vocab, static_cast<float*>(dlogits));
   PGICA_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return PGICA_OK;
 }
 

@@ -174,6 +174,17 @@ def scale_by_scalar(a, scalar, mult=1.0):
     return out
 
 
+def dpo_grad_seq(dpc, grad_loss):
+    """[dloss/dpc * g ; -dloss/dpc * g]: upstream gradient of the stacked (chosen ++ rejected) sequence log-probs."""
+    lib = _lib.load()
+    n = dpc.numel()
+    out = torch.empty(2 * n, dtype=torch.float32, device=dpc.device)
+    g = grad_loss.reshape(1)
+    _lib.check(lib.pgica_scale_by_scalar(_p(dpc), _p(g), 1.0, n, _p(out), _stream()))
+    _lib.check(lib.pgica_scale_by_scalar(_p(dpc), _p(g), -1.0, n, ctypes.c_void_p(out.data_ptr() + 4 * n), _stream()))
+    return out
+
+
 # ----------------------------------------------------------------------------------------- Stage-1 head
 def ntxent_fwd(a, b, inv_tau, diag_offset=0):
     _need_cuda(a, b)
@@ -226,7 +237,8 @@ def ntxent_bwd(a, b, inv_tau, diag_offset, lse_row, lse_col, grad_loss, grad_mul
     return da, db
 
 
-def rownorm_fwd(x, eps=1e-12):
+def rownorm_fwd(x, eps=1e-12, split=False):
+    """-> (unit rows bf16, 1/norm, x as used[, left3, right3 when split])."""
     _need_cuda(x)
     lib = _lib.load()
     if x.dtype not in (torch.float32, torch.bfloat16):
@@ -235,9 +247,11 @@ def rownorm_fwd(x, eps=1e-12):
     rows, dim = x.shape
     y = torch.empty(rows, dim, dtype=torch.bfloat16, device=x.device)
     inv = torch.empty(rows, dtype=torch.float32, device=x.device)
+    l3 = torch.empty(rows, 3 * dim, dtype=torch.bfloat16, device=x.device) if split else None
+    r3 = torch.empty(rows, 3 * dim, dtype=torch.bfloat16, device=x.device) if split else None
     _lib.check(lib.pgica_rownorm_fwd(_p(x), 1 if x.dtype == torch.bfloat16 else 0, rows, dim, float(eps), _p(y),
-                                     _p(inv), _stream()))
-    return y, inv, x
+                                     _p(inv), _p(l3), _p(r3), _stream()))
+    return (y, inv, x, l3, r3) if split else (y, inv, x)
 
 
 def rownorm_bwd(x, inv_norm, g):

@@ -73,6 +73,49 @@ def _ntxent_backward(ctx, g_loss, g_lr, g_lc):
 ntxent.register_autograd(_ntxent_backward, setup_context=_ntxent_setup)
 
 
+# ----------------------------------------------------------------- NT-Xent on cosine similarity (normalise inside)
+@torch.library.custom_op("pgica::ntxent_cosine", mutates_args=())
+def ntxent_cosine(x: Tensor, y: Tensor, inv_tau: float, reduce_mean: bool,
+                  eps: float) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """components.ContrastiveLoss arithmetic: L2-normalise both inputs, then symmetric NT-Xent.  The unit vectors are
+    not bf16-representable, so the forward similarity uses their two-term bf16 split (one GEMM of depth 3*D): the
+    loss keeps fp32-level accuracy.  -> (loss, lse_row, lse_col, xh, yh, inv_x, inv_y)."""
+    if x.shape != y.shape or x.dim() != 2:
+        raise ValueError(f"ntxent_cosine expects two (B, D) tensors of equal shape, got {tuple(x.shape)} {tuple(y.shape)}")
+    xh, inv_x, _, xl, xr = F.rownorm_fwd(x, eps, split=True)
+    yh, inv_y, _, yl, yr = F.rownorm_fwd(y, eps, split=True)
+    lse_row, diag = F.gemm_lse(xl, yr, inv_tau, None, 0)
+    lse_col, _ = F.gemm_lse(yl, xr, inv_tau, None, 0, want_tgt=False)
+    n = x.shape[0]
+    loss = F.ntxent_loss(lse_row, diag, lse_col, 1.0 / n if reduce_mean else 1.0)
+    return loss, lse_row, lse_col, xh, yh, inv_x, inv_y
+
+
+@ntxent_cosine.register_fake
+def _(x, y, inv_tau, reduce_mean, eps):
+    n = x.shape[0]
+    return (x.new_empty((), dtype=torch.float32), _f32(n, x), _f32(n, x), torch.empty_like(x, dtype=torch.bfloat16),
+            torch.empty_like(y, dtype=torch.bfloat16), _f32(n, x), _f32(n, x))
+
+
+def _ntxc_setup(ctx, inputs, output):
+    x, y, inv_tau, reduce_mean, eps = inputs
+    _, lse_row, lse_col, xh, yh, inv_x, inv_y = output
+    ctx.save_for_backward(x, y, xh, yh, inv_x, inv_y, lse_row, lse_col)
+    ctx.inv_tau, ctx.reduce_mean = inv_tau, reduce_mean
+
+
+def _ntxc_backward(ctx, g_loss, *unused):
+    x, y, xh, yh, inv_x, inv_y, lse_row, lse_col = ctx.saved_tensors
+    dxh, dyh = ntxent_bwd(xh, yh, lse_row, lse_col, g_loss.contiguous(), ctx.inv_tau, ctx.reduce_mean)
+    dx = l2_normalize_bwd(x, inv_x, dxh)
+    dy = l2_normalize_bwd(y, inv_y, dyh)
+    return dx.to(x.dtype), dy.to(y.dtype), None, None, None
+
+
+ntxent_cosine.register_autograd(_ntxc_backward, setup_context=_ntxc_setup)
+
+
 # ------------------------------------------------------------------------------------- L2 normalisation
 @torch.library.custom_op("pgica::l2_normalize", mutates_args=())
 def l2_normalize(x: Tensor, eps: float) -> Tuple[Tensor, Tensor]:
