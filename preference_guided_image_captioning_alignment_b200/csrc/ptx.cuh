@@ -186,6 +186,14 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+// Same, but the barrier lives in another CTA of the cluster (`remote_bar` is a mapa'd shared::cluster address).
+__device__ __forceinline__ void umma_commit_remote(uint32_t remote_bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives row (lane_base + t), cols [c, c+32).

@@ -12,6 +12,8 @@
 // the 128-row tiles of Y.  Per tile: MMA1 (128x128xK) -> Z in TMEM (double-buffered) -> epilogue warps turn Z
 // into the bf16 G tile in shared memory (K-major, 128-B swizzle) -> MMA2 (128x256x128) accumulates into Out
 // with the Y tile read MN-major.  Operands stream through one TMA ring of 32-KB slots.
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -343,6 +345,20 @@ sgg_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
 }
 
 }  // namespace
+
+int sgg_cluster_dispatch(int cluster, const void* x, const void* y, int64_t mx, int64_t my, int64_t k, float scale,
+                         const float* r_lse, const float* r_coef, const int32_t* r_tgt, const float* c_lse,
+                         const float* c_coef, const int32_t* c_tgt, void* out, int out_is_bf16, cudaStream_t st);
+
+// Cluster size for the shared-recompute kernel: the largest of {4, 2} whose 256-column slices tile k exactly, unless
+// PGICA_SGG_CLUSTER overrides it (1 = single-CTA kernel in this file).
+static int choose_cluster(int64_t k) {
+  int want = 4;
+  if (const char* e = getenv("PGICA_SGG_CLUSTER")) want = atoi(e);
+  if (want >= 4 && k % 1024 == 0) return 4;
+  if (want >= 2 && k % 512 == 0) return 2;
+  return 1;
+}
 }  // namespace pgica
 
 extern "C" int pgica_softmax_grad_gemm(const void* x, const void* y, int64_t mx, int64_t my, int64_t k, float scale,
@@ -361,6 +377,10 @@ extern "C" int pgica_softmax_grad_gemm(const void* x, const void* y, int64_t mx,
   PGICA_REQUIRE(!row || r_coef, "softmax_grad_gemm: r_coef missing");
   PGICA_REQUIRE(!col || c_coef, "softmax_grad_gemm: c_coef missing");
   PGICA_REQUIRE(scale > 0.f, "softmax_grad_gemm: scale must be positive");
+  const int cluster = choose_cluster(k);
+  if (cluster > 1)
+    return sgg_cluster_dispatch(cluster, x, y, mx, my, k, scale, r_lse, r_coef, r_tgt, c_lse, c_coef, c_tgt, out,
+                                out_is_bf16, static_cast<cudaStream_t>(stream));
   SggParams p{};
   p.mx = (int)mx;
   p.my = (int)my;

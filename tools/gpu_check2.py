@@ -202,6 +202,7 @@ def case_small():
 
 
 def driver():
+    only = os.environ.get("CHECK2_ONLY", "")
     cases = [["small"],
              ["sgg", 128, 128, 256, "row", 1.0, 0], ["sgg", 128, 128, 256, "col", 1.0, 0],
              ["sgg", 128, 128, 256, "both", 1.0, 0], ["sgg", 300, 1000, 512, "both", 2.0, 0],
@@ -210,7 +211,10 @@ def driver():
              ["ntxent", 64, 512, 0.5, 1], ["ntxent", 256, 512, 0.1, 0], ["ntxent", 4096, 512, 0.5, 1],
              ["sgg", 4064, 50257, 1024, "row", 1.0, 1], ["sgg", 50257, 4064, 1024, "col", 1.0, 1],
              ["lmhead", 32, 128, 1024, 50257, 0, 1]]
+    if only:
+        cases = [c for c in cases if c[0] in only.split(",")]
     t0 = time.time()
+    print("PGICA_SGG_CLUSTER =", os.environ.get("PGICA_SGG_CLUSTER", "(default)"))
     for c in cases:
         cmd = [sys.executable, os.path.abspath(__file__)] + [str(x) for x in c]
         try:
