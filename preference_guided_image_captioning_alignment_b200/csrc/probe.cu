@@ -19,7 +19,7 @@ constexpr size_t kProbeSmem = 1024 + 64 * 1024 + 128 * 1024 + 64;
 __global__ void __launch_bounds__(128, 1)
 probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const ProbeParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + 64 * 1024;
   uint64_t* load_bar = reinterpret_cast<uint64_t*>(smem + 192 * 1024);

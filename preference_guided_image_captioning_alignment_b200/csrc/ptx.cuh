@@ -19,6 +19,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// Round a dynamic-smem base up to 1024 B (SWIZZLE_128B tiles) WITHOUT laundering the pointer through an integer,
+// so the compiler keeps emitting LDS/STS (not generic LD/ST) for accesses derived from it.
+__device__ __forceinline__ uint8_t* align_smem_1024(uint8_t* base) {
+  return base + ((1024u - (smem_u32(base) & 1023u)) & 1023u);
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -193,6 +199,19 @@ __device__ __forceinline__ void umma_commit_remote(uint32_t remote_bar) {
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+// Arrive (count 1) + expect `bytes` of async-copy traffic on a barrier that lives in ANOTHER CTA of the cluster.
+__device__ __forceinline__ void mbar_expect_tx_remote(uint32_t remote_bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(remote_bar), "r"(bytes)
+               : "memory");
+}
+// Bulk DSMEM copy: this CTA's smem -> a peer CTA's smem; completion (bytes) lands on the PEER's mbarrier.
+__device__ __forceinline__ void dsmem_bulk_copy(uint32_t remote_dst, uint32_t local_src, uint32_t bytes,
+                                                uint32_t remote_bar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   remote_dst),
+               "r"(local_src), "r"(bytes), "r"(remote_bar)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 

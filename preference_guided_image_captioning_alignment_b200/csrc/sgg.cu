@@ -51,7 +51,7 @@ template <bool kRow, bool kCol>
 __global__ void __launch_bounds__(kThreads, 1)
 sgg_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y, const SggParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* ring = smem;
   uint8_t* p_tile = smem + kSlots * kSlotBytes;
   float* s_cl = reinterpret_cast<float*>(p_tile + kPBytes);

@@ -46,7 +46,7 @@ sgg_cluster_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                    const SggcParams p) {
   constexpr int kRing = Cfg<C>::kRing;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* ring = smem;
   uint8_t* g_tiles = smem + kRing * kSlotBytes;  // C slots, slot s holds the tile produced by CTA s
   float* s_cl = reinterpret_cast<float*>(g_tiles + C * kPBytes);
@@ -56,7 +56,7 @@ sgg_cluster_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   uint64_t* empty_bar = full_bar + kRing;
   uint64_t* zfull_bar = empty_bar + kRing;  // [2]
   uint64_t* zempty_bar = zfull_bar + 2;     // [2]
-  uint64_t* gfull_bar = zempty_bar + 2;     // [C]  tile in slot s is complete (128 remote/local arrivals)
+  uint64_t* gfull_bar = zempty_bar + 2;     // [C]  tile in slot s has landed (1 arrival + 32 KB of copy bytes)
   uint64_t* gfree_bar = gfull_bar + C;      // [1]  every CTA has consumed MY slot (C commit arrivals)
   uint64_t* out_bar = gfree_bar + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(out_bar + 1);
@@ -84,7 +84,7 @@ sgg_cluster_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       mbar_init(&zfull_bar[i], 1);
       mbar_init(&zempty_bar[i], 128);
     }
-    for (int i = 0; i < C; ++i) mbar_init(&gfull_bar[i], 128);
+    for (int i = 0; i < C; ++i) mbar_init(&gfull_bar[i], 1);
     mbar_init(gfree_bar, C);
     mbar_init(out_bar, 1);
     fence_mbar_init();
@@ -230,13 +230,8 @@ sgg_cluster_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     float nl = 0.f, nc = 0.f;
     int nt = -1;
     if ((int)q < J) load_col((int)q, nl, nc, nt);
-    // my G slot (index q) in every CTA of the cluster, and every CTA's gfull[q]
-    uint32_t g_dst[C], gfull_dst[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      g_dst[c] = mapa_u32(smem_u32(g_tiles + q * kPBytes), (uint32_t)c);
-      gfull_dst[c] = mapa_u32(smem_u32(&gfull_bar[q]), (uint32_t)c);
-    }
+    // my G slot (index q): written locally, then bulk-copied over DSMEM into the same slot of every peer
+    const uint32_t g_local = smem_u32(g_tiles + q * kPBytes);
     int zb = 0;
     uint32_t zphase = 0, fphase = 0;
     for (int r = 0; r < rounds; ++r) {
@@ -284,17 +279,24 @@ sgg_cluster_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
           const uint32_t off = chunk_off + sw128_offset(row_in_blk, (ch & 1) * 4 + c4);
-          const uint32_t w0 = pack_bf16x2(g[c4 * 8 + 0], g[c4 * 8 + 1]), w1 = pack_bf16x2(g[c4 * 8 + 2], g[c4 * 8 + 3]);
-          const uint32_t w2 = pack_bf16x2(g[c4 * 8 + 4], g[c4 * 8 + 5]), w3 = pack_bf16x2(g[c4 * 8 + 6], g[c4 * 8 + 7]);
-#pragma unroll
-          for (int c = 0; c < C; ++c) st_cluster_v4(g_dst[c] + off, w0, w1, w2, w3);
+          st_smem_v4(g_local + off, pack_bf16x2(g[c4 * 8 + 0], g[c4 * 8 + 1]), pack_bf16x2(g[c4 * 8 + 2], g[c4 * 8 + 3]),
+                     pack_bf16x2(g[c4 * 8 + 4], g[c4 * 8 + 5]), pack_bf16x2(g[c4 * 8 + 6], g[c4 * 8 + 7]));
         }
       }
-      fence_proxy_async_all();  // generic-proxy writes (local and remote smem) -> visible to the async proxy (UMMA)
+      fence_proxy_async_smem();  // my generic-proxy writes -> visible to the async proxy (UMMA reads, bulk copy)
       tc_fence_before_sync();
-#pragma unroll
-      for (int c = 0; c < C; ++c) mbar_arrive_remote(gfull_dst[c]);
       mbar_arrive(&zempty_bar[zb]);
+      asm volatile("bar.sync 2, 128;" ::: "memory");  // the whole tile is in shared memory
+      if (et == 0) {
+        mbar_arrive(&gfull_bar[q]);  // local consumer
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          if (c == (int)q) continue;
+          const uint32_t rbar = mapa_u32(smem_u32(&gfull_bar[q]), (uint32_t)c);
+          mbar_expect_tx_remote(rbar, kPBytes);
+          dsmem_bulk_copy(mapa_u32(g_local, (uint32_t)c), g_local, kPBytes, rbar);
+        }
+      }
       if (++zb == 2) {
         zb = 0;
         zphase ^= 1;
