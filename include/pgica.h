@@ -173,8 +173,10 @@ int pgica_ntxent_coef(const float* grad, float mult, int64_t n, int64_t tgt_offs
  * similarity at ~fp32 accuracy from a single bf16 tensor-core GEMM of depth 3*dim. */
 int pgica_rownorm_fwd(const void* x, int x_is_bf16, int64_t rows, int64_t dim, float eps, void* y_bf16,
                       float* inv_norm, void* left3_bf16, void* right3_bf16, void* stream);
+/* g: [rows][g_pitch]; the upstream gradient is g[:, 0:dim], plus g[:, g_second:g_second+dim] when g_second >= 0
+ * (the two column blocks that a softmax-gradient GEMM over the split operand [hi|hi|lo] yields for hi and lo). */
 int pgica_rownorm_bwd(const void* x, int x_is_bf16, const float* inv_norm, const void* g, int g_is_bf16, int64_t rows,
-                      int64_t dim, float* dx, void* stream);
+                      int64_t dim, int64_t g_pitch, int64_t g_second, float* dx, void* stream);
 int pgica_cast_f32_to_bf16(const float* x, int64_t n, void* y_bf16, void* stream);
 
 /* Plumbing pieces of the Stage-2 head, exported so the parity tests can pin them bit-exactly:

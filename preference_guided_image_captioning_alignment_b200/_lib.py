@@ -10,7 +10,8 @@ import re
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpgica.so")
+# PGICA_LIB_PATH selects another build of the same ABI (tools/ use it for the -DPGICA_TRACE diagnostics build)
+LIB_PATH = os.environ.get("PGICA_LIB_PATH") or os.path.join(_HERE, "libpgica.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "pgica.h")
 
 _lock = threading.Lock()

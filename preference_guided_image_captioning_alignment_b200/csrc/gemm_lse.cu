@@ -84,55 +84,58 @@ gemm_lse_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = t_begin; t < t_end; ++t) {
-        const int m_blk = t / p.num_n_tiles;
-        const int n_tile = t - m_blk * p.num_n_tiles;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // TMA producer: the whole warp walks the tile schedule, one elected lane issues the copies
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      const int m_blk = t / p.num_n_tiles;
+      const int n_tile = t - m_blk * p.num_n_tiles;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(&full_bar[stage], kABytes + kBBytes);
           tma_load_2d(smem_a + stage * kABytes, &tm_a, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
           tma_load_2d(smem_b + stage * kBBytes, &tm_b, &full_bar[stage], kb * kBlockK, n_tile * kBlockN);
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, kBlockN, 0, 0);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      for (int t = t_begin; t < t_end; ++t) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+    // Whole warp walks the pipeline (warp-uniform control flow keeps descriptors in uniform registers); one elected
+    // lane issues the tcgen05 instructions.
+    constexpr uint32_t idesc = make_idesc_bf16(kBlockM, kBlockN, 0, 0);
+    const uint64_t desc_hi = make_smem_desc(0, 16, 1024);  // everything but the start address
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + acc * kBlockN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + acc * kBlockN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after_sync();
-          const uint32_t a_addr = smem_u32(smem_a + stage * kABytes);
-          const uint32_t b_addr = smem_u32(smem_b + stage * kBBytes);
+        if (elect_one()) {
+          const uint64_t da = desc_hi | ((smem_u32(smem_a + stage * kABytes) >> 4) & 0x3FFF);
+          const uint64_t db = desc_hi | ((smem_u32(smem_b + stage * kBBytes) >> 4) & 0x3FFF);
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            const uint64_t da = make_smem_desc(a_addr + k * kUmmaK * 2, 16, 1024);
-            const uint64_t db = make_smem_desc(b_addr + k * kUmmaK * 2, 16, 1024);
-            umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            umma_bf16_ss(d_tmem, da + k * (kUmmaK * 2 / 16), db + k * (kUmmaK * 2 / 16), idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+          if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
         }
-        umma_commit(&tfull_bar[acc]);
-        if (++acc == kAccStages) {
-          acc = 0;
-          acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
         }
+      }
+      if (++acc == kAccStages) {
+        acc = 0;
+        acc_phase ^= 1;
       }
     }
   } else if (warp >= kEpilogueWarp0) {

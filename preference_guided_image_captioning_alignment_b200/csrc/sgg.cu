@@ -98,117 +98,128 @@ sgg_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- TMA producer
-      int slot = 0;
-      uint32_t phase = 0;
-      auto advance = [&]() {
-        if (++slot == kSlots) {
-          slot = 0;
-          phase ^= 1;
-        }
-      };
-      auto load_mma1 = [&](int j) {
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[slot], phase ^ 1);
+    // ------------------------------------------------------------------ TMA producer
+    // (whole warp walks the schedule so that control flow stays warp-uniform; one elected lane issues the copies)
+    int slot = 0;
+    uint32_t phase = 0;
+    auto advance = [&]() {
+      if (++slot == kSlots) {
+        slot = 0;
+        phase ^= 1;
+      }
+    };
+    auto load_mma1 = [&](int j) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[slot], phase ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(&full_bar[slot], kSlotBytes);
           uint8_t* dst = ring + slot * kSlotBytes;
           tma_load_2d(dst, &tm_x, &full_bar[slot], kb * kBK, m_blk * kBM);
           tma_load_2d(dst + kChunkBytes, &tm_y, &full_bar[slot], kb * kBK, j * kBT);
-          advance();
         }
-        if (pad) {  // keep every item an even number of slots
-          mbar_wait(&empty_bar[slot], phase ^ 1);
-          mbar_expect_tx(&full_bar[slot], 0);
-          advance();
-        }
-      };
-      auto load_mma2 = [&](int j) {  // Y[j tile, q*256 .. +256) as four [128][64] boxes in two slots
-        for (int h = 0; h < 2; ++h) {
-          mbar_wait(&empty_bar[slot], phase ^ 1);
+        __syncwarp();
+        advance();
+      }
+      if (pad) {  // keep every item an even number of slots
+        mbar_wait(&empty_bar[slot], phase ^ 1);
+        if (elect_one()) mbar_expect_tx(&full_bar[slot], 0);
+        __syncwarp();
+        advance();
+      }
+    };
+    auto load_mma2 = [&](int j) {  // Y[j tile, q*256 .. +256) as four [128][64] boxes in two slots
+      for (int h = 0; h < 2; ++h) {
+        mbar_wait(&empty_bar[slot], phase ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(&full_bar[slot], kSlotBytes);
           uint8_t* dst = ring + slot * kSlotBytes;
           tma_load_2d(dst, &tm_y, &full_bar[slot], q * kBD + (2 * h) * kBK, j * kBT);
           tma_load_2d(dst + kChunkBytes, &tm_y, &full_bar[slot], q * kBD + (2 * h + 1) * kBK, j * kBT);
-          advance();
         }
-      };
-      for (int j = 0; j < J; ++j) {
-        load_mma1(j);
-        if (j > 0) load_mma2(j - 1);
+        __syncwarp();
+        advance();
       }
-      load_mma2(J - 1);
+    };
+    for (int j = 0; j < J; ++j) {
+      load_mma1(j);
+      if (j > 0) load_mma2(j - 1);
     }
+    load_mma2(J - 1);
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- MMA issuer
-      constexpr uint32_t idesc1 = make_idesc_bf16(kBM, kBT, 0, 0);
-      constexpr uint32_t idesc2 = make_idesc_bf16(kBM, kBD, 0, 1);
-      int slot = 0;
-      uint32_t phase = 0;
-      auto advance = [&]() {
-        if (++slot == kSlots) {
-          slot = 0;
-          phase ^= 1;
-        }
-      };
-      uint32_t pphase = 0;
-      const uint32_t p_addr = smem_u32(p_tile);
-      auto mma2 = [&](int j) {
-        mbar_wait(pfull_bar, pphase);
-        pphase ^= 1;
-        mbar_wait(&full_bar[slot], phase);
-        const int slot2 = slot + 1;  // never wraps: items are even-sized, ring is even
-        mbar_wait(&full_bar[slot2], phase);
-        tc_fence_after_sync();
+    // ------------------------------------------------------------------ MMA issuer (whole warp, one elected lane)
+    constexpr uint32_t idesc1 = make_idesc_bf16(kBM, kBT, 0, 0);
+    constexpr uint32_t idesc2 = make_idesc_bf16(kBM, kBD, 0, 1);
+    const uint64_t desc_k = make_smem_desc(0, 16, 1024);            // K-major operand, start address 0
+    const uint64_t desc_mn = make_smem_desc(0, kChunkBytes, 1024);  // MN-major operand (Y tile of MMA2)
+    int slot = 0;
+    uint32_t phase = 0;
+    auto advance = [&]() {
+      if (++slot == kSlots) {
+        slot = 0;
+        phase ^= 1;
+      }
+    };
+    uint32_t pphase = 0;
+    const uint32_t p_addr = smem_u32(p_tile);
+    auto mma2 = [&](int j) {
+      mbar_wait(pfull_bar, pphase);
+      pphase ^= 1;
+      mbar_wait(&full_bar[slot], phase);
+      const int slot2 = slot + 1;  // never wraps: items are even-sized, ring is even
+      mbar_wait(&full_bar[slot2], phase);
+      tc_fence_after_sync();
+      if (elect_one()) {
         const uint32_t y_addr = smem_u32(ring + slot * kSlotBytes);
+        const uint64_t dg = desc_k | ((p_addr >> 4) & 0x3FFF);
+        const uint64_t dy = desc_mn | ((y_addr >> 4) & 0x3FFF);
 #pragma unroll
-        for (int ks = 0; ks < kBT / 16; ++ks) {
-          const uint64_t da = make_smem_desc(p_addr + (ks >> 2) * kChunkBytes + (ks & 3) * 32, 16, 1024);
-          const uint64_t db = make_smem_desc(y_addr + ks * 16 * 128, kChunkBytes, 1024);
-          umma_bf16_ss(tmem_base + kTmemOut, da, db, idesc2, (j | ks) != 0 ? 1u : 0u);
-        }
+        for (int ks = 0; ks < kBT / 16; ++ks)
+          umma_bf16_ss(tmem_base + kTmemOut, dg + (ks >> 2) * (kChunkBytes >> 4) + (ks & 3) * 2,
+                       dy + ks * (16 * 128 >> 4), idesc2, (j | ks) != 0 ? 1u : 0u);
         umma_commit(&empty_bar[slot]);
         umma_commit(&empty_bar[slot2]);
         umma_commit(pfree_bar);
-        advance();
-        advance();
-      };
-      int zb = 0;
-      uint32_t zphase = 0;
-      for (int j = 0; j < J; ++j) {
-        mbar_wait(&zempty_bar[zb], zphase ^ 1);
-        tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + kTmemZ + zb * kBT;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[slot], phase);
-          tc_fence_after_sync();
-          const uint32_t x_addr = smem_u32(ring + slot * kSlotBytes);
-          const uint32_t y_addr = x_addr + kChunkBytes;
-#pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            const uint64_t da = make_smem_desc(x_addr + k * 32, 16, 1024);
-            const uint64_t db = make_smem_desc(y_addr + k * 32, 16, 1024);
-            umma_bf16_ss(d_tmem, da, db, idesc1, (kb | k) != 0 ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[slot]);
-          advance();
-        }
-        if (pad) {
-          mbar_wait(&full_bar[slot], phase);
-          mbar_arrive(&empty_bar[slot]);
-          advance();
-        }
-        umma_commit(&zfull_bar[zb]);
-        if (++zb == 2) {
-          zb = 0;
-          zphase ^= 1;
-        }
-        if (j > 0) mma2(j - 1);
       }
-      mma2(J - 1);
-      umma_commit(out_bar);
+      __syncwarp();
+      advance();
+      advance();
+    };
+    int zb = 0;
+    uint32_t zphase = 0;
+    for (int j = 0; j < J; ++j) {
+      mbar_wait(&zempty_bar[zb], zphase ^ 1);
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + kTmemZ + zb * kBT;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[slot], phase);
+        tc_fence_after_sync();
+        if (elect_one()) {
+          const uint32_t x_addr = smem_u32(ring + slot * kSlotBytes);
+          const uint64_t da = desc_k | ((x_addr >> 4) & 0x3FFF);
+          const uint64_t db = desc_k | (((x_addr + kChunkBytes) >> 4) & 0x3FFF);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc1, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[slot]);
+          if (kb == num_kb - 1) umma_commit(&zfull_bar[zb]);
+        }
+        __syncwarp();
+        advance();
+      }
+      if (pad) {
+        mbar_wait(&full_bar[slot], phase);
+        if (elect_one()) mbar_arrive(&empty_bar[slot]);
+        __syncwarp();
+        advance();
+      }
+      if (++zb == 2) {
+        zb = 0;
+        zphase ^= 1;
+      }
+      if (j > 0) mma2(j - 1);
     }
+    mma2(J - 1);
+    if (elect_one()) umma_commit(out_bar);
+    __syncwarp();
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue: Z -> G (bf16, smem)
     const int quarter = warp & 3;

@@ -22,6 +22,40 @@ constexpr int kThreads = 256;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr uint32_t kTmemOut = 0, kTmemZ = 256;
 
+#ifdef PGICA_TRACE
+// Debug build only (-DPGICA_TRACE): per-CTA cycle accounting of the three roles, [grid][16] int64.
+__device__ long long* g_sgg_trace = nullptr;
+__device__ __forceinline__ long long trace_now() {
+#ifdef __CUDA_ARCH__
+  return clock64();
+#else
+  return 0;
+#endif
+}
+struct Lap {
+  long long t, acc[6];
+  __device__ Lap() : t(trace_now()) {
+    for (int i = 0; i < 6; ++i) acc[i] = 0;
+  }
+  __device__ void operator()(int i) {
+    const long long n = trace_now();
+    acc[i] += n - t;
+    t = n;
+  }
+  __device__ void flush(int base, int n) {
+    if (g_sgg_trace)
+      for (int i = 0; i < n; ++i) g_sgg_trace[(size_t)blockIdx.x * 16 + base + i] = acc[i];
+  }
+};
+#define LAP(i) lap(i)
+#define LAP_DECL Lap lap
+#define LAP_FLUSH(base, n) lap.flush(base, n)
+#else
+#define LAP(i) ((void)0)
+#define LAP_DECL ((void)0)
+#define LAP_FLUSH(base, n) ((void)0)
+#endif
+
 struct SggcParams {
   int mx, my, k, num_tiles, passes, ldo, out_bf16;
   float c;
@@ -97,111 +131,140 @@ sgg_cluster_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- TMA producer
-      int slot = 0;
-      uint32_t phase = 0;
-      auto advance = [&]() {
-        if (++slot == kRing) {
-          slot = 0;
-          phase ^= 1;
-        }
-      };
-      for (int r = 0; r <= rounds; ++r) {
-        const int own = r * C + (int)q;
-        if (own < J) {
-          for (int kb = 0; kb < num_kb; ++kb) {
-            mbar_wait(&empty_bar[slot], phase ^ 1);
+    // ------------------------------------------------------------------ TMA producer
+    // The whole warp walks the schedule (warp-uniform control flow, so addresses and coordinates stay in uniform
+    // registers); one elected lane issues the copies.
+    int slot = 0;
+    uint32_t phase = 0;
+    auto advance = [&]() {
+      if (++slot == kRing) {
+        slot = 0;
+        phase ^= 1;
+      }
+    };
+    LAP_DECL;
+    for (int r = 0; r <= rounds; ++r) {
+      const int own = r * C + (int)q;
+      if (own < J) {
+        for (int kb = 0; kb < num_kb; ++kb) {
+          LAP(0);
+          mbar_wait(&empty_bar[slot], phase ^ 1);
+          LAP(1);
+          if (elect_one()) {
             mbar_expect_tx(&full_bar[slot], kSlotBytes);
             uint8_t* dst = ring + slot * kSlotBytes;
             tma_load_2d(dst, &tm_x, &full_bar[slot], kb * kBK, m_blk * kBM);
             tma_load_2d(dst + kChunkBytes, &tm_y, &full_bar[slot], kb * kBK, own * kBT);
-            advance();
           }
+          __syncwarp();
+          advance();
         }
-        if (r > 0) {
-          const int t_end = min(r * C, J);
-          for (int t = (r - 1) * C; t < t_end; ++t) {
-            for (int h = 0; h < 2; ++h) {  // Y[t tile, out_col0 + h*128 .. +128): two [128][64] boxes per slot
-              mbar_wait(&empty_bar[slot], phase ^ 1);
+      }
+      if (r > 0) {
+        const int t_end = min(r * C, J);
+        for (int t = (r - 1) * C; t < t_end; ++t) {
+          for (int h = 0; h < 2; ++h) {  // Y[t tile, out_col0 + h*128 .. +128): two [128][64] boxes per slot
+            LAP(0);
+            mbar_wait(&empty_bar[slot], phase ^ 1);
+            LAP(2);
+            if (elect_one()) {
               mbar_expect_tx(&full_bar[slot], kSlotBytes);
               uint8_t* dst = ring + slot * kSlotBytes;
               tma_load_2d(dst, &tm_y, &full_bar[slot], out_col0 + h * 128, t * kBT);
               tma_load_2d(dst + kChunkBytes, &tm_y, &full_bar[slot], out_col0 + h * 128 + 64, t * kBT);
-              advance();
             }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- MMA issuer
-      constexpr uint32_t idesc1 = make_idesc_bf16(kBM, kBT, 0, 0);
-      constexpr uint32_t idesc2 = make_idesc_bf16(kBM, 128, 0, 1);
-      int slot = 0;
-      uint32_t phase = 0;
-      auto advance = [&]() {
-        if (++slot == kRing) {
-          slot = 0;
-          phase ^= 1;
-        }
-      };
-      int zb = 0;
-      uint32_t zphase = 0;
-      for (int r = 0; r <= rounds; ++r) {
-        const int own = r * C + (int)q;
-        if (own < J) {
-          mbar_wait(&zempty_bar[zb], zphase ^ 1);
-          tc_fence_after_sync();
-          const uint32_t d_tmem = tmem_base + kTmemZ + zb * kBT;
-          for (int kb = 0; kb < num_kb; ++kb) {
-            mbar_wait(&full_bar[slot], phase);
-            tc_fence_after_sync();
-            const uint32_t x_addr = smem_u32(ring + slot * kSlotBytes);
-            const uint32_t y_addr = x_addr + kChunkBytes;
-#pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) {
-              const uint64_t da = make_smem_desc(x_addr + k * 32, 16, 1024);
-              const uint64_t db = make_smem_desc(y_addr + k * 32, 16, 1024);
-              umma_bf16_ss(d_tmem, da, db, idesc1, (kb | k) != 0 ? 1u : 0u);
-            }
-            umma_commit(&empty_bar[slot]);
+            __syncwarp();
             advance();
           }
-          umma_commit(&zfull_bar[zb]);
-          if (++zb == 2) {
-            zb = 0;
-            zphase ^= 1;
-          }
         }
-        if (r > 0) {
-          const int t_end = min(r * C, J);
-          const uint32_t gphase = (uint32_t)(r - 1) & 1u;
-          for (int t = (r - 1) * C; t < t_end; ++t) {
-            const int s = t - (r - 1) * C;  // producer CTA == G slot
-            mbar_wait_cluster(&gfull_bar[s], gphase);
-            const uint32_t g_addr = smem_u32(g_tiles + s * kPBytes);
-            for (int h = 0; h < 2; ++h) {
-              mbar_wait(&full_bar[slot], phase);
-              tc_fence_after_sync();
-              const uint32_t y_addr = smem_u32(ring + slot * kSlotBytes);
+      }
+    }
+    LAP(0);
+    if (lane == 0) LAP_FLUSH(0, 3);
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp, one elected lane)
+    constexpr uint32_t idesc1 = make_idesc_bf16(kBM, kBT, 0, 0);
+    constexpr uint32_t idesc2 = make_idesc_bf16(kBM, 128, 0, 1);
+    const uint64_t desc_k = make_smem_desc(0, 16, 1024);            // K-major operand, start address 0
+    const uint64_t desc_mn = make_smem_desc(0, kChunkBytes, 1024);  // MN-major operand (Y tile of MMA2)
+    const uint32_t gfree_remote0 = smem_u32(gfree_bar);
+    int slot = 0;
+    uint32_t phase = 0;
+    auto advance = [&]() {
+      if (++slot == kRing) {
+        slot = 0;
+        phase ^= 1;
+      }
+    };
+    int zb = 0;
+    uint32_t zphase = 0;
+    LAP_DECL;
+    for (int r = 0; r <= rounds; ++r) {
+      const int own = r * C + (int)q;
+      if (own < J) {
+        LAP(0);
+        mbar_wait(&zempty_bar[zb], zphase ^ 1);
+        LAP(1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + kTmemZ + zb * kBT;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          LAP(0);
+          mbar_wait(&full_bar[slot], phase);
+          LAP(2);
+          tc_fence_after_sync();
+          if (elect_one()) {
+            const uint32_t x_addr = smem_u32(ring + slot * kSlotBytes);
+            const uint64_t da = desc_k | ((x_addr >> 4) & 0x3FFF);
+            const uint64_t db = desc_k | (((x_addr + kChunkBytes) >> 4) & 0x3FFF);
 #pragma unroll
-              for (int ks = 0; ks < kBT / 16; ++ks) {
-                const uint64_t da = make_smem_desc(g_addr + (ks >> 2) * kChunkBytes + (ks & 3) * 32, 16, 1024);
-                const uint64_t db = make_smem_desc(y_addr + ks * 16 * 128, kChunkBytes, 1024);
-                umma_bf16_ss(tmem_base + kTmemOut + h * 128, da, db, idesc2, (t | ks) != 0 ? 1u : 0u);
-              }
+            for (int k = 0; k < kBK / 16; ++k) umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc1, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&empty_bar[slot]);
+            if (kb == num_kb - 1) umma_commit(&zfull_bar[zb]);
+          }
+          __syncwarp();
+          advance();
+        }
+        if (++zb == 2) {
+          zb = 0;
+          zphase ^= 1;
+        }
+      }
+      if (r > 0) {
+        const int t_end = min(r * C, J);
+        const uint32_t gphase = (uint32_t)(r - 1) & 1u;
+        for (int t = (r - 1) * C; t < t_end; ++t) {
+          const int s = t - (r - 1) * C;  // producer CTA == G slot
+          LAP(0);
+          mbar_wait_cluster(&gfull_bar[s], gphase);
+          LAP(3);
+          const uint32_t g_addr = smem_u32(g_tiles + s * kPBytes);
+          for (int h = 0; h < 2; ++h) {
+            LAP(0);
+            mbar_wait(&full_bar[slot], phase);
+            LAP(4);
+            tc_fence_after_sync();
+            if (elect_one()) {
+              const uint32_t y_addr = smem_u32(ring + slot * kSlotBytes);
+              const uint64_t dg = desc_k | ((g_addr >> 4) & 0x3FFF);
+              const uint64_t dy = desc_mn | ((y_addr >> 4) & 0x3FFF);
+#pragma unroll
+              for (int ks = 0; ks < kBT / 16; ++ks)
+                umma_bf16_ss(tmem_base + kTmemOut + h * 128, dg + (ks >> 2) * (kChunkBytes >> 4) + (ks & 3) * 2,
+                             dy + ks * (16 * 128 >> 4), idesc2, (t | ks) != 0 ? 1u : 0u);
               umma_commit(&empty_bar[slot]);
-              advance();
+              // after the second half: tell the producer of slot s that this CTA is done reading it
+              if (h == 1) umma_commit_remote(mapa_u32(gfree_remote0, (uint32_t)s));
             }
-            // tell the producer of slot s that this CTA is done reading it
-            umma_commit_remote(mapa_u32(smem_u32(gfree_bar), (uint32_t)s));
+            __syncwarp();
+            advance();
           }
         }
       }
-      umma_commit(out_bar);
     }
+    if (elect_one()) umma_commit(out_bar);
+    __syncwarp();
+    LAP(0);
+    if (lane == 0) LAP_FLUSH(3, 5);
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue for this CTA's own tiles
     const int quarter = warp & 3;
@@ -234,9 +297,11 @@ sgg_cluster_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     const uint32_t g_local = smem_u32(g_tiles + q * kPBytes);
     int zb = 0;
     uint32_t zphase = 0, fphase = 0;
+    LAP_DECL;
     for (int r = 0; r < rounds; ++r) {
       const int own = r * C + (int)q;
       if (own >= J) break;
+      LAP(0);
       if (kCol) {
         s_cl[et] = nl;
         s_cc[et] = nc;
@@ -245,8 +310,10 @@ sgg_cluster_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         if (own + C < J) load_col(own + C, nl, nc, nt);
       }
       mbar_wait(&zfull_bar[zb], zphase);
+      LAP(1);
       tc_fence_after_sync();
       mbar_wait_cluster(gfree_bar, fphase ^ 1);  // every CTA has finished MMA2 on my previous tile
+      LAP(2);
       fphase ^= 1;
       const int col0 = own * kBT;
       const int rrel = rt - col0;
@@ -286,7 +353,9 @@ sgg_cluster_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       fence_proxy_async_smem();  // my generic-proxy writes -> visible to the async proxy (UMMA reads, bulk copy)
       tc_fence_before_sync();
       mbar_arrive(&zempty_bar[zb]);
+      LAP(3);
       asm volatile("bar.sync 2, 128;" ::: "memory");  // the whole tile is in shared memory
+      LAP(4);
       if (et == 0) {
         mbar_arrive(&gfull_bar[q]);  // local consumer
 #pragma unroll
@@ -305,6 +374,8 @@ sgg_cluster_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     }
     // every peer's "done with your slot" commit must have landed before this CTA may exit
     if ((int)q < J) mbar_wait_cluster(gfree_bar, fphase ^ 1);
+    LAP(0);
+    if (et == 0) LAP_FLUSH(8, 5);
     // ------------------------------------------------------------------ final: Out slice (TMEM) -> global
     mbar_wait(out_bar, 0);
     tc_fence_after_sync();
@@ -363,6 +434,13 @@ int launch(const CUtensorMap& tm_x, const CUtensorMap& tm_y, const SggcParams& p
 }
 
 }  // namespace
+
+#ifdef PGICA_TRACE
+extern "C" int pgica_debug_set_sgg_trace(void* buf) {
+  long long* p = static_cast<long long*>(buf);
+  return cudaMemcpyToSymbol(g_sgg_trace, &p, sizeof(p)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 // Called by pgica_softmax_grad_gemm when k is a multiple of 256*C.  Returns PGICA_OK or an error code.
 int sgg_cluster_dispatch(int cluster, const void* x, const void* y, int64_t mx, int64_t my, int64_t k, float scale,

@@ -229,20 +229,25 @@ __global__ void rownorm_fwd_kernel(const T* __restrict__ x, int rows, int dim, f
   if (lane == 0) inv_norm[r] = inv;
 }
 
-// dx = (g - xh * <xh, g>) * inv_norm with xh = x * inv_norm recomputed in fp32.  g is fp32 or bf16.
+// dx = (g - xh * <xh, g>) * inv_norm with xh = x * inv_norm recomputed in fp32.  g is fp32 or bf16, rows `g_pitch`
+// elements apart; with g_second >= 0 the upstream gradient is g[:, 0:dim] + g[:, g_second:g_second+dim] (the two
+// column blocks a softmax-gradient GEMM over split operands [hi|hi|lo] produces).
 template <typename TX, typename TG>
 __global__ void rownorm_bwd_kernel(const TX* __restrict__ x, const float* __restrict__ inv_norm,
-                                   const TG* __restrict__ g, int rows, int dim, float* __restrict__ dx) {
+                                   const TG* __restrict__ g, int rows, int dim, int64_t g_pitch, int64_t g_second,
+                                   float* __restrict__ dx) {
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= rows) return;
   const float inv = inv_norm[r];
+  const TG* gr = g + (size_t)r * g_pitch;
+  auto gv = [&](int k) { return g_second >= 0 ? ldf(gr, (size_t)k) + ldf(gr, (size_t)(g_second + k)) : ldf(gr, (size_t)k); };
   float dot = 0.f;
-  for (int k = lane; k < dim; k += 32) dot = fmaf(ldf(x, (size_t)r * dim + k) * inv, ldf(g, (size_t)r * dim + k), dot);
+  for (int k = lane; k < dim; k += 32) dot = fmaf(ldf(x, (size_t)r * dim + k) * inv, gv(k), dot);
   dot = warp_sum(dot);
   for (int k = lane; k < dim; k += 32) {
     const size_t i = (size_t)r * dim + k;
-    dx[i] = (ldf(g, i) - ldf(x, i) * inv * dot) * inv;
+    dx[i] = (gv(k) - ldf(x, i) * inv * dot) * inv;
   }
 }
 
@@ -449,23 +454,26 @@ int pgica_rownorm_fwd(const void* x, int x_is_bf16, int64_t rows, int64_t dim, f
 }
 
 int pgica_rownorm_bwd(const void* x, int x_is_bf16, const float* inv_norm, const void* g, int g_is_bf16, int64_t rows,
-                      int64_t dim, float* dx, void* stream) {
+                      int64_t dim, int64_t g_pitch, int64_t g_second, float* dx, void* stream) {
   PGICA_REQUIRE(x && inv_norm && g && dx && rows > 0 && dim > 0, "rownorm_bwd: bad argument");
+  PGICA_REQUIRE(g_pitch >= dim && (g_second < 0 || g_second + dim <= g_pitch),
+                "rownorm_bwd: gradient layout (pitch %lld, second block at %lld) does not hold %lld columns",
+                (long long)g_pitch, (long long)g_second, (long long)dim);
   const unsigned grid = (unsigned)ceil_div(rows, 8);
   cudaStream_t st = (cudaStream_t)stream;
   const int r = (int)rows, d = (int)dim;
   if (x_is_bf16 && g_is_bf16)
     rownorm_bwd_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), inv_norm,
-                                             static_cast<const __nv_bfloat16*>(g), r, d, dx);
+                                             static_cast<const __nv_bfloat16*>(g), r, d, g_pitch, g_second, dx);
   else if (x_is_bf16)
     rownorm_bwd_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), inv_norm,
-                                             static_cast<const float*>(g), r, d, dx);
+                                             static_cast<const float*>(g), r, d, g_pitch, g_second, dx);
   else if (g_is_bf16)
     rownorm_bwd_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(x), inv_norm,
-                                             static_cast<const __nv_bfloat16*>(g), r, d, dx);
+                                             static_cast<const __nv_bfloat16*>(g), r, d, g_pitch, g_second, dx);
   else
     rownorm_bwd_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(x), inv_norm, static_cast<const float*>(g), r, d,
-                                             dx);
+                                             g_pitch, g_second, dx);
   PGICA_CUDA_OK(cudaGetLastError());
   count_launches(1);
   return PGICA_OK;

@@ -254,13 +254,15 @@ def rownorm_fwd(x, eps=1e-12, split=False):
     return (y, inv, x, l3, r3) if split else (y, inv, x)
 
 
-def rownorm_bwd(x, inv_norm, g):
+def rownorm_bwd(x, inv_norm, g, second=-1):
+    """g is (rows, dim), or (rows, pitch) with the gradient in columns [0, dim) + [second, second + dim)."""
     lib = _lib.load()
     g = g.contiguous()
     rows, dim = x.shape
     dx = torch.empty(rows, dim, dtype=torch.float32, device=x.device)
     _lib.check(lib.pgica_rownorm_bwd(_p(x), 1 if x.dtype == torch.bfloat16 else 0, _p(inv_norm), _p(g),
-                                     1 if g.dtype == torch.bfloat16 else 0, rows, dim, _p(dx), _stream()))
+                                     1 if g.dtype == torch.bfloat16 else 0, rows, dim, g.shape[1], int(second),
+                                     _p(dx), _stream()))
     return dx
 
 

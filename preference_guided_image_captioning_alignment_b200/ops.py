@@ -76,40 +76,62 @@ ntxent.register_autograd(_ntxent_backward, setup_context=_ntxent_setup)
 # ----------------------------------------------------------------- NT-Xent on cosine similarity (normalise inside)
 @torch.library.custom_op("pgica::ntxent_cosine", mutates_args=())
 def ntxent_cosine(x: Tensor, y: Tensor, inv_tau: float, reduce_mean: bool,
-                  eps: float) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+                  eps: float) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     """components.ContrastiveLoss arithmetic: L2-normalise both inputs, then symmetric NT-Xent.  The unit vectors are
-    not bf16-representable, so the forward similarity uses their two-term bf16 split (one GEMM of depth 3*D): the
-    loss keeps fp32-level accuracy.  -> (loss, lse_row, lse_col, xh, yh, inv_x, inv_y)."""
+    not bf16-representable, so the similarity uses their two-term bf16 split (one GEMM of depth 3*D): the loss keeps
+    fp32-level accuracy, and the backward recomputes exactly the same logits from the same split operands.
+    -> (loss, lse_row, lse_col, x_left3, x_right3, y_left3, y_right3, inv_x, inv_y)."""
     if x.shape != y.shape or x.dim() != 2:
         raise ValueError(f"ntxent_cosine expects two (B, D) tensors of equal shape, got {tuple(x.shape)} {tuple(y.shape)}")
-    xh, inv_x, _, xl, xr = F.rownorm_fwd(x, eps, split=True)
-    yh, inv_y, _, yl, yr = F.rownorm_fwd(y, eps, split=True)
+    _, inv_x, _, xl, xr = F.rownorm_fwd(x, eps, split=True)
+    _, inv_y, _, yl, yr = F.rownorm_fwd(y, eps, split=True)
     lse_row, diag = F.gemm_lse(xl, yr, inv_tau, None, 0)
     lse_col, _ = F.gemm_lse(yl, xr, inv_tau, None, 0, want_tgt=False)
     n = x.shape[0]
     loss = F.ntxent_loss(lse_row, diag, lse_col, 1.0 / n if reduce_mean else 1.0)
-    return loss, lse_row, lse_col, xh, yh, inv_x, inv_y
+    return loss, lse_row, lse_col, xl, xr, yl, yr, inv_x, inv_y
 
 
 @ntxent_cosine.register_fake
 def _(x, y, inv_tau, reduce_mean, eps):
-    n = x.shape[0]
-    return (x.new_empty((), dtype=torch.float32), _f32(n, x), _f32(n, x), torch.empty_like(x, dtype=torch.bfloat16),
-            torch.empty_like(y, dtype=torch.bfloat16), _f32(n, x), _f32(n, x))
+    n, d = x.shape
+    s3 = lambda: torch.empty((n, 3 * d), dtype=torch.bfloat16, device=x.device)
+    return (x.new_empty((), dtype=torch.float32), _f32(n, x), _f32(n, x), s3(), s3(), s3(), s3(), _f32(n, x),
+            _f32(n, x))
+
+
+@torch.library.custom_op("pgica::ntxent_cosine_bwd", mutates_args=())
+def ntxent_cosine_bwd(x: Tensor, y: Tensor, xl: Tensor, xr: Tensor, yl: Tensor, yr: Tensor, inv_x: Tensor,
+                      inv_y: Tensor, lse_row: Tensor, lse_col: Tensor, grad_loss: Tensor, inv_tau: float,
+                      reduce_mean: bool) -> Tuple[Tensor, Tensor]:
+    """Backward of ntxent_cosine: two softmax-gradient GEMMs over the split operands (depth 3*D; columns [0, D) and
+    [2D, 3D) of each result are G.hi and G.lo of the other side), then the normalisation backward."""
+    n, d = x.shape
+    mult = 1.0 / (2.0 * n) if reduce_mean else 0.5
+    g3x, _ = F.ntxent_bwd(xl, yr, inv_tau, 0, lse_row, lse_col, grad_loss, mult, need_db=False)
+    _, g3y = F.ntxent_bwd(xr, yl, inv_tau, 0, lse_row, lse_col, grad_loss, mult, need_da=False)
+    xx = x if x.dtype in (torch.float32, torch.bfloat16) else x.float()
+    yy = y if y.dtype in (torch.float32, torch.bfloat16) else y.float()
+    return F.rownorm_bwd(xx.contiguous(), inv_x, g3x, second=2 * d), F.rownorm_bwd(yy.contiguous(), inv_y, g3y,
+                                                                                     second=2 * d)
+
+
+@ntxent_cosine_bwd.register_fake
+def _(x, y, xl, xr, yl, yr, inv_x, inv_y, lse_row, lse_col, grad_loss, inv_tau, reduce_mean):
+    return torch.empty_like(x, dtype=torch.float32), torch.empty_like(y, dtype=torch.float32)
 
 
 def _ntxc_setup(ctx, inputs, output):
     x, y, inv_tau, reduce_mean, eps = inputs
-    _, lse_row, lse_col, xh, yh, inv_x, inv_y = output
-    ctx.save_for_backward(x, y, xh, yh, inv_x, inv_y, lse_row, lse_col)
+    _, lse_row, lse_col, xl, xr, yl, yr, inv_x, inv_y = output
+    ctx.save_for_backward(x, y, xl, xr, yl, yr, inv_x, inv_y, lse_row, lse_col)
     ctx.inv_tau, ctx.reduce_mean = inv_tau, reduce_mean
 
 
 def _ntxc_backward(ctx, g_loss, *unused):
-    x, y, xh, yh, inv_x, inv_y, lse_row, lse_col = ctx.saved_tensors
-    dxh, dyh = ntxent_bwd(xh, yh, lse_row, lse_col, g_loss.contiguous(), ctx.inv_tau, ctx.reduce_mean)
-    dx = l2_normalize_bwd(x, inv_x, dxh)
-    dy = l2_normalize_bwd(y, inv_y, dyh)
+    x, y, xl, xr, yl, yr, inv_x, inv_y, lse_row, lse_col = ctx.saved_tensors
+    dx, dy = ntxent_cosine_bwd(x, y, xl, xr, yl, yr, inv_x, inv_y, lse_row, lse_col, g_loss.contiguous(), ctx.inv_tau,
+                               ctx.reduce_mean)
     return dx.to(x.dtype), dy.to(y.dtype), None, None, None
 
 
