@@ -40,6 +40,17 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner, torchrun its OMP notice) write to
+# file descriptor 1 behind Python's back, so fd 1 is pointed at stderr for the whole run and the JSON line goes to a
+# private duplicate of the original stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -153,7 +164,7 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------- our arm
@@ -322,7 +333,7 @@ def run_ours(args, rank, world, local_rank):
                          "sample": f"2 steps of 4 pairs (of 16; linear in pairs), fp32 torch ops, {cpu_model_name()}"},
         "ntxent": extras,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def ntxent_extras(torch, F, dev):

@@ -5,9 +5,10 @@
 //   warp 1      tcgen05.mma issuer (one elected thread), accumulators 128x256 fp32, double-buffered in TMEM
 //   warp 2      TMEM allocator
 //   warps 4..7  epilogue: tcgen05.ld 32 columns at a time, online log-sum-exp in the log2 domain
-// Tiles are linearised row-block-major and cut into equal contiguous ranges, one per CTA, so a CTA keeps
-// a row's (max, sum) in registers across consecutive column tiles; where a range boundary splits a row
-// block the pieces are written as partials and merged by lse_merge_kernel.
+// Tiles are linearised column-tile-major (all row blocks of column tile 0, then of column tile 1, ...) and dealt
+// round-robin to the persistent CTAs, so at any moment the whole grid works on the same four or five B tiles:
+// B (the 103 MB LM-head weight) is then read from HBM once instead of once per row block.  Every tile writes its
+// rows' (max, sum, target) as a partial; lse_merge_kernel folds the column tiles of a row (deterministic, no atomics).
 #include "common.h"
 #include "ptx.cuh"
 
@@ -30,13 +31,13 @@ constexpr float kLn2 = 0.6931471805599453f;
 
 struct GemmLseParams {
   int rows, cols, k;
-  int num_m_blocks, num_n_tiles, tiles_per_cta, rows_pad;
+  int num_m_blocks, num_n_tiles, rows_pad;
   float scale;
   const int* labels;
   int diag_offset;
-  float* part_max;  // [slots][rows_pad]  running max of scale*log2e*z
-  float* part_sum;  // [slots][rows_pad]  sum of exp2(. - max)
-  float* part_tgt;  // [slots][rows_pad]  scale*z at the label column, -inf if not seen in this piece
+  float* part_max;  // [num_n_tiles][rows_pad]  max of scale*log2e*z over the tile's columns
+  float* part_sum;  // [num_n_tiles][rows_pad]  sum of exp2(. - max)
+  float* part_tgt;  // [num_n_tiles][rows_pad]  scale*z at the label column, -inf if it is not in this tile
   float* z_out;     // optional dense [rows][cols] copy of scale*z (similarity-matrix API only)
 };
 
@@ -58,8 +59,7 @@ gemm_lse_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.num_m_blocks * p.num_n_tiles;
-  const int t_begin = blockIdx.x * p.tiles_per_cta;
-  const int t_end = min(t_begin + p.tiles_per_cta, total_tiles);
+  const int t_begin = blockIdx.x, t_step = gridDim.x, t_end = total_tiles;
   const int num_kb = (p.k + kBlockK - 1) / kBlockK;
 
   if (warp == 0 && lane == 0) {
@@ -87,9 +87,9 @@ gemm_lse_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     // TMA producer: the whole warp walks the tile schedule, one elected lane issues the copies
     int stage = 0;
     uint32_t phase = 0;
-    for (int t = t_begin; t < t_end; ++t) {
-      const int m_blk = t / p.num_n_tiles;
-      const int n_tile = t - m_blk * p.num_n_tiles;
+    for (int t = t_begin; t < t_end; t += t_step) {
+      const int n_tile = t / p.num_m_blocks;
+      const int m_blk = t - n_tile * p.num_m_blocks;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
@@ -111,7 +111,7 @@ gemm_lse_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     const uint64_t desc_hi = make_smem_desc(0, 16, 1024);  // everything but the start address
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
-    for (int t = t_begin; t < t_end; ++t) {
+    for (int t = t_begin; t < t_end; t += t_step) {
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + acc * kBlockN;
@@ -144,33 +144,13 @@ gemm_lse_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     const float c = p.scale * kLog2e;
     int acc = 0;
     uint32_t acc_phase = 0;
-    int cur_mblk = -1;
-    float run_m = -INFINITY, run_s = 0.f, run_t = -INFINITY;
-    int label = -1;
-
-    auto flush = [&]() {
-      if (cur_mblk < 0) return;
-      const int first_cta = (cur_mblk * p.num_n_tiles) / p.tiles_per_cta;
-      const int slot = blockIdx.x - first_cta;
-      const size_t o = static_cast<size_t>(slot) * p.rows_pad + cur_mblk * kBlockM + row_in_blk;
-      p.part_max[o] = run_m;
-      p.part_sum[o] = run_s;
-      p.part_tgt[o] = run_t;
-    };
-
-    for (int t = t_begin; t < t_end; ++t) {
-      const int m_blk = t / p.num_n_tiles;
-      const int n_tile = t - m_blk * p.num_n_tiles;
-      if (m_blk != cur_mblk) {
-        flush();
-        cur_mblk = m_blk;
-        run_m = -INFINITY;
-        run_s = 0.f;
-        run_t = -INFINITY;
-        const int row = m_blk * kBlockM + row_in_blk;
-        label = -1;
-        if (row < p.rows) label = p.labels ? p.labels[row] : row + p.diag_offset;
-      }
+    for (int t = t_begin; t < t_end; t += t_step) {
+      const int n_tile = t / p.num_m_blocks;
+      const int m_blk = t - n_tile * p.num_m_blocks;
+      const int row = m_blk * kBlockM + row_in_blk;
+      float run_m = -INFINITY, run_s = 0.f, run_t = -INFINITY;
+      int label = -1;
+      if (row < p.rows) label = p.labels ? p.labels[row] : row + p.diag_offset;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after_sync();
 
@@ -193,7 +173,6 @@ gemm_lse_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             if (n0 + ch * 32 + j >= p.cols) v[j] = -INFINITY;
         }
         if (p.z_out != nullptr) {
-          const int row = m_blk * kBlockM + row_in_blk;
           if (row < p.rows) {
             float* dst = p.z_out + static_cast<size_t>(row) * p.cols + n0 + ch * 32;
 #pragma unroll
@@ -229,8 +208,11 @@ gemm_lse_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         acc = 0;
         acc_phase ^= 1;
       }
+      const size_t o = static_cast<size_t>(n_tile) * p.rows_pad + m_blk * kBlockM + row_in_blk;
+      p.part_max[o] = run_m;
+      p.part_sum[o] = run_s;
+      p.part_tgt[o] = run_t;
     }
-    flush();
   }
 
   tc_fence_before_sync();
@@ -238,31 +220,49 @@ gemm_lse_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   if (warp == 2) tmem_dealloc<kAccStages * kBlockN>(tmem_base);
 }
 
-// One thread per row: fold the per-CTA pieces of that row into lse (natural log) and the target logit.
-__global__ void lse_merge_kernel(const GemmLseParams p, float* __restrict__ lse, float* __restrict__ tgt) {
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= p.rows) return;
-  const int m_blk = row / kBlockM;
-  const int first_cta = (m_blk * p.num_n_tiles) / p.tiles_per_cta;
-  const int last_cta = ((m_blk + 1) * p.num_n_tiles - 1) / p.tiles_per_cta;
-  float m = -INFINITY, t = -INFINITY;
-  for (int s = 0; s <= last_cta - first_cta; ++s) {
-    const size_t o = static_cast<size_t>(s) * p.rows_pad + row;
-    m = fmaxf(m, p.part_max[o]);
-    t = fmaxf(t, p.part_tgt[o]);
+// Fold the column-tile partials of every row into lse (natural log) and the target logit.  A block handles 32 rows
+// with 8 threads per row: thread (r, g) walks tiles g, g+8, ... (loads coalesced across r), then the 8 running
+// (max, sum, target) triples of a row are combined in a fixed order through shared memory.
+constexpr int kMergeRows = 32, kMergeGroups = 8;
+__global__ void __launch_bounds__(kMergeRows* kMergeGroups)
+lse_merge_kernel(const GemmLseParams p, float* __restrict__ lse, float* __restrict__ tgt) {
+  __shared__ float s_m[kMergeGroups][kMergeRows], s_s[kMergeGroups][kMergeRows], s_t[kMergeGroups][kMergeRows];
+  const int r = threadIdx.x % kMergeRows, g = threadIdx.x / kMergeRows;
+  const int row = blockIdx.x * kMergeRows + r;
+  float m = -INFINITY, sum = 0.f, t = -INFINITY;
+  if (row < p.rows) {
+    for (int s = g; s < p.num_n_tiles; s += kMergeGroups) {
+      const size_t o = static_cast<size_t>(s) * p.rows_pad + row;
+      const float pm = p.part_max[o], ps = p.part_sum[o];
+      const float mn = fmaxf(m, pm);
+      // (-inf) - (-inf) cannot occur: a tile always has at least one valid column, so pm is finite or NaN
+      sum = sum * exp2f(m - mn) + ps * exp2f(pm - mn);
+      m = mn;
+      t = fmaxf(t, p.part_tgt[o]);
+    }
   }
-  float sum = 0.f;
-  bool bad = false;
-  for (int s = 0; s <= last_cta - first_cta; ++s) {
-    const size_t o = static_cast<size_t>(s) * p.rows_pad + row;
-    const float ps = p.part_sum[o];
-    bad |= (ps != ps);
-    sum += ps * exp2f(p.part_max[o] - m);
+  s_m[g][r] = m;
+  s_s[g][r] = sum;
+  s_t[g][r] = t;
+  __syncthreads();
+  if (g == 0 && row < p.rows) {
+    float M = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < kMergeGroups; ++i) M = fmaxf(M, s_m[i][r]);
+    float S = 0.f, T = -INFINITY;
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < kMergeGroups; ++i) {
+      const float mi = s_m[i][r], si = s_s[i][r];
+      bad |= (si != si) || (mi != mi);
+      if (mi > -INFINITY) S += si * exp2f(mi - M);
+      T = fmaxf(T, s_t[i][r]);
+    }
+    float out = (M + log2f(S)) * kLn2;
+    if (bad) out = NAN;
+    lse[row] = out;
+    if (tgt) tgt[row] = (T == -INFINITY) ? 0.f : T;
   }
-  float out = (m + log2f(sum)) * kLn2;
-  if (bad) out = NAN;
-  lse[row] = out;
-  if (tgt) tgt[row] = (t == -INFINITY) ? 0.f : t;
 }
 
 int plan(int64_t rows, int64_t cols, int64_t k, GemmLseParams* p, int* grid, size_t* ws_bytes) {
@@ -279,12 +279,8 @@ int plan(int64_t rows, int64_t cols, int64_t k, GemmLseParams* p, int* grid, siz
   const int64_t total = (int64_t)p->num_m_blocks * p->num_n_tiles;
   PGICA_REQUIRE(total < (1ll << 31), "gemm_lse: too many tiles");
   const int sms = device_sm_count();
-  const int ctas = (int)(total < sms ? total : sms);
-  p->tiles_per_cta = (int)ceil_div(total, ctas);
-  *grid = (int)ceil_div(total, p->tiles_per_cta);
-  // a row block of num_n_tiles tiles can straddle at most this many CTA ranges
-  const int slots = (p->num_n_tiles + p->tiles_per_cta - 2) / p->tiles_per_cta + 1;
-  *ws_bytes = 3 * align_up((size_t)slots * p->rows_pad * sizeof(float), 256);
+  *grid = (int)(total < sms ? total : sms);
+  *ws_bytes = 3 * align_up((size_t)p->num_n_tiles * p->rows_pad * sizeof(float), 256);
   return PGICA_OK;
 }
 
@@ -336,7 +332,7 @@ static int gemm_lse_impl(const void* a, const void* b, int64_t rows, int64_t col
   gemm_lse_kernel<<<grid, kThreads, kSmemBytes, st>>>(tm_a, tm_b, p);
   PGICA_CUDA_OK(cudaGetLastError());
   count_launches(1);
-  lse_merge_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, st>>>(p, lse, tgt);
+  lse_merge_kernel<<<(unsigned)ceil_div(rows, kMergeRows), kMergeRows * kMergeGroups, 0, st>>>(p, lse, tgt);
   PGICA_CUDA_OK(cudaGetLastError());
   count_launches(1);
   return PGICA_OK;

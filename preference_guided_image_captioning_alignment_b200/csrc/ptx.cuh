@@ -153,6 +153,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// Pull one box into L2 ahead of time (no shared-memory destination, no completion tracking).
+__device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
 // Same, multicast to every CTA in `mask` (same smem offset, each CTA's own barrier at the same offset).
 __device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1,
                                                   uint16_t mask) {

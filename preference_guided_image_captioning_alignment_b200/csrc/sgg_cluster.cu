@@ -3,8 +3,10 @@
 // memory, so the logits of a (128 x 128) tile are recomputed once per cluster instead of once per 256 output
 // columns.  Tile j is produced by CTA (j mod C): MMA1 -> Z in TMEM -> epilogue -> bf16 G tile written into slot
 // (j mod C) of EVERY CTA's G buffers (st.shared::cluster), signalled with cluster-scope mbarrier arrives.  Every CTA
-// then runs MMA2 (Out_slice += G * Y[tile, slice]) for every tile.  A round = C consecutive tiles; a CTA issues
-// MMA1 for its tile of round r, then the MMA2s of round r-1, so the tensor pipe never waits for an epilogue.
+// then runs MMA2 (Out_slice += G * Y[tile, slice], N = 256 in one instruction, the tile taken in two 64-row halves)
+// for every tile.  A round = C consecutive tiles; a CTA issues MMA1 for its tile of round r, then the MMA2s of round
+// r-1, so the tensor pipe never waits for an epilogue.  The epilogue keeps the freshly computed G tile in registers
+// until its slot is free everywhere, so the exp/pack work overlaps the wait instead of following it.
 #include "common.h"
 #include "ptx.cuh"
 
@@ -17,6 +19,7 @@ constexpr int kBD = 256;
 constexpr int kBK = 64;
 constexpr uint32_t kChunkBytes = 128 * kBK * 2;   // 16 KB
 constexpr uint32_t kSlotBytes = 2 * kChunkBytes;  // 32 KB
+constexpr uint32_t kHalfBoxBytes = 64 * kBK * 2;  // 8 KB: a [64][64] bf16 box (MMA2 operand, one 64-column chunk)
 constexpr uint32_t kPBytes = kBM * kBT * 2;       // 32 KB
 constexpr int kThreads = 256;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -57,7 +60,7 @@ struct Lap {
 #endif
 
 struct SggcParams {
-  int mx, my, k, num_tiles, passes, ldo, out_bf16;
+  int mx, my, k, num_tiles, passes, ldo, out_bf16, prefetch_y;
   float c;
   const float* r_lse;
   const float* r_coef;
@@ -77,7 +80,7 @@ struct Cfg {
 template <int C, bool kRow, bool kCol>
 __global__ void __launch_bounds__(kThreads, 1)
 sgg_cluster_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y,
-                   const SggcParams p) {
+                   const __grid_constant__ CUtensorMap tm_y2, const SggcParams p) {
   constexpr int kRing = Cfg<C>::kRing;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
@@ -108,6 +111,7 @@ sgg_cluster_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_y);
+    tma_prefetch_desc(&tm_y2);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kRing; ++i) {
@@ -146,6 +150,10 @@ sgg_cluster_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     for (int r = 0; r <= rounds; ++r) {
       const int own = r * C + (int)q;
       if (own < J) {
+        // A large Y (the LM-head weight in dH) streams from HBM: one cluster in eight pulls the tile this CTA will
+        // need two rounds from now into L2, so that nobody's ring stalls on a DRAM round trip.
+        const int ahead = own + 2 * C;
+        const bool pf = p.prefetch_y && ahead < J && (((own / C) ^ cluster_id) & 7) == 0;
         for (int kb = 0; kb < num_kb; ++kb) {
           LAP(0);
           mbar_wait(&empty_bar[slot], phase ^ 1);
@@ -155,6 +163,7 @@ sgg_cluster_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             uint8_t* dst = ring + slot * kSlotBytes;
             tma_load_2d(dst, &tm_x, &full_bar[slot], kb * kBK, m_blk * kBM);
             tma_load_2d(dst + kChunkBytes, &tm_y, &full_bar[slot], kb * kBK, own * kBT);
+            if (pf) tma_prefetch_2d(&tm_y, kb * kBK, ahead * kBT);
           }
           __syncwarp();
           advance();
@@ -163,15 +172,16 @@ sgg_cluster_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       if (r > 0) {
         const int t_end = min(r * C, J);
         for (int t = (r - 1) * C; t < t_end; ++t) {
-          for (int h = 0; h < 2; ++h) {  // Y[t tile, out_col0 + h*128 .. +128): two [128][64] boxes per slot
+          for (int h = 0; h < 2; ++h) {  // Y[64-row half h of tile t, out_col0 .. +256): four [64][64] boxes per slot
             LAP(0);
             mbar_wait(&empty_bar[slot], phase ^ 1);
             LAP(2);
             if (elect_one()) {
               mbar_expect_tx(&full_bar[slot], kSlotBytes);
               uint8_t* dst = ring + slot * kSlotBytes;
-              tma_load_2d(dst, &tm_y, &full_bar[slot], out_col0 + h * 128, t * kBT);
-              tma_load_2d(dst + kChunkBytes, &tm_y, &full_bar[slot], out_col0 + h * 128 + 64, t * kBT);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                tma_load_2d(dst + i * kHalfBoxBytes, &tm_y2, &full_bar[slot], out_col0 + i * kBK, t * kBT + h * 64);
             }
             __syncwarp();
             advance();
@@ -184,9 +194,9 @@ sgg_cluster_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (whole warp, one elected lane)
     constexpr uint32_t idesc1 = make_idesc_bf16(kBM, kBT, 0, 0);
-    constexpr uint32_t idesc2 = make_idesc_bf16(kBM, 128, 0, 1);
-    const uint64_t desc_k = make_smem_desc(0, 16, 1024);            // K-major operand, start address 0
-    const uint64_t desc_mn = make_smem_desc(0, kChunkBytes, 1024);  // MN-major operand (Y tile of MMA2)
+    constexpr uint32_t idesc2 = make_idesc_bf16(kBM, kBD, 0, 1);
+    const uint64_t desc_k = make_smem_desc(0, 16, 1024);              // K-major operand, start address 0
+    const uint64_t desc_mn = make_smem_desc(0, kHalfBoxBytes, 1024);  // MN-major operand: 64-column chunks 8 KB apart
     const uint32_t gfree_remote0 = smem_u32(gfree_bar);
     int slot = 0;
     uint32_t phase = 0;
@@ -245,12 +255,13 @@ sgg_cluster_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             tc_fence_after_sync();
             if (elect_one()) {
               const uint32_t y_addr = smem_u32(ring + slot * kSlotBytes);
-              const uint64_t dg = desc_k | ((g_addr >> 4) & 0x3FFF);
+              // half h of the G tile = its k-chunk h ([128 rows][64 vocab]); four K=16 steps, N = 256 each
+              const uint64_t dg = desc_k | (((g_addr + h * kChunkBytes) >> 4) & 0x3FFF);
               const uint64_t dy = desc_mn | ((y_addr >> 4) & 0x3FFF);
 #pragma unroll
-              for (int ks = 0; ks < kBT / 16; ++ks)
-                umma_bf16_ss(tmem_base + kTmemOut + h * 128, dg + (ks >> 2) * (kChunkBytes >> 4) + (ks & 3) * 2,
-                             dy + ks * (16 * 128 >> 4), idesc2, (t | ks) != 0 ? 1u : 0u);
+              for (int ks = 0; ks < 4; ++ks)
+                umma_bf16_ss(tmem_base + kTmemOut, dg + ks * 2, dy + ks * (16 * 128 >> 4), idesc2,
+                             (t | h | ks) != 0 ? 1u : 0u);
               umma_commit(&empty_bar[slot]);
               // after the second half: tell the producer of slot s that this CTA is done reading it
               if (h == 1) umma_commit_remote(mapa_u32(gfree_remote0, (uint32_t)s));
@@ -312,12 +323,10 @@ sgg_cluster_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       mbar_wait(&zfull_bar[zb], zphase);
       LAP(1);
       tc_fence_after_sync();
-      mbar_wait_cluster(gfree_bar, fphase ^ 1);  // every CTA has finished MMA2 on my previous tile
-      LAP(2);
-      fphase ^= 1;
       const int col0 = own * kBT;
       const int rrel = rt - col0;
-#pragma unroll 1
+      uint32_t gp[kBT / 2];  // this thread's row of the G tile, bf16 pairs, held in registers until the slot is free
+#pragma unroll
       for (int ch = 0; ch < kBT / 32; ++ch) {
         uint32_t rr[32];
         tmem_ld_32x32(tmem_base + lane_addr + kTmemZ + zb * kBT + ch * 32, rr);
@@ -342,18 +351,26 @@ sgg_cluster_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
           for (int jj = 0; jj < 32; ++jj)
             if (jj == jj0) g[jj] -= rc;
         }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) gp[ch * 16 + i] = pack_bf16x2(g[2 * i], g[2 * i + 1]);
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&zempty_bar[zb]);  // Z buffer is free for the MMA1 after next
+      LAP(3);
+      mbar_wait_cluster(gfree_bar, fphase ^ 1);  // every CTA has finished MMA2 on my previous tile
+      LAP(2);
+      fphase ^= 1;
+#pragma unroll
+      for (int ch = 0; ch < kBT / 32; ++ch) {
         const uint32_t chunk_off = (ch >> 1) * kChunkBytes;
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
           const uint32_t off = chunk_off + sw128_offset(row_in_blk, (ch & 1) * 4 + c4);
-          st_smem_v4(g_local + off, pack_bf16x2(g[c4 * 8 + 0], g[c4 * 8 + 1]), pack_bf16x2(g[c4 * 8 + 2], g[c4 * 8 + 3]),
-                     pack_bf16x2(g[c4 * 8 + 4], g[c4 * 8 + 5]), pack_bf16x2(g[c4 * 8 + 6], g[c4 * 8 + 7]));
+          st_smem_v4(g_local + off, gp[ch * 16 + c4 * 4 + 0], gp[ch * 16 + c4 * 4 + 1], gp[ch * 16 + c4 * 4 + 2],
+                     gp[ch * 16 + c4 * 4 + 3]);
         }
       }
       fence_proxy_async_smem();  // my generic-proxy writes -> visible to the async proxy (UMMA reads, bulk copy)
-      tc_fence_before_sync();
-      mbar_arrive(&zempty_bar[zb]);
-      LAP(3);
       asm volatile("bar.sync 2, 128;" ::: "memory");  // the whole tile is in shared memory
       LAP(4);
       if (et == 0) {
@@ -413,7 +430,8 @@ sgg_cluster_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 }
 
 template <int C, bool kRow, bool kCol>
-int launch(const CUtensorMap& tm_x, const CUtensorMap& tm_y, const SggcParams& p, int64_t clusters, cudaStream_t st) {
+int launch(const CUtensorMap& tm_x, const CUtensorMap& tm_y, const CUtensorMap& tm_y2, const SggcParams& p,
+           int64_t clusters, cudaStream_t st) {
   auto kern = sgg_cluster_kernel<C, kRow, kCol>;
   PGICA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<C>::kSmem));
   cudaLaunchConfig_t cfg{};
@@ -428,7 +446,7 @@ int launch(const CUtensorMap& tm_x, const CUtensorMap& tm_y, const SggcParams& p
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PGICA_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tm_x, tm_y, p));
+  PGICA_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tm_x, tm_y, tm_y2, p));
   count_launches(1);
   return PGICA_OK;
 }
@@ -462,19 +480,22 @@ int sgg_cluster_dispatch(int cluster, const void* x, const void* y, int64_t mx, 
   p.c_coef = c_coef;
   p.c_tgt = c_tgt;
   p.out = out;
-  CUtensorMap tm_x, tm_y;
+  p.prefetch_y = (my * k * 2 > (int64_t)(32 << 20)) ? 1 : 0;  // only an operand that cannot sit in L2
+  CUtensorMap tm_x, tm_y, tm_y2;
   int rc = make_tmap_bf16(&tm_x, x, mx, k, k, 128);
   if (rc != PGICA_OK) return rc;
   rc = make_tmap_bf16(&tm_y, y, my, k, k, 128);
+  if (rc != PGICA_OK) return rc;
+  rc = make_tmap_bf16(&tm_y2, y, my, k, k, 64);  // 64-row boxes: one K-half of a tile for MMA2
   if (rc != PGICA_OK) return rc;
   const int64_t clusters = ceil_div(mx, kBM) * p.passes;
   PGICA_REQUIRE(clusters * cluster < (1ll << 31), "softmax_grad_gemm: grid too large");
   const bool row = r_lse != nullptr, col = c_lse != nullptr;
 #define PGICA_SGGC(CC)                                                        \
   do {                                                                        \
-    if (row && col) return launch<CC, true, true>(tm_x, tm_y, p, clusters, st); \
-    if (row) return launch<CC, true, false>(tm_x, tm_y, p, clusters, st);     \
-    return launch<CC, false, true>(tm_x, tm_y, p, clusters, st);              \
+    if (row && col) return launch<CC, true, true>(tm_x, tm_y, tm_y2, p, clusters, st); \
+    if (row) return launch<CC, true, false>(tm_x, tm_y, tm_y2, p, clusters, st);     \
+    return launch<CC, false, true>(tm_x, tm_y, tm_y2, p, clusters, st);              \
   } while (0)
   if (cluster == 2) PGICA_SGGC(2);
   if (cluster == 4) PGICA_SGGC(4);
