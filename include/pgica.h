@@ -97,10 +97,15 @@ int pgica_probe_umma(const void* a, const void* b, int64_t n, int64_t k, int b_m
  * pkg/models/components.py:346-358 / pkg/models/model.py:1074-1083 (log_softmax, gather, mask, sum) chained
  * into the lm_head matmul, and from F.cross_entropy x2 + matmul in pkg/models/model.py:988-998 /
  * pkg/models/components.py:131-141 (closed forms: SURVEY.md Appendix A).
+ * workspace (pgica_softmax_grad_gemm_workspace_bytes, 128-byte aligned): the exchange ring through which the CTAs of
+ * a cluster hand each other 128 x 128 bf16 tiles of G (8 tiles per resident cluster, L2-resident, overwritten every
+ * 8 tiles).  With workspace == NULL the cluster exchanges tiles over distributed shared memory instead (slower).
  * ---------------------------------------------------------------------------------------------- */
+int pgica_softmax_grad_gemm_workspace_bytes(int64_t mx, int64_t my, int64_t k, size_t* bytes_host);
 int pgica_softmax_grad_gemm(const void* x, const void* y, int64_t mx, int64_t my, int64_t k, float scale,
                             const float* r_lse, const float* r_coef, const int32_t* r_tgt, const float* c_lse,
-                            const float* c_coef, const int32_t* c_tgt, void* out, int out_is_bf16, void* stream);
+                            const float* c_coef, const int32_t* c_tgt, void* out, int out_is_bf16, void* workspace,
+                            size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Stage-2 head, hidden-state level (logits never materialised).

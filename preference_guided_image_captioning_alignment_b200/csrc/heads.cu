@@ -8,18 +8,19 @@ extern "C" {
 using namespace pgica;
 
 // ---- internal building blocks defined in the other translation units
-int pgica_softmax_grad_gemm(const void* x, const void* y, int64_t mx, int64_t my, int64_t k, float scale,
-                            const float* r_lse, const float* r_coef, const int32_t* r_tgt, const float* c_lse,
-                            const float* c_coef, const int32_t* c_tgt, void* out, int out_is_bf16, void* stream);
+// (pgica_softmax_grad_gemm and its workspace query are declared in pgica.h)
 
 int pgica_lmhead_logprob_workspace_bytes(int64_t nseq, int64_t seqlen, int64_t d, int64_t vocab, size_t* bytes_host) {
   PGICA_REQUIRE(bytes_host, "workspace query: null result pointer");
   size_t g = 0;
   int rc = pgica_gemm_lse_workspace_bytes(nseq * seqlen, vocab, d, &g);
   if (rc != PGICA_OK) return rc;
-  // backward needs one float per row for the coefficients; forward needs the LSE partials
-  const size_t coef = align_up((size_t)(nseq * seqlen) * sizeof(float), 256);
-  *bytes_host = g > coef ? g : coef;
+  // backward: one float per row for the coefficients + the G-tile exchange ring; forward: the LSE partials
+  size_t x = 0;
+  rc = pgica_softmax_grad_gemm_workspace_bytes(nseq * seqlen, vocab, d, &x);
+  if (rc != PGICA_OK) return rc;
+  const size_t bwd = align_up((size_t)(nseq * seqlen) * sizeof(float), 256) + x;
+  *bytes_host = g > bwd ? g : bwd;
   return PGICA_OK;
 }
 
@@ -51,16 +52,19 @@ int pgica_lmhead_logprob_bwd(const void* hidden, const void* weight, const int32
     return PGICA_ERR_WORKSPACE_TOO_SMALL;
   }
   float* ncoef = static_cast<float*>(workspace);  // -grad_seq[b] * w (/len): multiplies (softmax - onehot)
+  const size_t coef_bytes = align_up((size_t)rows * sizeof(float), 256);
+  void* xws = workspace_bytes > coef_bytes ? static_cast<uint8_t*>(workspace) + coef_bytes : nullptr;
+  const size_t xws_bytes = xws ? workspace_bytes - coef_bytes : 0;
   int rc = pgica_row_coef(grad_seq, row_weight, nseq, seqlen, length_normalize, -1.0f, ncoef, stream);
   if (rc != PGICA_OK) return rc;
   if (dhidden) {
     rc = pgica_softmax_grad_gemm(hidden, weight, rows, vocab, d, 1.0f, lse, ncoef, row_label, nullptr, nullptr,
-                                 nullptr, dhidden, dhidden_is_bf16, stream);
+                                 nullptr, dhidden, dhidden_is_bf16, xws, xws_bytes, stream);
     if (rc != PGICA_OK) return rc;
   }
   if (dweight) {
     rc = pgica_softmax_grad_gemm(weight, hidden, vocab, rows, d, 1.0f, nullptr, nullptr, nullptr, lse, ncoef,
-                                 row_label, dweight, dweight_is_bf16, stream);
+                                 row_label, dweight, dweight_is_bf16, xws, xws_bytes, stream);
     if (rc != PGICA_OK) return rc;
   }
   return PGICA_OK;
@@ -74,7 +78,10 @@ int pgica_ntxent_workspace_bytes(int64_t rows_a, int64_t rows_b, int64_t dim, si
   rc = pgica_gemm_lse_workspace_bytes(rows_b, rows_a, dim, &g2);
   if (rc != PGICA_OK) return rc;
   const size_t fwd = g1 > g2 ? g1 : g2;
-  const size_t bwd = 2 * align_up((size_t)rows_a * 4, 256) + 2 * align_up((size_t)rows_b * 4, 256);
+  size_t x = 0;
+  rc = pgica_softmax_grad_gemm_workspace_bytes(rows_a, rows_b, dim, &x);
+  if (rc != PGICA_OK) return rc;
+  const size_t bwd = 2 * align_up((size_t)rows_a * 4, 256) + 2 * align_up((size_t)rows_b * 4, 256) + x;
   *bytes_host = fwd > bwd ? fwd : bwd;
   return PGICA_OK;
 }
@@ -109,6 +116,9 @@ int pgica_ntxent_bwd(const void* a, const void* b, int64_t rows_a, int64_t rows_
   int32_t* rtgt = reinterpret_cast<int32_t*>(w + sa);
   float* ccoef = reinterpret_cast<float*>(w + 2 * sa);
   int32_t* ctgt = reinterpret_cast<int32_t*>(w + 2 * sa + sb);
+  const size_t stat_bytes = 2 * sa + 2 * sb;
+  void* xws = workspace_bytes > stat_bytes ? w + stat_bytes : nullptr;
+  const size_t xws_bytes = xws ? workspace_bytes - stat_bytes : 0;
   // dS = grad * mult * (P_row + P_col - 2 I);  dA = dS B / tau;  dB = dS^T A / tau
   int rc = pgica_ntxent_coef(grad_loss, grad_mult * inv_tau, rows_a, diag_offset, rows_b, rcoef, rtgt, stream);
   if (rc != PGICA_OK) return rc;
@@ -116,12 +126,12 @@ int pgica_ntxent_bwd(const void* a, const void* b, int64_t rows_a, int64_t rows_
   if (rc != PGICA_OK) return rc;
   if (da) {
     rc = pgica_softmax_grad_gemm(a, b, rows_a, rows_b, dim, inv_tau, lse_row, rcoef, rtgt, lse_col, ccoef, ctgt, da,
-                                 da_is_bf16, stream);
+                                 da_is_bf16, xws, xws_bytes, stream);
     if (rc != PGICA_OK) return rc;
   }
   if (db) {
     rc = pgica_softmax_grad_gemm(b, a, rows_b, rows_a, dim, inv_tau, lse_col, ccoef, ctgt, lse_row, rcoef, rtgt, db,
-                                 db_is_bf16, stream);
+                                 db_is_bf16, xws, xws_bytes, stream);
     if (rc != PGICA_OK) return rc;
   }
   return PGICA_OK;

@@ -100,9 +100,12 @@ def softmax_grad_gemm(x, y, scale=1.0, row=None, col=None, out_dtype=torch.float
     out = torch.empty(mx, k, dtype=out_dtype, device=x.device)
     r = row if row is not None else (None, None, None)
     c = col if col is not None else (None, None, None)
+    need = ctypes.c_size_t(0)
+    _lib.check(lib.pgica_softmax_grad_gemm_workspace_bytes(mx, my, k, ctypes.byref(need)))
+    ws = _ws(need.value, x.device)
     _lib.check(lib.pgica_softmax_grad_gemm(_p(x), _p(y), mx, my, k, float(scale), _p(r[0]), _p(r[1]), _p(r[2]),
                                            _p(c[0]), _p(c[1]), _p(c[2]), _p(out),
-                                           1 if out_dtype == torch.bfloat16 else 0, _stream()))
+                                           1 if out_dtype == torch.bfloat16 else 0, _p(ws), need.value, _stream()))
     return out
 
 
@@ -144,7 +147,9 @@ def lmhead_logprob_bwd(hidden, weight, row_label, row_weight, lse, grad_seq, len
     dev = hidden.device
     dh = torch.empty(nseq, T, d, dtype=dhidden_dtype, device=dev) if need_dhidden else None
     dw = torch.empty(V, d, dtype=dweight_dtype, device=dev) if need_dweight else None
-    ws = _ws(nseq * T * 4, dev)
+    need = ctypes.c_size_t(0)
+    _lib.check(lib.pgica_lmhead_logprob_workspace_bytes(nseq, T, d, V, ctypes.byref(need)))
+    ws = _ws(need.value, dev)
     grad_seq = grad_seq.contiguous().float()
     _lib.check(lib.pgica_lmhead_logprob_bwd(_p(hidden), _p(weight), _p(row_label), _p(row_weight), _p(lse),
                                             _p(grad_seq), nseq, T, d, V, 1 if length_normalize else 0, _p(dh),
