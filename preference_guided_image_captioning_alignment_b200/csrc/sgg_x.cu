@@ -13,9 +13,12 @@
 //   * the 4 x 32 KB landing slots disappear: the operand ring grows from 3 to 6 stages of 32 KB,
 //   * the exchange latency drops from ~8000 to ~3000 cycles and no longer gates on "slot free in every CTA",
 //   * the kernel can be persistent (clusters loop over row blocks), which matters for dW with its 393 row blocks.
-// A round = C consecutive tiles; a CTA issues MMA1 for its tile of round r, then the MMA2s of round r-2: two rounds
-// of slack between producing a tile and needing it absorb the jitter between the CTAs of a cluster (the slack
-// costs no shared memory, the tiles wait in the exchange ring).
+// MMA1 runs with N = 256 (two G tiles at once: a 128 x N x 16 tcgen05.mma with shared-memory operands costs
+// N/2 + 43 cycles, so N = 256 reaches 75 % of the tensor peak where N = 128 reaches 60 %).  A round = C such
+// 256-wide tiles = 2C G tiles; a CTA issues MMA1 for its tile of round r, then the MMA2s of the 2C tiles of round
+// r-1.  Between a Z tile being complete and its G tiles being needed lie a whole MMA2 phase and the next MMA1
+// (~20000 cycles); the epilogue + exchange need ~10000, and the slack costs no shared memory because finished tiles
+// wait in the exchange ring.
 #include "common.h"
 #include "ptx.cuh"
 
@@ -27,16 +30,18 @@ constexpr int kBT = 128;
 constexpr int kBD = 256;
 constexpr int kBK = 64;
 constexpr uint32_t kChunkBytes = 128 * kBK * 2;   // 16 KB: a [128][64] bf16 box
-constexpr uint32_t kSlotBytes = 2 * kChunkBytes;  // 32 KB
-constexpr uint32_t kHalfBoxBytes = 64 * kBK * 2;  // 8 KB: a [64][64] bf16 box
+constexpr uint32_t kQ0BoxBytes = 32 * kBK * 2;    // 4 KB: a [32][64] bf16 box (rows 0..31 of a Y tile, MMA2 operand)
+constexpr uint32_t kQ1BoxBytes = 96 * kBK * 2;    // 12 KB: a [96][64] bf16 box (rows 32..127)
 constexpr uint32_t kPBytes = kBM * kBT * 2;       // 32 KB: one G tile
-constexpr int kRing = 6;
-constexpr int kXSlots = 16;  // exchange-ring depth in tiles (four rounds of a 4-CTA cluster)
-constexpr int kLag = 2;       // MMA2 consumes the tiles of round r - kLag while MMA1 produces round r
+constexpr int kBT2 = 2 * kBT;                     // MMA1 covers two G tiles at once (N = 256: 75 % vs 60 % of peak)
+constexpr uint32_t kStageBytes = kChunkBytes + 2 * kChunkBytes;  // 48 KB ring slot: X chunk + 256-row Y chunk
+constexpr int kRing = 4;
+constexpr int kXSlots = 16;  // exchange-ring depth in tiles (two rounds of a 4-CTA cluster)
+constexpr int kLag = 1;       // MMA2 consumes the tiles of round r - kLag while MMA1 produces round r
 constexpr int kThreads = 256;
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr uint32_t kTmemOut = 0, kTmemZ = 256;
-constexpr size_t kSmem = 1024 + (kRing + 1) * kSlotBytes + 3 * kBT * 4 + 512;
+constexpr uint32_t kTmemOut = 0, kTmemZ = 256;  // Out [0,256), Z [256,512) (single buffer, 256 columns)
+constexpr size_t kSmem = 1024 + kRing * kStageBytes + kPBytes + 3 * kBT * 4 + 512;
 
 #ifdef PGICA_TRACE
 __device__ long long* g_sggx_trace = nullptr;
@@ -105,18 +110,19 @@ __device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) 
 template <int C, bool kRow, bool kCol>
 __global__ void __launch_bounds__(kThreads, 1)
 sggx_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y,
-            const __grid_constant__ CUtensorMap tm_y2, const __grid_constant__ CUtensorMap tm_s, const SggxParams p) {
+            const __grid_constant__ CUtensorMap tm_y32, const __grid_constant__ CUtensorMap tm_y96,
+            const __grid_constant__ CUtensorMap tm_s, const SggxParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* ring = smem;
-  uint8_t* staging = smem + kRing * kSlotBytes;  // this CTA's freshly produced G tile, source of the TMA store
+  uint8_t* staging = smem + kRing * kStageBytes;  // this CTA's freshly produced G tile, source of the TMA store
   float* s_cl = reinterpret_cast<float*>(staging + kPBytes);
   float* s_cc = s_cl + kBT;
   int* s_ct = reinterpret_cast<int*>(s_cc + kBT);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_ct + kBT);
   uint64_t* empty_bar = full_bar + kRing;
-  uint64_t* zfull_bar = empty_bar + kRing;   // [2]
-  uint64_t* zempty_bar = zfull_bar + 2;      // [2]
+  uint64_t* zfull_bar = empty_bar + kRing;   // [1] (+1 spare)
+  uint64_t* zempty_bar = zfull_bar + 2;      // [1] (+1 spare)
   uint64_t* gready_bar = zempty_bar + 2;     // [kXSlots] tile in exchange slot s is complete in global memory
   uint64_t* gdone_bar = gready_bar + kXSlots;  // [kXSlots] every CTA has finished MMA2 on the tile in slot s
   uint64_t* outfull_bar = gdone_bar + kXSlots;
@@ -128,14 +134,16 @@ sggx_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   const int cluster_id = blockIdx.x / C;
   const int num_clusters = gridDim.x / C;
   const int num_kb = (p.k + kBK - 1) / kBK;
-  const int J = p.num_tiles;
-  const int rounds = (J + C - 1) / C;
+  const int J = p.num_tiles;       // G tiles (128 rows of Y each)
+  const int J2 = (J + 1) / 2;      // MMA1 tiles (256 rows of Y each)
+  const int rounds = (J2 + C - 1) / C;
   const int xrow0 = cluster_id * kXSlots * kBM;  // first row of this cluster's exchange ring in the scratch matrix
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_y);
-    tma_prefetch_desc(&tm_y2);
+    tma_prefetch_desc(&tm_y32);
+    tma_prefetch_desc(&tm_y96);
     tma_prefetch_desc(&tm_s);
   }
   if (warp == 1 && lane == 0) {
@@ -178,30 +186,34 @@ sggx_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       const int m_blk = item / p.passes;
       const int out_col0 = ((item - m_blk * p.passes) * C + (int)q) * kBD;
       for (int r = 0; r < rounds + kLag; ++r) {
-        const int own = r * C + (int)q;
-        if (own < J) {
+        const int own2 = r * C + (int)q;
+        if (own2 < J2) {
           // A large Y (the LM-head weight in dH) streams from HBM: one cluster in eight pulls the tile this CTA
           // needs two rounds from now into L2, so that nobody's ring stalls on a DRAM round trip.
-          const int ahead = own + 2 * C;
-          const bool pf = p.prefetch_y && ahead < J && (((own / C) ^ cluster_id) & 7) == 0;
+          const int ahead = own2 + 2 * C;
+          const bool pf = p.prefetch_y && ahead < J2 && (((own2 / C) ^ cluster_id) & 7) == 0;
           for (int kb = 0; kb < num_kb; ++kb) {
             LAP(0);
             mbar_wait(&empty_bar[slot], phase ^ 1);
             LAP(1);
             if (elect_one()) {
-              mbar_expect_tx(&full_bar[slot], kSlotBytes);
-              uint8_t* dst = ring + slot * kSlotBytes;
+              mbar_expect_tx(&full_bar[slot], kStageBytes);
+              uint8_t* dst = ring + slot * kStageBytes;
               tma_load_2d(dst, &tm_x, &full_bar[slot], kb * kBK, m_blk * kBM);
-              tma_load_2d(dst + kChunkBytes, &tm_y, &full_bar[slot], kb * kBK, own * kBT);
-              if (pf) tma_prefetch_2d(&tm_y, kb * kBK, ahead * kBT);
+              tma_load_2d(dst + kChunkBytes, &tm_y, &full_bar[slot], kb * kBK, own2 * kBT2);
+              tma_load_2d(dst + 2 * kChunkBytes, &tm_y, &full_bar[slot], kb * kBK, own2 * kBT2 + kBT);
+              if (pf) {
+                tma_prefetch_2d(&tm_y, kb * kBK, ahead * kBT2);
+                tma_prefetch_2d(&tm_y, kb * kBK, ahead * kBT2 + kBT);
+              }
             }
             __syncwarp();
             advance();
           }
         }
         if (r >= kLag) {
-          const int t_end = min((r - kLag + 1) * C, J);
-          for (int t = (r - kLag) * C; t < t_end; ++t) {
+          const int t_end = min((r - kLag + 1) * 2 * C, J);
+          for (int t = (r - kLag) * 2 * C; t < t_end; ++t) {
             const int g = gbase + t;
             const int xs = g % kXSlots;
             LAP(0);
@@ -212,27 +224,30 @@ sggx_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
             if (elect_one()) {
               // order the acquire above (generic proxy) before the async-proxy read of the tile below
               asm volatile("fence.proxy.async.global;" ::: "memory");
-              mbar_expect_tx(&full_bar[slot], kSlotBytes);
-              uint8_t* dst = ring + slot * kSlotBytes;
+              // slot A: the G tile (32 KB) + rows 0..31 of Y[tile t, out_col0 .. +256) as four [32][64] boxes (16 KB)
+              mbar_expect_tx(&full_bar[slot], kStageBytes);
+              uint8_t* dst = ring + slot * kStageBytes;
               tma_load_2d(dst, &tm_s, &full_bar[slot], 0, xrow0 + xs * kBM);
               tma_load_2d(dst + kChunkBytes, &tm_s, &full_bar[slot], kBK, xrow0 + xs * kBM);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                tma_load_2d(dst + kPBytes + i * kQ0BoxBytes, &tm_y32, &full_bar[slot], out_col0 + i * kBK, t * kBT);
             }
             __syncwarp();
             advance();
-            for (int h = 0; h < 2; ++h) {  // Y[64-row half h of tile t, out_col0 .. +256): four [64][64] boxes
-              LAP(0);
-              mbar_wait(&empty_bar[slot], phase ^ 1);
-              LAP(2);
-              if (elect_one()) {
-                mbar_expect_tx(&full_bar[slot], kSlotBytes);
-                uint8_t* dst = ring + slot * kSlotBytes;
+            LAP(0);
+            mbar_wait(&empty_bar[slot], phase ^ 1);
+            LAP(2);
+            if (elect_one()) {
+              // slot B: rows 32..127 of the same Y tile as four [96][64] boxes (48 KB)
+              mbar_expect_tx(&full_bar[slot], kStageBytes);
+              uint8_t* dst = ring + slot * kStageBytes;
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  tma_load_2d(dst + i * kHalfBoxBytes, &tm_y2, &full_bar[slot], out_col0 + i * kBK, t * kBT + h * 64);
-              }
-              __syncwarp();
-              advance();
+              for (int i = 0; i < 4; ++i)
+                tma_load_2d(dst + i * kQ1BoxBytes, &tm_y96, &full_bar[slot], out_col0 + i * kBK, t * kBT + 32);
             }
+            __syncwarp();
+            advance();
           }
         }
       }
@@ -241,10 +256,11 @@ sggx_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     if (lane == 0) LAP_FLUSH(0, 4);
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (whole warp, one elected lane)
-    constexpr uint32_t idesc1 = make_idesc_bf16(kBM, kBT, 0, 0);
+    constexpr uint32_t idesc1 = make_idesc_bf16(kBM, kBT2, 0, 0);
     constexpr uint32_t idesc2 = make_idesc_bf16(kBM, kBD, 0, 1);
     const uint64_t desc_k = make_smem_desc(0, 16, 1024);              // K-major operand, start address 0
-    const uint64_t desc_mn = make_smem_desc(0, kHalfBoxBytes, 1024);  // MN-major operand: 64-column chunks 8 KB apart
+    const uint64_t desc_mn32 = make_smem_desc(0, kQ0BoxBytes, 1024);  // MN-major operand: 64-column chunks 4 KB apart
+    const uint64_t desc_mn96 = make_smem_desc(0, kQ1BoxBytes, 1024);  // ... 12 KB apart
     constexpr uint16_t kAllCtas = (uint16_t)((1u << C) - 1u);
     int slot = 0;
     uint32_t phase = 0;
@@ -254,44 +270,40 @@ sggx_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         phase ^= 1;
       }
     };
-    int zb = 0;
-    uint32_t zphase = 0;
+    uint32_t zuse = 0;  // own MMA1 tiles issued so far (Z is a single 256-column buffer)
     LAP_DECL;
     int gbase = 0, nitem = 0;
     for (int item = cluster_id; item < p.num_items; item += num_clusters, gbase += J, ++nitem) {
       for (int r = 0; r < rounds + kLag; ++r) {
-        const int own = r * C + (int)q;
-        if (own < J) {
+        const int own2 = r * C + (int)q;
+        if (own2 < J2) {
           LAP(0);
-          mbar_wait(&zempty_bar[zb], zphase ^ 1);
+          mbar_wait(zempty_bar, (zuse & 1u) ^ 1u);  // the epilogue has read the previous Z tile out of TMEM
           LAP(1);
           tc_fence_after_sync();
-          const uint32_t d_tmem = tmem_base + kTmemZ + zb * kBT;
+          const uint32_t d_tmem = tmem_base + kTmemZ;
           for (int kb = 0; kb < num_kb; ++kb) {
             LAP(0);
             mbar_wait(&full_bar[slot], phase);
             LAP(2);
             tc_fence_after_sync();
             if (elect_one()) {
-              const uint32_t x_addr = smem_u32(ring + slot * kSlotBytes);
+              const uint32_t x_addr = smem_u32(ring + slot * kStageBytes);
               const uint64_t da = desc_k | ((x_addr >> 4) & 0x3FFF);
               const uint64_t db = desc_k | (((x_addr + kChunkBytes) >> 4) & 0x3FFF);
 #pragma unroll
               for (int k = 0; k < kBK / 16; ++k) umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc1, (kb | k) != 0 ? 1u : 0u);
               umma_commit(&empty_bar[slot]);
-              if (kb == num_kb - 1) umma_commit(&zfull_bar[zb]);
+              if (kb == num_kb - 1) umma_commit(zfull_bar);
             }
             __syncwarp();
             advance();
           }
-          if (++zb == 2) {
-            zb = 0;
-            zphase ^= 1;
-          }
+          ++zuse;
         }
         if (r >= kLag) {
-          const int t_end = min((r - kLag + 1) * C, J);
-          for (int t = (r - kLag) * C; t < t_end; ++t) {
+          const int t_end = min((r - kLag + 1) * 2 * C, J);
+          for (int t = (r - kLag) * 2 * C; t < t_end; ++t) {
             if (t == 0 && nitem > 0) {
               // the previous item's Out slice must have left TMEM before this item starts accumulating
               LAP(0);
@@ -300,35 +312,38 @@ sggx_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
               tc_fence_after_sync();
             }
             LAP(0);
-            mbar_wait(&full_bar[slot], phase);  // the G tile
+            mbar_wait(&full_bar[slot], phase);  // slot A: the G tile + the first 32 rows of the Y tile
             LAP(3);
-            const int gslot = slot;
-            const uint32_t g_addr = smem_u32(ring + slot * kSlotBytes);
-            advance();
-            for (int h = 0; h < 2; ++h) {
-              LAP(0);
-              mbar_wait(&full_bar[slot], phase);
-              LAP(4);
-              tc_fence_after_sync();
-              if (elect_one()) {
-                const uint32_t y_addr = smem_u32(ring + slot * kSlotBytes);
-                // half h of the G tile = its k-chunk h ([128 rows][64 vocab]); four K=16 steps, N = 256 each
-                const uint64_t dg = desc_k | (((g_addr + h * kChunkBytes) >> 4) & 0x3FFF);
-                const uint64_t dy = desc_mn | ((y_addr >> 4) & 0x3FFF);
+            tc_fence_after_sync();
+            const int aslot = slot;
+            const uint32_t g_addr = smem_u32(ring + slot * kStageBytes);
+            const uint64_t dg = desc_k | ((g_addr >> 4) & 0x3FFF);
+            if (elect_one()) {
+              const uint64_t dy = desc_mn32 | (((g_addr + kPBytes) >> 4) & 0x3FFF);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                  umma_bf16_ss(tmem_base + kTmemOut, dg + ks * 2, dy + ks * (16 * 128 >> 4), idesc2,
-                               (t | h | ks) != 0 ? 1u : 0u);
-                umma_commit(&empty_bar[slot]);
-                if (h == 1) {
-                  umma_commit(&empty_bar[gslot]);
-                  // every CTA of the cluster learns that this CTA is done with exchange slot (gbase + t) % kXSlots
-                  umma_commit_mcast(&gdone_bar[(gbase + t) % kXSlots], kAllCtas);
-                }
-              }
-              __syncwarp();
-              advance();
+              for (int ks = 0; ks < 2; ++ks)  // K = 16 vocab rows per step, N = 256
+                umma_bf16_ss(tmem_base + kTmemOut, dg + ks * 2, dy + ks * (16 * 128 >> 4), idesc2, (t | ks) != 0 ? 1u : 0u);
             }
+            __syncwarp();
+            advance();
+            LAP(0);
+            mbar_wait(&full_bar[slot], phase);  // slot B: rows 32..127 of the Y tile
+            LAP(4);
+            tc_fence_after_sync();
+            if (elect_one()) {
+              const uint32_t y_addr = smem_u32(ring + slot * kStageBytes);
+              const uint64_t dy = desc_mn96 | ((y_addr >> 4) & 0x3FFF);
+#pragma unroll
+              for (int ks = 2; ks < 8; ++ks)
+                umma_bf16_ss(tmem_base + kTmemOut, dg + (ks >> 2) * (kChunkBytes >> 4) + (ks & 3) * 2,
+                             dy + (ks - 2) * (16 * 128 >> 4), idesc2, 1u);
+              umma_commit(&empty_bar[slot]);
+              umma_commit(&empty_bar[aslot]);
+              // every CTA of the cluster learns that this CTA is done with exchange slot (gbase + t) % kXSlots
+              umma_commit_mcast(&gdone_bar[(gbase + t) % kXSlots], kAllCtas);
+            }
+            __syncwarp();
+            advance();
           }
         }
       }
@@ -344,8 +359,7 @@ sggx_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     const int row_in_blk = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const uint32_t g_local = smem_u32(staging);
-    int zb = 0;
-    uint32_t zphase = 0;
+    uint32_t zuse = 0;
     LAP_DECL;
     int gbase = 0, nitem = 0;
     for (int item = cluster_id; item < p.num_items; item += num_clusters, gbase += J, ++nitem) {
@@ -364,7 +378,7 @@ sggx_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         l = 0.f;
         cf = 0.f;
         tg = -1;
-        if (kCol && col < p.my) {
+        if (kCol && j < J && col < p.my) {
           l = p.c_lse[col] * kLog2e;
           cf = p.c_coef[col];
           tg = p.c_tgt ? p.c_tgt[col] : -1;
@@ -372,96 +386,100 @@ sggx_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       };
       float nl = 0.f, nc = 0.f;
       int nt = -1;
-      if ((int)q < J) load_col((int)q, nl, nc, nt);
+      load_col(2 * (int)q, nl, nc, nt);  // column statistics of the first G tile this CTA produces
       for (int r = 0; r < rounds; ++r) {
-        const int own = r * C + (int)q;
-        if (own >= J) break;
+        const int own2 = r * C + (int)q;
+        if (own2 >= J2) break;
         LAP(0);
-        if (kCol) {
-          s_cl[et] = nl;
-          s_cc[et] = nc;
-          s_ct[et] = nt;
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (own + C < J) load_col(own + C, nl, nc, nt);
-        }
-        mbar_wait(&zfull_bar[zb], zphase);
+        mbar_wait(zfull_bar, zuse & 1u);
+        ++zuse;
         LAP(1);
         tc_fence_after_sync();
-        const int col0 = own * kBT;
-        const int rrel = rt - col0;
-        uint32_t gp[kBT / 2];  // this thread's row of the G tile as bf16 pairs
+        for (int half = 0; half < 2; ++half) {
+          const int t = 2 * own2 + half;  // G tile index
+          if (t >= J) break;
+          const bool last_half = (half == 1) || (t + 1 >= J);
+          if (kCol) {
+            s_cl[et] = nl;
+            s_cc[et] = nc;
+            s_ct[et] = nt;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            load_col((half == 0 && t + 1 < J) ? t + 1 : 2 * (own2 + C), nl, nc, nt);  // next G tile of this CTA
+          }
+          const int col0 = t * kBT;
+          const int rrel = rt - col0;
+          uint32_t gp[kBT / 2];  // this thread's row of the G tile as bf16 pairs
 #pragma unroll
-        for (int ch = 0; ch < kBT / 32; ++ch) {
-          uint32_t rr[32];
-          tmem_ld_32x32(tmem_base + lane_addr + kTmemZ + zb * kBT + ch * 32, rr);
-          tmem_ld_wait();
-          float g[32];
+          for (int ch = 0; ch < kBT / 32; ++ch) {
+            uint32_t rr[32];
+            tmem_ld_32x32(tmem_base + lane_addr + kTmemZ + half * kBT + ch * 32, rr);
+            tmem_ld_wait();
+            float g[32];
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) {
-            const float t = __uint_as_float(rr[jj]) * p.c;
-            float v = 0.f;
-            if (kRow) v = rc * fast_exp2(t - rl);
-            if (kCol) {
-              const int cj = ch * 32 + jj;
-              const float ccj = s_cc[cj];
-              v = fmaf(ccj, fast_exp2(t - s_cl[cj]), v);
-              if (s_ct[cj] == row) v -= ccj;
+            for (int jj = 0; jj < 32; ++jj) {
+              const float tz = __uint_as_float(rr[jj]) * p.c;
+              float v = 0.f;
+              if (kRow) v = rc * fast_exp2(tz - rl);
+              if (kCol) {
+                const int cj = ch * 32 + jj;
+                const float ccj = s_cc[cj];
+                v = fmaf(ccj, fast_exp2(tz - s_cl[cj]), v);
+                if (s_ct[cj] == row) v -= ccj;
+              }
+              g[jj] = v;
             }
-            g[jj] = v;
+            if (kRow && rrel >= 0 && (rrel >> 5) == ch) {
+              const int jj0 = rrel & 31;
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj)
+                if (jj == jj0) g[jj] -= rc;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) gp[ch * 16 + i] = pack_bf16x2(g[2 * i], g[2 * i + 1]);
           }
-          if (kRow && rrel >= 0 && (rrel >> 5) == ch) {
-            const int jj0 = rrel & 31;
-#pragma unroll
-            for (int jj = 0; jj < 32; ++jj)
-              if (jj == jj0) g[jj] -= rc;
+          if (last_half) {
+            tc_fence_before_sync();
+            mbar_arrive(zempty_bar);  // the Z tile has been read: the next MMA1 of this CTA may overwrite it
           }
+          LAP(2);
+          // staging is free: thread 0 passed the bar.sync 3 of the previous tile only after its TMA store completed
 #pragma unroll
-          for (int i = 0; i < 16; ++i) gp[ch * 16 + i] = pack_bf16x2(g[2 * i], g[2 * i + 1]);
-        }
-        tc_fence_before_sync();
-        mbar_arrive(&zempty_bar[zb]);  // Z buffer is free for the MMA1 after next
-        if (++zb == 2) {
-          zb = 0;
-          zphase ^= 1;
-        }
-        LAP(2);
-        // staging is free: thread 0 passed the bar.sync 3 of the previous tile only after its TMA store completed
+          for (int ch = 0; ch < kBT / 32; ++ch) {
+            const uint32_t chunk_off = (ch >> 1) * kChunkBytes;
 #pragma unroll
-        for (int ch = 0; ch < kBT / 32; ++ch) {
-          const uint32_t chunk_off = (ch >> 1) * kChunkBytes;
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            const uint32_t off = chunk_off + sw128_offset(row_in_blk, (ch & 1) * 4 + c4);
-            st_smem_v4(g_local + off, gp[ch * 16 + c4 * 4 + 0], gp[ch * 16 + c4 * 4 + 1], gp[ch * 16 + c4 * 4 + 2],
-                       gp[ch * 16 + c4 * 4 + 3]);
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const uint32_t off = chunk_off + sw128_offset(row_in_blk, (ch & 1) * 4 + c4);
+              st_smem_v4(g_local + off, gp[ch * 16 + c4 * 4 + 0], gp[ch * 16 + c4 * 4 + 1], gp[ch * 16 + c4 * 4 + 2],
+                         gp[ch * 16 + c4 * 4 + 3]);
+            }
           }
-        }
-        fence_proxy_async_smem();  // generic-proxy writes -> visible to the async proxy (the TMA store reads them)
-        asm volatile("bar.sync 2, 128;" ::: "memory");  // the whole tile is in shared memory
-        if (et == 0) {
-          const int g = gbase + own;
-          const int xs = g % kXSlots;
-          const int use = g / kXSlots;
+          fence_proxy_async_smem();  // generic-proxy writes -> visible to the async proxy (the TMA store reads them)
+          asm volatile("bar.sync 2, 128;" ::: "memory");  // the whole tile is in shared memory
+          if (et == 0) {
+            const int g = gbase + t;
+            const int xs = g % kXSlots;
+            const int use = g / kXSlots;
+            LAP(3);
+            if (use > 0) mbar_wait_cluster(&gdone_bar[xs], (uint32_t)(use - 1) & 1u);  // nobody still reads slot xs
+            LAP(6);
+            tma_store_2d(&tm_s, staging, 0, xrow0 + xs * kBM);
+            tma_store_2d(&tm_s, staging + kChunkBytes, kBK, xrow0 + xs * kBM);
+            bulk_commit_and_wait_all();
+            LAP(7);
+            // the tile is complete in global memory (async proxy); one cluster-scope release fence, then relaxed arrives
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            asm volatile("fence.acq_rel.cluster;" ::: "memory");
+            LAP(8);
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+              asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(
+                               mapa_u32(smem_u32(&gready_bar[xs]), (uint32_t)c))
+                           : "memory");
+          }
           LAP(3);
-          if (use > 0) mbar_wait_cluster(&gdone_bar[xs], (uint32_t)(use - 1) & 1u);  // nobody still reads slot xs
-          LAP(6);
-          tma_store_2d(&tm_s, staging, 0, xrow0 + xs * kBM);
-          tma_store_2d(&tm_s, staging + kChunkBytes, kBK, xrow0 + xs * kBM);
-          bulk_commit_and_wait_all();
-          LAP(7);
-          // the tile is complete in global memory (async proxy); one cluster-scope release fence, then relaxed arrives
-          asm volatile("fence.proxy.async.global;" ::: "memory");
-          asm volatile("fence.acq_rel.cluster;" ::: "memory");
-          LAP(8);
-#pragma unroll
-          for (int c = 0; c < C; ++c)
-            asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(
-                             mapa_u32(smem_u32(&gready_bar[xs]), (uint32_t)c))
-                         : "memory");
+          asm volatile("bar.sync 3, 128;" ::: "memory");  // staging (and the column statistics) may be overwritten
+          LAP(4);
         }
-        LAP(3);
-        asm volatile("bar.sync 3, 128;" ::: "memory");  // staging may be overwritten again
-        LAP(4);
       }
       // ---------------------------------------------------------------- this item's Out slice: TMEM -> global
       LAP(0);
@@ -536,7 +554,8 @@ int max_clusters(int* out) {
 }
 
 template <int C, bool kRow, bool kCol>
-int launch(const CUtensorMap& tm_x, const CUtensorMap& tm_y, const CUtensorMap& tm_y2, const void* scratch,
+int launch(const CUtensorMap& tm_x, const CUtensorMap& tm_y, const CUtensorMap& tm_y32, const CUtensorMap& tm_y96,
+           const void* scratch,
            size_t scratch_bytes, const SggxParams& p, cudaStream_t st) {
   int resident = 0;
   int rc = max_clusters<C, kRow, kCol>(&resident);
@@ -561,7 +580,7 @@ int launch(const CUtensorMap& tm_x, const CUtensorMap& tm_y, const CUtensorMap& 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PGICA_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tm_x, tm_y, tm_y2, tm_s, p));
+  PGICA_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tm_x, tm_y, tm_y32, tm_y96, tm_s, p));
   count_launches(1);
   return PGICA_OK;
 }
@@ -605,19 +624,21 @@ int sggx_dispatch(int cluster, const void* x, const void* y, int64_t mx, int64_t
   p.c_coef = c_coef;
   p.c_tgt = c_tgt;
   p.out = out;
-  CUtensorMap tm_x, tm_y, tm_y2;
+  CUtensorMap tm_x, tm_y, tm_y32, tm_y96;
   int rc = make_tmap_bf16(&tm_x, x, mx, k, k, 128);
   if (rc != PGICA_OK) return rc;
   rc = make_tmap_bf16(&tm_y, y, my, k, k, 128);
   if (rc != PGICA_OK) return rc;
-  rc = make_tmap_bf16(&tm_y2, y, my, k, k, 64);  // 64-row boxes: one K-half of a tile for MMA2
+  rc = make_tmap_bf16(&tm_y32, y, my, k, k, 32);  // MMA2 operand, rows 0..31 of a tile (shares a slot with G)
+  if (rc != PGICA_OK) return rc;
+  rc = make_tmap_bf16(&tm_y96, y, my, k, k, 96);  // MMA2 operand, rows 32..127 (a slot of its own)
   if (rc != PGICA_OK) return rc;
   const bool row = r_lse != nullptr, col = c_lse != nullptr;
 #define PGICA_SGGX(CC)                                                                                    \
   do {                                                                                                    \
-    if (row && col) return launch<CC, true, true>(tm_x, tm_y, tm_y2, workspace, workspace_bytes, p, st);   \
-    if (row) return launch<CC, true, false>(tm_x, tm_y, tm_y2, workspace, workspace_bytes, p, st);         \
-    return launch<CC, false, true>(tm_x, tm_y, tm_y2, workspace, workspace_bytes, p, st);                  \
+    if (row && col) return launch<CC, true, true>(tm_x, tm_y, tm_y32, tm_y96, workspace, workspace_bytes, p, st);   \
+    if (row) return launch<CC, true, false>(tm_x, tm_y, tm_y32, tm_y96, workspace, workspace_bytes, p, st);         \
+    return launch<CC, false, true>(tm_x, tm_y, tm_y32, tm_y96, workspace, workspace_bytes, p, st);                  \
   } while (0)
   if (cluster == 2) PGICA_SGGX(2);
   if (cluster == 4) PGICA_SGGX(4);
