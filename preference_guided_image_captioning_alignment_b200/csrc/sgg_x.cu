@@ -37,7 +37,6 @@ constexpr int kBT2 = 2 * kBT;                     // MMA1 covers two G tiles at 
 constexpr uint32_t kStageBytes = kChunkBytes + 2 * kChunkBytes;  // 48 KB ring slot: X chunk + 256-row Y chunk
 constexpr int kRing = 4;
 constexpr int kXSlots = 16;  // exchange-ring depth in tiles (two rounds of a 4-CTA cluster)
-constexpr int kLag = 1;       // MMA2 consumes the tiles of round r - kLag while MMA1 produces round r
 constexpr int kThreads = 256;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr uint32_t kTmemOut = 0, kTmemZ = 256;  // Out [0,256), Z [256,512) (single buffer, 256 columns)
@@ -137,6 +136,11 @@ sggx_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   const int J = p.num_tiles;       // G tiles (128 rows of Y each)
   const int J2 = (J + 1) / 2;      // MMA1 tiles (256 rows of Y each)
   const int rounds = (J2 + C - 1) / C;
+  // This cluster's items (row block, pass), and its rounds numbered straight through all of them ("global rounds"):
+  // MMA1 of global round R is followed by the MMA2s of global round R-1, across item boundaries too, so the tensor
+  // pipe never idles while an Out slice is drained or the first Z tile of an item is turned into G.
+  const int n_my = (p.num_items - cluster_id + num_clusters - 1) / num_clusters;
+  const int T = n_my * rounds;
   const int xrow0 = cluster_id * kXSlots * kBM;  // first row of this cluster's exchange ring in the scratch matrix
 
   if (warp == 0 && lane == 0) {
@@ -181,13 +185,12 @@ sggx_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       }
     };
     LAP_DECL;
-    int gbase = 0;  // exchange-ring sequence number of tile 0 of the current item
-    for (int item = cluster_id; item < p.num_items; item += num_clusters, gbase += J) {
-      const int m_blk = item / p.passes;
-      const int out_col0 = ((item - m_blk * p.passes) * C + (int)q) * kBD;
-      for (int r = 0; r < rounds + kLag; ++r) {
+    for (int R = 0; R <= T; ++R) {
+      {
+        const int it = R / rounds, r = R - it * rounds;
+        const int m_blk = (cluster_id + it * num_clusters) / p.passes;
         const int own2 = r * C + (int)q;
-        if (own2 < J2) {
+        if (R < T && own2 < J2) {
           // A large Y (the LM-head weight in dH) streams from HBM: one cluster in eight pulls the tile this CTA
           // needs two rounds from now into L2, so that nobody's ring stalls on a DRAM round trip.
           const int ahead = own2 + 2 * C;
@@ -211,9 +214,15 @@ sggx_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
             advance();
           }
         }
-        if (r >= kLag) {
-          const int t_end = min((r - kLag + 1) * 2 * C, J);
-          for (int t = (r - kLag) * 2 * C; t < t_end; ++t) {
+      }
+      if (R >= 1) {
+        {
+          const int itp = (R - 1) / rounds, rp = (R - 1) - itp * rounds;
+          const int item_p = cluster_id + itp * num_clusters;
+          const int out_col0 = ((item_p - (item_p / p.passes) * p.passes) * C + (int)q) * kBD;
+          const int gbase = itp * J;  // exchange-ring sequence number of tile 0 of that item
+          const int t_end = min((rp + 1) * 2 * C, J);
+          for (int t = rp * 2 * C; t < t_end; ++t) {
             const int g = gbase + t;
             const int xs = g % kXSlots;
             LAP(0);
@@ -272,11 +281,10 @@ sggx_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     };
     uint32_t zuse = 0;  // own MMA1 tiles issued so far (Z is a single 256-column buffer)
     LAP_DECL;
-    int gbase = 0, nitem = 0;
-    for (int item = cluster_id; item < p.num_items; item += num_clusters, gbase += J, ++nitem) {
-      for (int r = 0; r < rounds + kLag; ++r) {
-        const int own2 = r * C + (int)q;
-        if (own2 < J2) {
+    for (int R = 0; R <= T; ++R) {
+      {
+        const int own2 = (R % rounds) * C + (int)q;
+        if (R < T && own2 < J2) {
           LAP(0);
           mbar_wait(zempty_bar, (zuse & 1u) ^ 1u);  // the epilogue has read the previous Z tile out of TMEM
           LAP(1);
@@ -301,13 +309,17 @@ sggx_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
           }
           ++zuse;
         }
-        if (r >= kLag) {
-          const int t_end = min((r - kLag + 1) * 2 * C, J);
-          for (int t = (r - kLag) * 2 * C; t < t_end; ++t) {
-            if (t == 0 && nitem > 0) {
+      }
+      if (R >= 1) {
+        {
+          const int itp = (R - 1) / rounds, rp = (R - 1) - itp * rounds;
+          const int gbase = itp * J;
+          const int t_end = min((rp + 1) * 2 * C, J);
+          for (int t = rp * 2 * C; t < t_end; ++t) {
+            if (t == 0 && itp > 0) {
               // the previous item's Out slice must have left TMEM before this item starts accumulating
               LAP(0);
-              mbar_wait(outfree_bar, (uint32_t)(nitem - 1) & 1u);
+              mbar_wait(outfree_bar, (uint32_t)(itp - 1) & 1u);
               LAP(1);
               tc_fence_after_sync();
             }
@@ -345,10 +357,12 @@ sggx_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
             __syncwarp();
             advance();
           }
+          if (rp == rounds - 1) {  // that was the last round of an item: its Out slice is complete
+            if (elect_one()) umma_commit(outfull_bar);
+            __syncwarp();
+          }
         }
       }
-      if (elect_one()) umma_commit(outfull_bar);
-      __syncwarp();
     }
     LAP(0);
     if (lane == 0) LAP_FLUSH(4, 5);
@@ -361,35 +375,78 @@ sggx_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     const uint32_t g_local = smem_u32(staging);
     uint32_t zuse = 0;
     LAP_DECL;
-    int gbase = 0, nitem = 0;
-    for (int item = cluster_id; item < p.num_items; item += num_clusters, gbase += J, ++nitem) {
-      const int m_blk = item / p.passes;
-      const int out_col0 = ((item - m_blk * p.passes) * C + (int)q) * kBD;
-      const int row = m_blk * kBM + row_in_blk;
-      float rl = 0.f, rc = 0.f;
-      int rt = -1;
-      if (kRow && row < p.mx) {
-        rl = p.r_lse[row] * kLog2e;
-        rc = p.r_coef[row];
-        rt = p.r_tgt ? p.r_tgt[row] : -1;
-      }
-      auto load_col = [&](int j, float& l, float& cf, int& tg) {
-        const int col = j * kBT + et;
-        l = 0.f;
-        cf = 0.f;
-        tg = -1;
-        if (kCol && j < J && col < p.my) {
-          l = p.c_lse[col] * kLog2e;
-          cf = p.c_coef[col];
-          tg = p.c_tgt ? p.c_tgt[col] : -1;
+    // Out slice of item number `itd` of this cluster: TMEM -> global, then hand TMEM back to the MMA warp
+    auto drain_out = [&](int itd) {
+      const int item_d = cluster_id + itd * num_clusters;
+      const int m_blk_d = item_d / p.passes;
+      const int ocol0 = ((item_d - m_blk_d * p.passes) * C + (int)q) * kBD;
+      const int row_d = m_blk_d * kBM + row_in_blk;
+      LAP(0);
+      mbar_wait(outfull_bar, (uint32_t)itd & 1u);
+      LAP(5);
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int ch = 0; ch < kBD / 32; ++ch) {
+        uint32_t rr[32];
+        tmem_ld_32x32(tmem_base + lane_addr + kTmemOut + ch * 32, rr);
+        tmem_ld_wait();
+        const int col = ocol0 + ch * 32;
+        if (row_d < p.mx) {
+          if (p.out_bf16) {
+            uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + (size_t)row_d * p.ldo + col);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              uint4 v;
+              v.x = pack_bf16x2(__uint_as_float(rr[c4 * 8 + 0]), __uint_as_float(rr[c4 * 8 + 1]));
+              v.y = pack_bf16x2(__uint_as_float(rr[c4 * 8 + 2]), __uint_as_float(rr[c4 * 8 + 3]));
+              v.z = pack_bf16x2(__uint_as_float(rr[c4 * 8 + 4]), __uint_as_float(rr[c4 * 8 + 5]));
+              v.w = pack_bf16x2(__uint_as_float(rr[c4 * 8 + 6]), __uint_as_float(rr[c4 * 8 + 7]));
+              dst[c4] = v;
+            }
+          } else {
+            uint4* dst = reinterpret_cast<uint4*>(static_cast<float*>(p.out) + (size_t)row_d * p.ldo + col);
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) dst[c4] = make_uint4(rr[c4 * 4], rr[c4 * 4 + 1], rr[c4 * 4 + 2], rr[c4 * 4 + 3]);
+          }
         }
-      };
-      float nl = 0.f, nc = 0.f;
-      int nt = -1;
-      load_col(2 * (int)q, nl, nc, nt);  // column statistics of the first G tile this CTA produces
-      for (int r = 0; r < rounds; ++r) {
+      }
+      tc_fence_before_sync();
+      mbar_arrive(outfree_bar);
+    };
+    int row = 0;
+    float rl = 0.f, rc = 0.f, nl = 0.f, nc = 0.f;
+    int rt = -1, nt = -1, gbase = 0;
+    auto load_col = [&](int j, float& l, float& cf, int& tg) {
+      const int col = j * kBT + et;
+      l = 0.f;
+      cf = 0.f;
+      tg = -1;
+      if (kCol && j < J && col < p.my) {
+        l = p.c_lse[col] * kLog2e;
+        cf = p.c_coef[col];
+        tg = p.c_tgt ? p.c_tgt[col] : -1;
+      }
+    };
+    for (int R = 0; R < T; ++R) {
+      const int it = R / rounds, r = R - it * rounds;
+      if (r == 0) {  // a new item: its row block's statistics
+        const int m_blk = (cluster_id + it * num_clusters) / p.passes;
+        row = m_blk * kBM + row_in_blk;
+        gbase = it * J;
+        rl = 0.f;
+        rc = 0.f;
+        rt = -1;
+        if (kRow && row < p.mx) {
+          rl = p.r_lse[row] * kLog2e;
+          rc = p.r_coef[row];
+          rt = p.r_tgt ? p.r_tgt[row] : -1;
+        }
+        load_col(2 * (int)q, nl, nc, nt);  // column statistics of the first G tile this CTA produces
+      }
+      {
         const int own2 = r * C + (int)q;
-        if (own2 >= J2) break;
+        if (own2 < J2) {
+
         LAP(0);
         mbar_wait(zfull_bar, zuse & 1u);
         ++zuse;
@@ -480,40 +537,12 @@ sggx_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
           asm volatile("bar.sync 3, 128;" ::: "memory");  // staging (and the column statistics) may be overwritten
           LAP(4);
         }
-      }
-      // ---------------------------------------------------------------- this item's Out slice: TMEM -> global
-      LAP(0);
-      mbar_wait(outfull_bar, (uint32_t)nitem & 1u);
-      LAP(5);
-      tc_fence_after_sync();
-#pragma unroll 1
-      for (int ch = 0; ch < kBD / 32; ++ch) {
-        uint32_t rr[32];
-        tmem_ld_32x32(tmem_base + lane_addr + kTmemOut + ch * 32, rr);
-        tmem_ld_wait();
-        const int col = out_col0 + ch * 32;
-        if (row < p.mx) {
-          if (p.out_bf16) {
-            uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + col);
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-              uint4 v;
-              v.x = pack_bf16x2(__uint_as_float(rr[c4 * 8 + 0]), __uint_as_float(rr[c4 * 8 + 1]));
-              v.y = pack_bf16x2(__uint_as_float(rr[c4 * 8 + 2]), __uint_as_float(rr[c4 * 8 + 3]));
-              v.z = pack_bf16x2(__uint_as_float(rr[c4 * 8 + 4]), __uint_as_float(rr[c4 * 8 + 5]));
-              v.w = pack_bf16x2(__uint_as_float(rr[c4 * 8 + 6]), __uint_as_float(rr[c4 * 8 + 7]));
-              dst[c4] = v;
-            }
-          } else {
-            uint4* dst = reinterpret_cast<uint4*>(static_cast<float*>(p.out) + (size_t)row * p.ldo + col);
-#pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) dst[c4] = make_uint4(rr[c4 * 4], rr[c4 * 4 + 1], rr[c4 * 4 + 2], rr[c4 * 4 + 3]);
-          }
         }
       }
-      tc_fence_before_sync();
-      mbar_arrive(outfree_bar);
+      // the MMA2s of the previous item's last round were issued right after this round's MMA1: drain that item now
+      if (r == 0 && it > 0) drain_out(it - 1);
     }
+    drain_out(n_my - 1);
     LAP(0);
     if (et == 0) LAP_FLUSH(9, 9);
   }
