@@ -94,10 +94,6 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
-__device__ __forceinline__ void bulk_commit_and_wait_all() {
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // writes performed, not only the source read
-}
 // tcgen05.commit that arrives on the same-offset barrier of every CTA in `mask`
 __device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
@@ -126,7 +122,9 @@ sggx_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   uint64_t* gdone_bar = gready_bar + kXSlots;  // [kXSlots] every CTA has finished MMA2 on the tile in slot s
   uint64_t* outfull_bar = gdone_bar + kXSlots;
   uint64_t* outfree_bar = outfull_bar + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(outfree_bar + 1);
+  uint64_t* stfull_bar = outfree_bar + 1;   // staging holds a complete G tile (128 epilogue arrivals)
+  uint64_t* stfree_bar = stfull_bar + 1;    // the TMA store has read staging: it may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stfree_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t q = cluster_ctarank();
@@ -165,6 +163,8 @@ sggx_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     }
     mbar_init(outfull_bar, 1);
     mbar_init(outfree_bar, 128);
+    mbar_init(stfull_bar, 128);
+    mbar_init(stfree_bar, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -366,6 +366,51 @@ sggx_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     }
     LAP(0);
     if (lane == 0) LAP_FLUSH(4, 5);
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ exchange warp
+    // Takes each finished G tile from the staging buffer to the cluster: TMA store into the exchange ring, wait for
+    // the store to complete, release it to every CTA.  Runs beside the epilogue warps, so the ~3000 cycles of store
+    // completion + fences are off their critical path (they matter when k is small and the epilogue is the pace).
+    uint32_t ntile = 0;
+    LAP_DECL;
+    for (int R = 0; R < T; ++R) {
+      const int it = R / rounds, r = R - it * rounds;
+      const int own2 = r * C + (int)q;
+      if (own2 >= J2) continue;
+      for (int half = 0; half < 2; ++half) {
+        const int t = 2 * own2 + half;
+        if (t >= J) break;
+        const int g = it * J + t;
+        const int xs = g % kXSlots;
+        const int use = g / kXSlots;
+        LAP(0);
+        mbar_wait(stfull_bar, ntile & 1u);
+        LAP(1);
+        if (use > 0) mbar_wait_cluster(&gdone_bar[xs], (uint32_t)(use - 1) & 1u);  // nobody still reads slot xs
+        LAP(2);
+        if (lane == 0) {
+          tma_store_2d(&tm_s, staging, 0, xrow0 + xs * kBM);
+          tma_store_2d(&tm_s, staging + kChunkBytes, kBK, xrow0 + xs * kBM);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging has been read
+          mbar_arrive(stfree_bar);
+          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the tile is complete in global memory
+          // async-proxy writes ordered before one cluster-scope release fence, then relaxed arrives
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+          asm volatile("fence.acq_rel.cluster;" ::: "memory");
+#pragma unroll
+          for (int c = 0; c < C; ++c)
+            asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(
+                             mapa_u32(smem_u32(&gready_bar[xs]), (uint32_t)c))
+                         : "memory");
+        }
+        __syncwarp();
+        LAP(3);
+        ++ntile;
+      }
+    }
+    LAP(0);
+    if (lane == 0) LAP_FLUSH(18, 4);
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue: Z -> G for this CTA's own tiles
     const int quarter = warp & 3;
@@ -373,7 +418,7 @@ sggx_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     const int row_in_blk = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const uint32_t g_local = smem_u32(staging);
-    uint32_t zuse = 0;
+    uint32_t zuse = 0, ntile = 0;
     LAP_DECL;
     // Out slice of item number `itd` of this cluster: TMEM -> global, then hand TMEM back to the MMA warp
     auto drain_out = [&](int itd) {
@@ -499,7 +544,8 @@ sggx_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
             mbar_arrive(zempty_bar);  // the Z tile has been read: the next MMA1 of this CTA may overwrite it
           }
           LAP(2);
-          // staging is free: thread 0 passed the bar.sync 3 of the previous tile only after its TMA store completed
+          mbar_wait(stfree_bar, (ntile & 1u) ^ 1u);  // the exchange warp's TMA store has read the previous tile
+          LAP(3);
 #pragma unroll
           for (int ch = 0; ch < kBT / 32; ++ch) {
             const uint32_t chunk_off = (ch >> 1) * kChunkBytes;
@@ -511,30 +557,9 @@ sggx_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
             }
           }
           fence_proxy_async_smem();  // generic-proxy writes -> visible to the async proxy (the TMA store reads them)
-          asm volatile("bar.sync 2, 128;" ::: "memory");  // the whole tile is in shared memory
-          if (et == 0) {
-            const int g = gbase + t;
-            const int xs = g % kXSlots;
-            const int use = g / kXSlots;
-            LAP(3);
-            if (use > 0) mbar_wait_cluster(&gdone_bar[xs], (uint32_t)(use - 1) & 1u);  // nobody still reads slot xs
-            LAP(6);
-            tma_store_2d(&tm_s, staging, 0, xrow0 + xs * kBM);
-            tma_store_2d(&tm_s, staging + kChunkBytes, kBK, xrow0 + xs * kBM);
-            bulk_commit_and_wait_all();
-            LAP(7);
-            // the tile is complete in global memory (async proxy); one cluster-scope release fence, then relaxed arrives
-            asm volatile("fence.proxy.async.global;" ::: "memory");
-            asm volatile("fence.acq_rel.cluster;" ::: "memory");
-            LAP(8);
-#pragma unroll
-            for (int c = 0; c < C; ++c)
-              asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(
-                               mapa_u32(smem_u32(&gready_bar[xs]), (uint32_t)c))
-                           : "memory");
-          }
-          LAP(3);
-          asm volatile("bar.sync 3, 128;" ::: "memory");  // staging (and the column statistics) may be overwritten
+          mbar_arrive(stfull_bar);   // hand the tile to the exchange warp
+          ++ntile;
+          if (kCol) asm volatile("bar.sync 3, 128;" ::: "memory");  // the column statistics may be overwritten
           LAP(4);
         }
         }

@@ -17,8 +17,9 @@ TRACE_LIB = os.path.join(PKG, "libpgica_trace.so")
 # layout written by sgg_x.cu (exchange through L2); the DSMEM kernel (PGICA_SGG_EXCHANGE=dsmem) has its own layout
 NAMES = ["prod_other", "prod_wait_empty_mma1", "prod_wait_empty_mma2", "prod_wait_gready",
          "mma_issue", "mma_wait_zempty_outfree", "mma_wait_full1", "mma_wait_gtile", "mma_wait_full2",
-         "epi_other", "epi_wait_zfull", "epi_compute", "epi_stage_and_arrive", "epi_barsync3", "epi_wait_outfull",
-         "epi_wait_gdone", "epi_tma_store_complete", "epi_fences"]
+         "epi_other", "epi_wait_zfull", "epi_compute", "epi_wait_stfree", "epi_stage_write", "epi_wait_outfull",
+         "epi_unused6", "epi_unused7", "epi_unused8",
+         "xw_other", "xw_wait_stfull", "xw_wait_gdone", "xw_store_fence_arrive"]
 NAMES_DSMEM = ["prod_other", "prod_wait_empty_mma1", "prod_wait_empty_mma2",
                "mma_issue", "mma_wait_zempty", "mma_wait_full1", "mma_wait_gfull", "mma_wait_full2",
                "epi_other", "epi_wait_zfull", "epi_wait_gfree", "epi_compute", "epi_barsync"]
