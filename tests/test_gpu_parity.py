@@ -408,3 +408,102 @@ def test_opcheck(pg, cuda_device):
     W = torch.randn(30, 64, device=dev, requires_grad=True)
     y = torch.randint(0, 30, (2, 5), device=dev)
     torch.library.opcheck(ops.lmhead_seq_logprob, (h, W, y, None, False), test_utils=("test_schema", "test_faketensor"))
+
+
+# ================================================================================================ backward core
+def _sgg_reference(x, y, scale, row, col):
+    """fp32 torch restatement of the softmax-gradient GEMM (include/pgica.h), G rounded to bf16 like the kernel."""
+    xf, yf = x.float(), y.float()
+    z = (xf @ yf.t()) * scale
+    g = torch.zeros_like(z)
+    rows = torch.arange(x.shape[0], device=x.device)
+    if row is not None:
+        lse, coef, tgt = row
+        oh = torch.zeros_like(z)
+        v = tgt >= 0
+        oh[rows[v], tgt[v].long()] = 1
+        g += coef[:, None] * (torch.exp(z - lse[:, None]) - oh)
+    if col is not None:
+        lse, coef, tgt = col
+        oh = (tgt[None, :].long() == rows[:, None]).float()
+        g += coef[None, :] * (torch.exp(z - lse[None, :]) - oh)
+    return g @ yf, g.to(torch.bfloat16).float() @ yf
+
+
+@pytest.mark.parametrize("mx,my,k,mode", [
+    (128, 128, 256, "row"),        # single-CTA kernel (k = 256)
+    (77, 90, 64, "col"),           # k < 256, ragged rows and columns
+    (300, 1000, 512, "both"),      # 2-CTA clusters, last 256-wide tile half empty
+    (200, 333, 1024, "row"),       # 4-CTA clusters, fewer 256-wide tiles than CTAs
+    (128 * 37 + 5, 700, 1024, "col"),   # more row blocks than resident clusters: persistent loop over items
+    (520, 128 * 9 + 1, 1024, "both"),   # odd number of G tiles, one-column tail
+    (4500, 260, 512, "row"),       # 2-CTA clusters, one round per item, many items
+])
+def test_softmax_grad_gemm_shapes(pg, cuda_device, mx, my, k, mode):
+    from preference_guided_image_captioning_alignment_b200 import functional as F
+    dev = cuda_device
+    torch.manual_seed(mx * 7 + my)
+    x = (torch.randn(mx, k, device=dev) * 0.5).to(torch.bfloat16)
+    y = (torch.randn(my, k, device=dev) * 0.2).to(torch.bfloat16)
+    row = col = None
+    if mode in ("row", "both"):
+        lse_r, _ = F.gemm_lse(x, y, 1.0)
+        coef_r = torch.randn(mx, device=dev)
+        coef_r[::5] = 0
+        tgt_r = torch.randint(0, my, (mx,), device=dev, dtype=torch.int32)
+        tgt_r[::3] = -1
+        row = (lse_r, coef_r, tgt_r)
+    if mode in ("col", "both"):
+        lse_c, _ = F.gemm_lse(y, x, 1.0)
+        coef_c = torch.randn(my, device=dev)
+        coef_c[::5] = 0
+        tgt_c = torch.randint(0, mx, (my,), device=dev, dtype=torch.int32)
+        tgt_c[::3] = -1
+        col = (lse_c, coef_c, tgt_c)
+    out = F.softmax_grad_gemm(x, y, 1.0, row=row, col=col)
+    out2 = F.softmax_grad_gemm(x, y, 1.0, row=row, col=col)
+    assert torch.equal(out, out2)  # deterministic: no atomics anywhere
+    exact, emul = _sgg_reference(x, y, 1.0, row, col)
+    scale = exact.abs().max().item()
+    assert (out - emul).abs().max().item() < 2e-3 * scale + 1e-5    # same arithmetic as the kernel (bf16 G)
+    assert rel(out, exact) < GRAD_RTOL                               # and within the gradient tolerance of fp32
+    ob = F.softmax_grad_gemm(x, y, 1.0, row=row, col=col, out_dtype=torch.bfloat16)
+    assert rel(ob.float(), exact) < GRAD_RTOL
+
+
+def test_softmax_grad_gemm_dsmem_variant_matches(pg, cuda_device, monkeypatch):
+    """The DSMEM-exchange cluster kernel (PGICA_SGG_EXCHANGE=dsmem) and the default L2-exchange kernel agree."""
+    from preference_guided_image_captioning_alignment_b200 import functional as F
+    dev = cuda_device
+    torch.manual_seed(9)
+    x = (torch.randn(640, 1024, device=dev) * 0.5).to(torch.bfloat16)
+    y = (torch.randn(1500, 1024, device=dev) * 0.2).to(torch.bfloat16)
+    lse, _ = F.gemm_lse(x, y, 1.0)
+    row = (lse, torch.randn(640, device=dev), torch.randint(0, 1500, (640,), device=dev, dtype=torch.int32))
+    a = F.softmax_grad_gemm(x, y, 1.0, row=row)
+    monkeypatch.setenv("PGICA_SGG_EXCHANGE", "dsmem")
+    b = F.softmax_grad_gemm(x, y, 1.0, row=row)
+    monkeypatch.delenv("PGICA_SGG_EXCHANGE")
+    assert rel(a, b) < 1e-5
+
+
+def test_cfg4_slice_properties(pg, cuda_device):
+    """One rank's slice of BASELINE config 4 (T = 512, 8 pairs -> 8176 scored rows, 64 row blocks > resident
+    clusters): size-independent properties through the persistent backward."""
+    dev = cuda_device
+    B, T = 4, 512
+    W, h, y, m = _cfg2_inputs(dev, B, T=T)
+    head = pg.FusedDPOHead(beta=0.1)
+    loss, met = head(h[:B], h[B:], W, y[:B], y[B:], m[:B], m[B:], h[:B], h[B:], W)          # KA1
+    assert loss.item() == pytest.approx(math.log(2), rel=1e-6)
+    Wg, hg = W.clone().requires_grad_(True), h.clone().requires_grad_(True)
+    seq = pg.lmhead_sequence_logprobs(hg, Wg, y, m)
+    g1 = torch.autograd.grad(seq.sum(), (hg, Wg), retain_graph=True)
+    g2 = torch.autograd.grad(seq.sum(), (hg, Wg))
+    assert torch.equal(g1[0], g2[0]) and torch.equal(g1[1], g2[1])
+    assert torch.count_nonzero(g1[0][(m[:, 1:] == 0).nonzero(as_tuple=True)]).item() == 0
+    # gradient of sum_b seq_logp[b] w.r.t. hidden on one sequence against the oracle
+    o = cf.lmhead_sequence_logprobs(h[:1].double().cpu().numpy(), W.double().cpu().numpy(), y[:1].cpu().numpy(),
+                                    m[:1].cpu().numpy(), False, grad_seq=np.ones(1))
+    np.testing.assert_allclose(seq.detach()[:1].cpu().numpy(), o["seq_logp"], rtol=LOSS_RTOL)
+    assert rel(g1[0][:1].float(), o["dhidden"]) < GRAD_RTOL
