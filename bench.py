@@ -199,6 +199,15 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    reducer = None
+    state_r = {}
+    if world > 1 and os.environ.get("PGICA_DW_ALLREDUCE", "peer") == "peer":
+        from preference_guided_image_captioning_alignment_b200 import distributed as D
+        reducer = D.PeerAllReduce((V, d), dev)
+        reducer.trace = bool(os.environ.get("PGICA_BENCH_TRACE_AR"))
+        state_r["done"] = torch.cuda.Event()
+        state_r["done"].record()
+
     # ------------------------------------------------------------------ resident step (functional API + events)
     def resident_step(ev=None):
         def mark(i):
@@ -212,18 +221,24 @@ def run_ours(args, rank, world, local_rank):
         loss, metrics, dpc = F.dpo_loss_fwd(seq_p[:B], seq_p[B:], seq_r[:B], seq_r[B:], beta, 0.0, n_global)
         gseq = F.dpo_grad_seq(dpc, one)
         mark(3)
-        _, dw = F.lmhead_logprob_bwd(H, W, rl, rw, lse_p, gseq, False, need_dhidden=False)
+        if reducer is not None:
+            torch.cuda.current_stream().wait_event(state_r["done"])  # last step's all-reduce has left the buffer
+        _, dw = F.lmhead_logprob_bwd(H, W, rl, rw, lse_p, gseq, False, need_dhidden=False,
+                                     dweight_out=reducer.view if reducer is not None else None)
         mark(4)
+        if reducer is not None:
+            dw_ready = torch.cuda.Event()
+            dw_ready.record()
         dh, _ = F.lmhead_logprob_bwd(H, W, rl, rw, lse_p, gseq, False, need_dweight=False)
         mark(5)
-        # The dW all-reduce runs AFTER the dH kernel, not beside it: dH keeps 32 four-CTA clusters resident, and every
-        # cluster that NCCL's CTAs displace waits for the whole collective and then still needs a full row-block time
-        # (measured at N=2: overlapped 1.27 ms vs 0.82 + 0.34 ms back to back).
-        work = None
         if world > 1:
-            work = dist.all_reduce(dw, async_op=True)
-        if world > 1:
-            work.wait()
+            if reducer is not None:
+                # copy-engine all-reduce of dW (distributed.PeerAllReduce), enqueued after the dH kernel so that its
+                # clusters are resident first; the peer copies use no SM and overlap dH
+                state_r["done"] = reducer.all_reduce(after=dw_ready)
+                torch.cuda.current_stream().wait_event(state_r["done"])
+            else:
+                dist.all_reduce(dw)
             packed = torch.cat([loss.reshape(1), metrics])
             dist.all_reduce(packed)
             mark(6)
@@ -245,6 +260,12 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     clocks = sampler.stop() if sampler else None
     launches = lib.pgica_kernel_launches() - launches0
+    if reducer is not None and reducer.trace and rank == 0:
+        tr = reducer.last_trace
+        ref_ev = events[-1][4]  # end of the dW kernel of the last step
+        log("peer all-reduce timeline (ms after the dW kernel finished): " +
+            ", ".join(f"{n} {ref_ev.elapsed_time(e):.3f}" for n, e in tr) +
+            f"; dH kernel done {ref_ev.elapsed_time(events[-1][5]):.3f}")
     elapsed_ms = t_begin.elapsed_time(t_end)
     # order of marks: 0 start,1 after fwd_policy,2 after fwd_ref,3 after dpo,4 after dW,5 after dH,(6 after all-reduce)
     names_in_order = ["fwd_policy", "fwd_reference", "dpo_scalar", "bwd_dW", "bwd_dH"] + (["allreduce_dW"] if world > 1 else [])
@@ -292,7 +313,7 @@ def run_ours(args, rank, world, local_rank):
         loss, metrics = head.forward_stacked(hin, Wp, yd, md, Hrd, Wr, n_global)
         loss.backward()
         if world > 1:
-            dist.all_reduce(Wp.grad)
+            dist.all_reduce(Wp.grad)  # the module API hands back an ordinary autograd gradient: NCCL all-reduce
         hin.requires_grad_(False)
         consumed[slot].record()
         return loss.item()  # device -> host read of the step's result
@@ -337,6 +358,8 @@ def run_ours(args, rank, world, local_rank):
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "pairs_per_gpu": B, "global_pairs": n_global, "seq_len": T, "d": d, "vocab": V,
                    "parallelism": f"dp{world}", "pair_tokens_per_step_per_gpu": pair_tokens_step,
+                   "dw_allreduce": ("none" if world == 1 else "copy-engine peer all-reduce overlapping dH"
+                                    if reducer is not None else "nccl after dH"),
                    "l2": "inputs larger than L2: the step streams 2x103 MB of bf16 LM-head weights and writes a "
                          "206 MB fp32 dW (L2 = 126 MB)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

@@ -184,6 +184,13 @@ int pgica_rownorm_bwd(const void* x, int x_is_bf16, const float* inv_norm, const
                       int64_t dim, int64_t g_pitch, int64_t g_second, float* dx, void* stream);
 int pgica_cast_f32_to_bf16(const float* x, int64_t n, void* y_bf16, void* stream);
 
+/* dst[i] += sum_s srcs[s][i], fp32, n elements (n % 4 == 0, 16-byte aligned pointers), n_src <= 15 sources given as a
+ * HOST array of device pointers.  The reduction step of the copy-engine all-reduce of the LM-head weight gradient
+ * (distributed.PeerAllReduce: chunks pulled from the peers over NVLink, summed here, pushed back); what DDP's
+ * bucket all-reduce does for the reference (pkg/training/trainer.py:201,492,616).  max_ctas bounds the grid so the
+ * kernel fits beside a resident persistent kernel (0 = one CTA per SM).  HBM-bound: (n_src + 2) * 4 bytes / element. */
+int pgica_sum_into_f32(float* dst, const void* const* srcs_host, int n_src, int64_t n, int max_ctas, void* stream);
+
 /* Plumbing pieces of the Stage-2 head, exported so the parity tests can pin them bit-exactly:
  * shift / label / mask layout (components.py:339-344), per-sequence masked sum (components.py:355-360,
  * model.py:1082-1083), per-row backward coefficients. */

@@ -251,6 +251,49 @@ __global__ void rownorm_bwd_kernel(const TX* __restrict__ x, const float* __rest
   }
 }
 
+struct SumSources {
+  const float4* src[15];
+  int n;
+};
+// A handful of CTAs has to stream hundreds of MB (the kernel runs beside a resident persistent kernel), so every
+// thread keeps kSumUnroll independent 16-byte loads per source in flight.
+constexpr int kSumUnroll = 8;
+__global__ void __launch_bounds__(256) sum_into_kernel(float4* __restrict__ dst, const SumSources ss, size_t n4) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  for (; i + (kSumUnroll - 1) * stride < n4; i += kSumUnroll * stride) {
+    float4 a[kSumUnroll];
+#pragma unroll
+    for (int u = 0; u < kSumUnroll; ++u) a[u] = dst[i + u * stride];
+#pragma unroll 1
+    for (int s = 0; s < ss.n; ++s) {
+      float4 v[kSumUnroll];
+#pragma unroll
+      for (int u = 0; u < kSumUnroll; ++u) v[u] = __ldcs(ss.src[s] + i + u * stride);
+#pragma unroll
+      for (int u = 0; u < kSumUnroll; ++u) {
+        a[u].x += v[u].x;
+        a[u].y += v[u].y;
+        a[u].z += v[u].z;
+        a[u].w += v[u].w;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kSumUnroll; ++u) dst[i + u * stride] = a[u];
+  }
+  for (; i < n4; i += stride) {
+    float4 a = dst[i];
+    for (int s = 0; s < ss.n; ++s) {
+      const float4 v = ss.src[s][i];
+      a.x += v.x;
+      a.y += v.y;
+      a.z += v.z;
+      a.w += v.w;
+    }
+    dst[i] = a;
+  }
+}
+
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, size_t n, __nv_bfloat16* __restrict__ y) {
   const size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
@@ -474,6 +517,25 @@ int pgica_rownorm_bwd(const void* x, int x_is_bf16, const float* inv_norm, const
   else
     rownorm_bwd_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(x), inv_norm, static_cast<const float*>(g), r, d,
                                              g_pitch, g_second, dx);
+  PGICA_CUDA_OK(cudaGetLastError());
+  count_launches(1);
+  return PGICA_OK;
+}
+
+int pgica_sum_into_f32(float* dst, const void* const* srcs_host, int n_src, int64_t n, int max_ctas, void* stream) {
+  PGICA_REQUIRE(dst && srcs_host && n_src >= 1 && n_src <= 15 && n > 0 && n % 4 == 0, "sum_into: bad argument");
+  SumSources ss{};
+  ss.n = n_src;
+  for (int s = 0; s < n_src; ++s) {
+    PGICA_REQUIRE(srcs_host[s] && (reinterpret_cast<uintptr_t>(srcs_host[s]) & 15u) == 0, "sum_into: source %d unaligned", s);
+    ss.src[s] = static_cast<const float4*>(srcs_host[s]);
+  }
+  PGICA_REQUIRE((reinterpret_cast<uintptr_t>(dst) & 15u) == 0, "sum_into: destination unaligned");
+  const size_t n4 = (size_t)n / 4;
+  int64_t grid = ceil_div((int64_t)n4, 256);
+  const int64_t cap = max_ctas > 0 ? max_ctas : device_sm_count();
+  if (grid > cap) grid = cap;
+  sum_into_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(dst), ss, n4);
   PGICA_CUDA_OK(cudaGetLastError());
   count_launches(1);
   return PGICA_OK;

@@ -137,16 +137,32 @@ def lmhead_logprob_fwd(hidden, weight, labels, mask=None, length_normalize=False
     return seq_logp, lse, ztgt, row_label, row_weight, nll
 
 
+def sum_into(dst, sources, max_ctas=0):
+    """dst += sum(sources) (fp32, same shape, contiguous); the grid is capped at max_ctas CTAs."""
+    _need_cuda(dst, *sources)
+    lib = _lib.load()
+    arr = (ctypes.c_void_p * len(sources))(*[s.data_ptr() for s in sources])
+    _lib.check(lib.pgica_sum_into_f32(_p(dst), arr, len(sources), dst.numel(), int(max_ctas), _stream()))
+    return dst
+
+
 def lmhead_logprob_bwd(hidden, weight, row_label, row_weight, lse, grad_seq, length_normalize=False,
                        need_dhidden=True, need_dweight=True, dhidden_dtype=torch.bfloat16,
-                       dweight_dtype=torch.float32):
+                       dweight_dtype=torch.float32, dweight_out=None):
     _need_cuda(hidden, weight, grad_seq)
     lib = _lib.load()
     nseq, T, d = hidden.shape
     V = weight.shape[0]
     dev = hidden.device
     dh = torch.empty(nseq, T, d, dtype=dhidden_dtype, device=dev) if need_dhidden else None
-    dw = torch.empty(V, d, dtype=dweight_dtype, device=dev) if need_dweight else None
+    dw = None
+    if need_dweight:
+        if dweight_out is not None:  # caller-owned destination (e.g. a symmetric-memory buffer for the peer all-reduce)
+            if tuple(dweight_out.shape) != (V, d) or not dweight_out.is_contiguous():
+                raise ValueError("dweight_out must be a contiguous (V, d) tensor")
+            dw, dweight_dtype = dweight_out, dweight_out.dtype
+        else:
+            dw = torch.empty(V, d, dtype=dweight_dtype, device=dev)
     need = ctypes.c_size_t(0)
     _lib.check(lib.pgica_lmhead_logprob_workspace_bytes(nseq, T, d, V, ctypes.byref(need)))
     ws = _ws(need.value, dev)

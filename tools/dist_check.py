@@ -96,6 +96,22 @@ def main():
     ok &= res["ok"]
     if rank == 0:
         print(json.dumps(res), flush=True)
+    # ---------------------------------------------------------------- copy-engine all-reduce == NCCL all-reduce
+    from preference_guided_image_captioning_alignment_b200 import distributed as D2
+    red = D2.PeerAllReduce((1003, 257), dev)
+    g = torch.Generator(device="cpu").manual_seed(100 + rank)
+    local = torch.randn(1003, 257, generator=g).to(dev)
+    for trial in range(3):
+        red.view.copy_(local * (trial + 1))
+        want = (local * (trial + 1)).clone()
+        dist.all_reduce(want)
+        ev = red.all_reduce()
+        torch.cuda.current_stream().wait_event(ev)
+        err = (red.view - want).abs().max().item()
+        res = {"check": "peer_allreduce", "world": world, "trial": trial, "maxabs": err, "ok": bool(err < 1e-5)}
+        ok &= res["ok"]
+        if rank == 0:
+            print(json.dumps(res), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
