@@ -19,9 +19,7 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
-import tempfile
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -61,43 +59,56 @@ def peaks():
 
 
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled through NVML from a thread DURING the timed region (about one sample per
+    millisecond; `nvidia-smi -lms` needs longer to start than a 100 ms timed region lasts)."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4))
 
     def __init__(self, index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        import threading
+        self.samples, self.masks, self.power = [], [], []
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}",
-                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
-                                      stderr=subprocess.DEVNULL)
-        except Exception:
-            pass
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].strip().isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        except Exception as e:  # no NVML: report nulls rather than fail the bench
+            log("clock sampler unavailable:", repr(e))
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.masks.append(int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(0.001)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        if self._t is None:
             return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 6]
-        os.unlink(self.f.name)
-        if not rows:
-            return out
-        sm = [float(r[0]) for r in rows if r[0].strip().replace(".", "").isdigit()]
-        if sm:
-            out["sm_mhz"] = statistics.median(sm)
-            out["sm_max_mhz"] = float(rows[0][1])
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for i, n in enumerate(names):
-            if any(r[3 + i].strip().lower().startswith("active") for r in rows):
-                out["reasons"].append(n)
-        out["samples"] = len(rows)
+        self._stop.set()
+        self._t.join(timeout=2)
+        if self.samples:
+            out["sm_mhz"] = statistics.median(self.samples)
+            out["sm_min_mhz"] = min(self.samples)
+            out["samples"] = len(self.samples)
+        if self.power:
+            out["power_w_max"] = max(self.power)
+        for name, bit in self.REASONS:
+            if any(m & bit for m in self.masks):
+                out["reasons"].append(name)
         return out
 
 
