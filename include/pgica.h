@@ -108,6 +108,27 @@ int pgica_softmax_grad_gemm(const void* x, const void* y, int64_t mx, int64_t my
                             size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * K2+K4 in one launch — "dual softmax-gradient GEMM": both products of a backward pass from ONE tile-wise
+ * recomputation of the logits (3 GEMM-units of tensor work instead of the 4 that two pgica_softmax_grad_gemm
+ * calls execute):
+ *
+ *   out_x[i,:] = sum_j G(i,j) * y[j,:]      out_y[j,:] = sum_i G(i,j) * x[i,:]      (G as above)
+ *
+ * DPO head: x = hidden, y = LM-head weight, row term  =>  out_x = dhidden, out_y = dweight.
+ * NT-Xent:  x = a, y = b, both terms                  =>  out_x = da,      out_y = db.
+ * k must be a multiple of 512 (<= 2048).  One persistent cooperative grid over all SMs (sgg_f.cu): CTAs either
+ * recompute G tiles or keep a 128 x 512 slice of out_x / out_y resident in TMEM; tiles travel through an
+ * L2-resident exchange ring inside `workspace` (pgica_softmax_grad_gemm_dual_workspace_bytes, 256-byte aligned).
+ * out_y must be fp32 when x has more row blocks than fit one chunk (it is then accumulated in place).
+ * ---------------------------------------------------------------------------------------------- */
+int pgica_softmax_grad_gemm_dual_workspace_bytes(int64_t mx, int64_t my, int64_t k, size_t* bytes_host);
+int pgica_softmax_grad_gemm_dual(const void* x, const void* y, int64_t mx, int64_t my, int64_t k, float scale,
+                                 const float* r_lse, const float* r_coef, const int32_t* r_tgt, const float* c_lse,
+                                 const float* c_coef, const int32_t* c_tgt, void* out_x, int out_x_is_bf16,
+                                 void* out_y, int out_y_is_bf16, void* workspace, size_t workspace_bytes,
+                                 void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Stage-2 head, hidden-state level (logits never materialised).
  *
  * pgica_lmhead_logprob_fwd: for nseq sequences of seqlen positions, hidden bf16 [nseq*seqlen][d], weight bf16

@@ -6,6 +6,12 @@
 extern "C" {
 
 using namespace pgica;
+}
+namespace pgica {
+bool sggf_supported(int64_t mx, int64_t my, int64_t k);  // sgg_f.cu
+size_t sggf_workspace_bytes();
+}  // namespace pgica
+extern "C" {
 
 // ---- internal building blocks defined in the other translation units
 // (pgica_softmax_grad_gemm and its workspace query are declared in pgica.h)
@@ -19,6 +25,7 @@ int pgica_lmhead_logprob_workspace_bytes(int64_t nseq, int64_t seqlen, int64_t d
   size_t x = 0;
   rc = pgica_softmax_grad_gemm_workspace_bytes(nseq * seqlen, vocab, d, &x);
   if (rc != PGICA_OK) return rc;
+  if (sggf_supported(nseq * seqlen, vocab, d) && sggf_workspace_bytes() > x) x = sggf_workspace_bytes();
   const size_t bwd = align_up((size_t)(nseq * seqlen) * sizeof(float), 256) + x;
   *bytes_host = g > bwd ? g : bwd;
   return PGICA_OK;
@@ -57,6 +64,12 @@ int pgica_lmhead_logprob_bwd(const void* hidden, const void* weight, const int32
   const size_t xws_bytes = xws ? workspace_bytes - coef_bytes : 0;
   int rc = pgica_row_coef(grad_seq, row_weight, nseq, seqlen, length_normalize, -1.0f, ncoef, stream);
   if (rc != PGICA_OK) return rc;
+  if (dhidden && dweight && sggf_supported(rows, vocab, d) && xws_bytes >= sggf_workspace_bytes() &&
+      !(dweight_is_bf16 && rows > 24 * 128))
+    // both gradients from one recomputation of the logits (sgg_f.cu)
+    return pgica_softmax_grad_gemm_dual(hidden, weight, rows, vocab, d, 1.0f, lse, ncoef, row_label, nullptr, nullptr,
+                                        nullptr, dhidden, dhidden_is_bf16, dweight, dweight_is_bf16, xws, xws_bytes,
+                                        stream);
   if (dhidden) {
     rc = pgica_softmax_grad_gemm(hidden, weight, rows, vocab, d, 1.0f, lse, ncoef, row_label, nullptr, nullptr,
                                  nullptr, dhidden, dhidden_is_bf16, xws, xws_bytes, stream);

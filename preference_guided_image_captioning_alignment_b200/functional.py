@@ -109,6 +109,27 @@ def softmax_grad_gemm(x, y, scale=1.0, row=None, col=None, out_dtype=torch.float
     return out
 
 
+def softmax_grad_gemm_dual(x, y, scale=1.0, row=None, col=None, out_x_dtype=torch.float32, out_y_dtype=torch.float32):
+    """(out_x, out_y) = (G y, G^T x) from one recomputation of G(x y^T) (pgica_softmax_grad_gemm_dual)."""
+    _need_cuda(x, y)
+    lib = _lib.load()
+    mx, k = x.shape
+    my = y.shape[0]
+    out_x = torch.empty(mx, k, dtype=out_x_dtype, device=x.device)
+    out_y = torch.empty(my, k, dtype=out_y_dtype, device=x.device)
+    r = row if row is not None else (None, None, None)
+    c = col if col is not None else (None, None, None)
+    need = ctypes.c_size_t(0)
+    _lib.check(lib.pgica_softmax_grad_gemm_dual_workspace_bytes(mx, my, k, ctypes.byref(need)))
+    ws = _ws(need.value, x.device)
+    _lib.check(lib.pgica_softmax_grad_gemm_dual(_p(x), _p(y), mx, my, k, float(scale), _p(r[0]), _p(r[1]), _p(r[2]),
+                                                _p(c[0]), _p(c[1]), _p(c[2]), _p(out_x),
+                                                1 if out_x_dtype == torch.bfloat16 else 0, _p(out_y),
+                                                1 if out_y_dtype == torch.bfloat16 else 0, _p(ws), need.value,
+                                                _stream()))
+    return out_x, out_y
+
+
 # ----------------------------------------------------------------------------------------- Stage-2 head
 def lmhead_logprob_fwd(hidden, weight, labels, mask=None, length_normalize=False, want_nll=False):
     """hidden bf16 [nseq, T, d], weight bf16 [V, d], labels int64 [nseq, T] -> seq_logp [nseq] + saved ctx."""

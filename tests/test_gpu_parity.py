@@ -507,3 +507,80 @@ def test_cfg4_slice_properties(pg, cuda_device):
                                     m[:1].cpu().numpy(), False, grad_seq=np.ones(1))
     np.testing.assert_allclose(seq.detach()[:1].cpu().numpy(), o["seq_logp"], rtol=LOSS_RTOL)
     assert rel(g1[0][:1].float(), o["dhidden"]) < GRAD_RTOL
+
+
+# ================================================================================================ dual backward
+def _dual_inputs(dev, mx, my, k, mode):
+    from preference_guided_image_captioning_alignment_b200 import functional as F
+    torch.manual_seed(mx * 11 + my)
+    x = (torch.randn(mx, k, device=dev) * 0.5).to(torch.bfloat16)
+    y = (torch.randn(my, k, device=dev) * 0.2).to(torch.bfloat16)
+    row = col = None
+    if mode in ("row", "both"):
+        lse_r, _ = F.gemm_lse(x, y, 1.0)
+        coef_r = torch.randn(mx, device=dev)
+        coef_r[::5] = 0
+        tgt_r = torch.randint(0, my, (mx,), device=dev, dtype=torch.int32)
+        tgt_r[::3] = -1
+        row = (lse_r, coef_r, tgt_r)
+    if mode in ("col", "both"):
+        lse_c, _ = F.gemm_lse(y, x, 1.0)
+        coef_c = torch.randn(my, device=dev)
+        coef_c[::5] = 0
+        tgt_c = torch.randint(0, mx, (my,), device=dev, dtype=torch.int32)
+        tgt_c[::3] = -1
+        col = (lse_c, coef_c, tgt_c)
+    return x, y, row, col
+
+
+@pytest.mark.parametrize("mx,my,k,mode,plan", [
+    (128, 128, 512, "row", None),          # one tile, one split
+    (300, 1000, 512, "both", None),        # ragged rows and columns, odd tile count
+    (200, 333, 1024, "row", None),         # two 512-column splits
+    (128 * 5 + 7, 128 * 9 + 1, 1024, "row", "2,4"),   # 3 chunks of 2 row blocks (OutY accumulated), 3 passes, 1-col tail
+    (128 * 7, 128 * 6, 512, "both", "3,2"),           # chunks of 3/3/1, passes of 2: Rc < column pairs never, odd rows
+    (128 * 2, 128 * 11, 1024, "col", "4,6"),          # fewer row blocks than the chunk; column term only
+    (2048, 5003, 1024, "row", None),       # the planner's own split on a mid-size head
+])
+def test_softmax_grad_gemm_dual(pg, cuda_device, monkeypatch, mx, my, k, mode, plan):
+    """Both backward products from one recomputation (sgg_f.cu) against fp32 torch, the bf16-G emulation and the
+    two single-product launches; deterministic."""
+    from preference_guided_image_captioning_alignment_b200 import functional as F
+    x, y, row, col = _dual_inputs(cuda_device, mx, my, k, mode)
+    if plan:
+        monkeypatch.setenv("PGICA_SGGF_PLAN", plan)
+    ox, oy = F.softmax_grad_gemm_dual(x, y, 1.0, row=row, col=col)
+    ox2, oy2 = F.softmax_grad_gemm_dual(x, y, 1.0, row=row, col=col)
+    assert torch.equal(ox, ox2) and torch.equal(oy, oy2)
+    exact_x, emul_x = _sgg_reference(x, y, 1.0, row, col)
+    exact_y, emul_y = _sgg_reference(y, x, 1.0, col, row)
+    for out, exact, emul in ((ox, exact_x, emul_x), (oy, exact_y, emul_y)):
+        scale = exact.abs().max().item()
+        assert (out - emul).abs().max().item() < 2e-3 * scale + 1e-5
+        assert rel(out, exact) < GRAD_RTOL
+    sx = F.softmax_grad_gemm(x, y, 1.0, row=row, col=col)
+    sy = F.softmax_grad_gemm(y, x, 1.0, row=col, col=row)
+    assert rel(ox, sx) < 1e-3 and rel(oy, sy) < 1e-3
+    bx, _ = F.softmax_grad_gemm_dual(x, y, 1.0, row=row, col=col, out_x_dtype=torch.bfloat16)
+    assert rel(bx.float(), exact_x) < GRAD_RTOL
+
+
+def test_lmhead_backward_dual_matches_split(pg, cuda_device, monkeypatch):
+    """pgica_lmhead_logprob_bwd: the one-launch dual backward and the two-launch backward give the same gradients."""
+    from preference_guided_image_captioning_alignment_b200 import functional as F
+    dev = cuda_device
+    B, T, d, V = 6, 64, 1024, 5003
+    g = torch.Generator().manual_seed(5)
+    W = (torch.randn(V, d, generator=g) * 0.02).to(torch.bfloat16).to(dev)
+    H = torch.randn(B, T, d, generator=g).to(torch.bfloat16).to(dev)
+    y = torch.randint(0, V, (B, T), generator=g).to(dev)
+    m = torch.ones(B, T, dtype=torch.long, device=dev)
+    m[:, T - 9:] = 0
+    seq, lse, _, rl, rw, _ = F.lmhead_logprob_fwd(H, W, y, m, False)
+    gseq = torch.randn(B, device=dev)
+    monkeypatch.setenv("PGICA_SGG_FUSED", "1")
+    dh1, dw1 = F.lmhead_logprob_bwd(H, W, rl, rw, lse, gseq, False)
+    monkeypatch.setenv("PGICA_SGG_FUSED", "0")
+    dh0, dw0 = F.lmhead_logprob_bwd(H, W, rl, rw, lse, gseq, False)
+    assert rel(dh1.float(), dh0.float()) < 2e-3 and rel(dw1, dw0) < 2e-3
+    assert torch.count_nonzero(dh1[:, T - 10:]).item() == 0  # rows that score nothing get exactly zero
