@@ -32,6 +32,7 @@ UNIT = "pair-tokens/s"
 WORKLOAD = ("cfg2: Stage-2 DPO loss head, GPT-2 Medium LM head d=1024 V=50257, chosen/rejected seq 128, 16 pairs per "
             "GPU, beta=0.1, policy fwd+bwd + frozen-reference fwd, random-init, all-ones masks")
 FLOP_PER_PAIR_TOKEN = 16 * CFG["d"] * CFG["vocab"]  # policy fwd 4dV + ref fwd 4dV + policy bwd 8dV
+NCU_TRAFFIC_DUAL = 872.0e6  # dram read + write of one sggf_kernel launch on cfg2 (profiles/r1_ncu_full_sggf.txt)
 
 
 def log(*a):
@@ -203,7 +204,7 @@ def run_ours(args, rank, world, local_rank):
     m_host = torch.ones(2 * B, T, dtype=torch.long).pin_memory()
     H, Hr, y, m = H_host.to(dev), Hr_host.to(dev), y_host.to(dev), m_host.to(dev)
     one = torch.ones((), device=dev)
-    phases = ["fwd_policy", "fwd_reference", "dpo_scalar", "bwd_dH", "bwd_dW"] + (["allreduce_dW"] if world > 1 else [])
+    fused = os.environ.get("PGICA_SGG_FUSED", "1") != "0"  # dH and dW from one recomputation (sgg_f.cu) vs two launches
 
     def barrier():
         if world > 1:
@@ -212,7 +213,7 @@ def run_ours(args, rank, world, local_rank):
 
     reducer = None
     state_r = {}
-    if world > 1 and os.environ.get("PGICA_DW_ALLREDUCE", "peer") == "peer":
+    if world > 1 and not fused and os.environ.get("PGICA_DW_ALLREDUCE", "peer") == "peer":
         from preference_guided_image_captioning_alignment_b200 import distributed as D
         reducer = D.PeerAllReduce((V, d), dev)
         reducer.trace = bool(os.environ.get("PGICA_BENCH_TRACE_AR"))
@@ -232,16 +233,21 @@ def run_ours(args, rank, world, local_rank):
         loss, metrics, dpc = F.dpo_loss_fwd(seq_p[:B], seq_p[B:], seq_r[:B], seq_r[B:], beta, 0.0, n_global)
         gseq = F.dpo_grad_seq(dpc, one)
         mark(3)
-        if reducer is not None:
-            torch.cuda.current_stream().wait_event(state_r["done"])  # last step's all-reduce has left the buffer
-        _, dw = F.lmhead_logprob_bwd(H, W, rl, rw, lse_p, gseq, False, need_dhidden=False,
-                                     dweight_out=reducer.view if reducer is not None else None)
-        mark(4)
-        if reducer is not None:
-            dw_ready = torch.cuda.Event()
-            dw_ready.record()
-        dh, _ = F.lmhead_logprob_bwd(H, W, rl, rw, lse_p, gseq, False, need_dweight=False)
-        mark(5)
+        if fused:
+            dh, dw = F.lmhead_logprob_bwd(H, W, rl, rw, lse_p, gseq, False)
+            mark(4)
+            mark(5)
+        else:
+            if reducer is not None:
+                torch.cuda.current_stream().wait_event(state_r["done"])  # last step's all-reduce has left the buffer
+            _, dw = F.lmhead_logprob_bwd(H, W, rl, rw, lse_p, gseq, False, need_dhidden=False,
+                                         dweight_out=reducer.view if reducer is not None else None)
+            mark(4)
+            if reducer is not None:
+                dw_ready = torch.cuda.Event()
+                dw_ready.record()
+            dh, _ = F.lmhead_logprob_bwd(H, W, rl, rw, lse_p, gseq, False, need_dweight=False)
+            mark(5)
         if world > 1:
             if reducer is not None:
                 # copy-engine all-reduce of dW (distributed.PeerAllReduce), enqueued after the dH kernel so that its
@@ -278,10 +284,14 @@ def run_ours(args, rank, world, local_rank):
             ", ".join(f"{n} {ref_ev.elapsed_time(e):.3f}" for n, e in tr) +
             f"; dH kernel done {ref_ev.elapsed_time(events[-1][5]):.3f}")
     elapsed_ms = t_begin.elapsed_time(t_end)
-    # order of marks: 0 start,1 after fwd_policy,2 after fwd_ref,3 after dpo,4 after dW,5 after dH,(6 after all-reduce)
-    names_in_order = ["fwd_policy", "fwd_reference", "dpo_scalar", "bwd_dW", "bwd_dH"] + (["allreduce_dW"] if world > 1 else [])
+    # order of marks: 0 start,1 after fwd_policy,2 after fwd_ref,3 after dpo,4 after dW (or the fused backward),
+    # 5 after dH,(6 after all-reduce)
+    names_in_order = ["fwd_policy", "fwd_reference", "dpo_scalar", "bwd_dH_dW" if fused else "bwd_dW", "bwd_dH"] + \
+        (["allreduce_dW"] if world > 1 else [])
     phase_ms = {n: statistics.mean(events[k][i].elapsed_time(events[k][i + 1]) for k in range(args.steps))
                 for i, n in enumerate(names_in_order)}
+    if fused:
+        del phase_ms["bwd_dH"]
     if world > 1:
         t = torch.tensor([elapsed_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -349,16 +359,22 @@ def run_ours(args, rank, world, local_rank):
         return
     pk = peaks()
     rows = 2 * B * T  # rows the GEMMs actually run over (the unscored last position included)
-    flops = {"fwd_policy": 2.0 * rows * d * V, "fwd_reference": 2.0 * rows * d * V, "bwd_dH": 2.0 * rows * d * V,
-             "bwd_dW": 2.0 * rows * d * V}
+    gemm = 2.0 * rows * d * V  # one GEMM-unit: rows x V x d
+    flops = {"fwd_policy": gemm, "fwd_reference": gemm}
+    flops.update({"bwd_dH_dW": 2 * gemm} if fused else {"bwd_dH": gemm, "bwd_dW": gemm})
     kernels = {n: {"ms": phase_ms[n], "tflops": flops[n] / phase_ms[n] / 1e9, "algorithmic_flops": flops[n]}
                for n in flops}
     dom = max(flops, key=lambda n: phase_ms[n])
-    roofline = {"bound": "tensor", "kernel": {"fwd_policy": "gemm_lse_kernel", "fwd_reference": "gemm_lse_kernel",
-                                               "bwd_dH": "sgg_kernel<row>", "bwd_dW": "sgg_kernel<col>"}[dom],
+    kname = {"fwd_policy": "gemm_lse_kernel", "fwd_reference": "gemm_lse_kernel", "bwd_dH": "sggx_kernel<4,row>",
+             "bwd_dW": "sggx_kernel<4,col>", "bwd_dH_dW": "sggf_kernel<row> (dual: dH and dW from one recomputation)"}
+    # DRAM bytes per launch of that kernel from `ncu --set full` (profiles/r1_ncu_full_*.txt), cfg2 shape
+    traffic = {"fwd_policy": 121.4e6, "fwd_reference": 120.3e6, "bwd_dH": 116.9e6, "bwd_dW": 282.1e6,
+               "bwd_dH_dW": NCU_TRAFFIC_DUAL}
+    roofline = {"bound": "tensor", "kernel": kname[dom],
                 "phase": dom, "achieved": kernels[dom]["tflops"], "peak": pk["burst"], "unit": "TFLOP/s",
                 "frac": kernels[dom]["tflops"] / pk["burst"], "peak_source": pk["source"] + " bf16 dense, burst",
-                "traffic": None,
+                "traffic": traffic[dom],
+                "executed_tflops": kernels[dom]["tflops"] * (1.5 if dom == "bwd_dH_dW" else 2.0 if dom.startswith("bwd") else 1.0),
                 "step_achieved": FLOP_PER_PAIR_TOKEN * pair_tokens_step / (elapsed_ms / args.steps) / 1e9,
                 "step_frac": FLOP_PER_PAIR_TOKEN * pair_tokens_step / (elapsed_ms / args.steps) / 1e9 / pk["burst"]}
     cpu_val, cpu_sec, cpu_threads = time_cpu_reference(4, 2, 1)
@@ -369,8 +385,10 @@ def run_ours(args, rank, world, local_rank):
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "pairs_per_gpu": B, "global_pairs": n_global, "seq_len": T, "d": d, "vocab": V,
                    "parallelism": f"dp{world}", "pair_tokens_per_step_per_gpu": pair_tokens_step,
+                   "backward": "dual kernel: dH and dW from one recomputation of the logits" if fused
+                               else "one launch per product",
                    "dw_allreduce": ("none" if world == 1 else "copy-engine peer all-reduce overlapping dH"
-                                    if reducer is not None else "nccl after dH"),
+                                    if reducer is not None else "nccl fp32 all-reduce after the backward"),
                    "l2": "inputs larger than L2: the step streams 2x103 MB of bf16 LM-head weights and writes a "
                          "206 MB fp32 dW (L2 = 126 MB)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

@@ -59,6 +59,33 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t c
   return PGICA_OK;
 }
 
+int make_tmap_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride,
+                  uint32_t box_rows) {
+  PFN_cuTensorMapEncodeTiled enc = resolve_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return PGICA_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || (row_stride * 4) % 16 != 0) {
+    set_error("TMA operand must be 16-byte aligned with a 16-byte-multiple row pitch (base %p, pitch %llu B)", base,
+              (unsigned long long)(row_stride * 4));
+    return PGICA_ERR_INVALID_ARGUMENT;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {row_stride * 4};
+  cuuint32_t box[2] = {32u, box_rows};
+  cuuint32_t estride[2] = {1u, 1u};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (fp32) failed with CUresult %d (rows %llu cols %llu pitch %llu box_rows %u)", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)row_stride, box_rows);
+    return PGICA_ERR_CUDA;
+  }
+  return PGICA_OK;
+}
+
 static std::atomic<unsigned long long> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 unsigned long long launches_so_far() { return g_launches.load(std::memory_order_relaxed); }

@@ -36,6 +36,10 @@ const char* get_error();
 int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride,
                    uint32_t box_rows);
 
+// Row-major [rows][cols] fp32 matrix; box = box_rows x 32 columns (128 B), SWIZZLE_128B (TMA stores / reductions).
+int make_tmap_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride,
+                  uint32_t box_rows);
+
 int device_sm_count();
 
 // process-wide count of kernels this library has launched (bench.py reports it as `gpu_launches`)

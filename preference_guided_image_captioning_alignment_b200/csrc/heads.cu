@@ -64,8 +64,7 @@ int pgica_lmhead_logprob_bwd(const void* hidden, const void* weight, const int32
   const size_t xws_bytes = xws ? workspace_bytes - coef_bytes : 0;
   int rc = pgica_row_coef(grad_seq, row_weight, nseq, seqlen, length_normalize, -1.0f, ncoef, stream);
   if (rc != PGICA_OK) return rc;
-  if (dhidden && dweight && sggf_supported(rows, vocab, d) && xws_bytes >= sggf_workspace_bytes() &&
-      !(dweight_is_bf16 && rows > 24 * 128))
+  if (dhidden && dweight && !dweight_is_bf16 && sggf_supported(rows, vocab, d) && xws_bytes >= sggf_workspace_bytes())
     // both gradients from one recomputation of the logits (sgg_f.cu)
     return pgica_softmax_grad_gemm_dual(hidden, weight, rows, vocab, d, 1.0f, lse, ncoef, row_label, nullptr, nullptr,
                                         nullptr, dhidden, dhidden_is_bf16, dweight, dweight_is_bf16, xws, xws_bytes,
@@ -94,6 +93,7 @@ int pgica_ntxent_workspace_bytes(int64_t rows_a, int64_t rows_b, int64_t dim, si
   size_t x = 0;
   rc = pgica_softmax_grad_gemm_workspace_bytes(rows_a, rows_b, dim, &x);
   if (rc != PGICA_OK) return rc;
+  if (sggf_supported(rows_a, rows_b, dim) && sggf_workspace_bytes() > x) x = sggf_workspace_bytes();
   const size_t bwd = 2 * align_up((size_t)rows_a * 4, 256) + 2 * align_up((size_t)rows_b * 4, 256) + x;
   *bytes_host = fwd > bwd ? fwd : bwd;
   return PGICA_OK;
@@ -137,6 +137,10 @@ int pgica_ntxent_bwd(const void* a, const void* b, int64_t rows_a, int64_t rows_
   if (rc != PGICA_OK) return rc;
   rc = pgica_ntxent_coef(grad_loss, grad_mult * inv_tau, rows_b, -diag_offset, rows_a, ccoef, ctgt, stream);
   if (rc != PGICA_OK) return rc;
+  if (da && db && !db_is_bf16 && sggf_supported(rows_a, rows_b, dim) && xws_bytes >= sggf_workspace_bytes())
+    // dA and dB from one recomputation of the similarity tiles (sgg_f.cu)
+    return pgica_softmax_grad_gemm_dual(a, b, rows_a, rows_b, dim, inv_tau, lse_row, rcoef, rtgt, lse_col, ccoef, ctgt,
+                                        da, da_is_bf16, db, db_is_bf16, xws, xws_bytes, stream);
   if (da) {
     rc = pgica_softmax_grad_gemm(a, b, rows_a, rows_b, dim, inv_tau, lse_row, rcoef, rtgt, lse_col, ccoef, ctgt, da,
                                  da_is_bf16, xws, xws_bytes, stream);

@@ -8,25 +8,29 @@
 // 4 GEMM-units of tensor work for 2 units of result.  Here a tile of G is produced once and consumed twice, 3 units.
 // TMEM is what makes that possible and what shapes the kernel: an SM holds 128 x 512 fp32 accumulators, so the
 // 148 SMs together hold 74 slices of (128 rows x 1024 columns).  The whole GPU runs ONE persistent cooperative
-// grid whose CTAs take one of three roles for the lifetime of the launch:
+// grid of CTA PAIRS (2-CTA clusters, tcgen05 cta_group::2: M = 256 instructions whose B operand is split across
+// the two shared memories, which halves the operand fill and read traffic per SM — with single-CTA instructions
+// the tensor pipe lost 15-25 % to shared-memory bandwidth, profiles/r1_trace_sggf_v1_1cta.log).  A pair takes one
+// of three roles for the lifetime of the launch:
 //
-//   X-holders  R*S CTAs   (S = k/512) keep OutX of R row blocks resident in TMEM for a whole chunk of R row
-//                         blocks and accumulate OutX[r] += G(r, c) * Y[c]  for every column tile c,
-//   Y-holders  Cw*S CTAs  keep OutY of Cw column tiles resident for one pass over the chunk's R row blocks and
-//                         accumulate OutY[c] += G(r, c)^T * X[r]  (G^T is the same tile read MN-major),
-//   producers  the rest   recompute Z = X[r] Y[c, c+1]^T (N = 256), turn it into two bf16 G tiles and publish them
-//                         with a TMA store into an exchange ring in global memory (a few MB, overwritten every few
-//                         tiles, L2-resident) followed by a release store to a per-slot flag.
+//   X-holders  (R/2)*S pairs (S = k/512): CTA rho keeps OutX of row block 2rp + rho (512 columns) resident in
+//              TMEM for a whole chunk of R row blocks and accumulates OutX[r] += G(r, c) * Y[c] over all c,
+//   Y-holders  (Cw/2)*S pairs: CTA rho keeps OutY of column tile 2cp + rho resident for one pass over the chunk's
+//              row blocks and accumulates OutY[c] += G(r, c)^T * X[r]  (G^T is the same tile read MN-major),
+//   producers  the rest: recompute the 256 x 256 quad Z = X[2rp, 2rp+1] Y[2cp, 2cp+1]^T (CTA rho ends up with
+//              the rows of block 2rp + rho), turn it into bf16 G tiles and publish them with a TMA store into an
+//              exchange ring in global memory (a few MB, overwritten every few tiles, L2-resident) followed by a
+//              release store to a per-slot flag.
 //
 // Consumers poll the flag (acquire), pull the tile through TMA into shared memory and feed tcgen05.mma; when the
-// tile has landed they bump a per-slot counter that lets the producer reuse the slot.  Within a pass the tiles are
-// produced along diagonals (time step t: row block (cp + t) mod Rc for column pair cp), so every Y-holder consumes
-// one tile per time step and every X-holder at most two: consumers run at a steady rate and the exchange ring
-// stays short.  Nothing tile-sized beyond that ring ever reaches memory.  No reduction through memory is needed:
-// OutX is complete when its chunk ends, OutY when its pass ends (and is accumulated in place, fp32, when X needs
-// more than one chunk).
+// tile has landed they bump a per-slot counter that lets the producer reuse the slot.  Within a pass the quads are
+// produced along diagonals (time step t: row pair (cp + t) mod Rc for column pair cp), so every holder consumes at
+// a steady rate and the exchange ring stays short.  Nothing tile-sized beyond that ring ever reaches memory, and no
+// reduction through memory is needed: OutX is complete when its chunk ends, OutY when its pass ends (and is
+// accumulated in place, fp32, when X needs more than one chunk).  Row blocks / column tiles past the end of X / Y
+// (odd counts) are computed from TMA's zero fill and never stored.
 //
-// Progress: every role walks the tiles in the same global production order q.  The lowest-numbered unfinished tile
+// Progress: every role walks the quads in the same global production order q.  The lowest-numbered unfinished tile
 // can always be produced (its slot's previous tenant has a lower number) and consumed (its consumers have nothing
 // older to wait for), so the grid cannot deadlock provided all CTAs are co-resident — hence the cooperative launch.
 #include <stdlib.h>
@@ -40,20 +44,21 @@ namespace {
 constexpr int kBM = 128;
 constexpr int kBT = 128;
 constexpr int kBK = 64;
-constexpr int kNC = 512;                              // output columns per consumer CTA (all of its TMEM)
+constexpr int kNC = 512;                              // output columns per holder CTA (all of its TMEM)
 constexpr uint32_t kChunkBytes = 128 * kBK * 2;       // 16 KB: a [128][64] bf16 box
 constexpr uint32_t kPBytes = kBM * kBT * 2;           // 32 KB: one G tile
-constexpr uint32_t kPStageBytes = 3 * kChunkBytes;    // producer ring slot: X chunk + 256-row Y chunk
-constexpr int kPRing = 4;
-constexpr uint32_t kBox32Bytes = 32 * kBK * 2;        // 4 KB: a [32][64] box
-constexpr uint32_t kCStageBytes = 8 * kBox32Bytes;    // consumer ring slot: 32 operand rows x 512 columns
-constexpr int kCRing = 5;
-constexpr int kStagesPerTile = kBT / 32;              // 4
+constexpr uint32_t kPStageBytes = 2 * kChunkBytes;    // producer ring slot: X chunk + this CTA's half of the Y chunk
+constexpr int kPRing = 6;
+constexpr uint32_t kBox64Bytes = 64 * kBK * 2;        // 8 KB: a [64][64] box
+constexpr uint32_t kCStageBytes = 4 * kBox64Bytes;    // holder ring slot: 64 operand rows x this CTA's 256 columns
+constexpr int kCRing = 4;
+constexpr uint32_t kDrainBytes = 32768;                // holder: 4 drain warps x two 4 KB TMA-store buffers
+constexpr int kStagesPerTile = kBT / 64;              // 2
 constexpr int kThreads = 256;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr size_t kSmem = 1024 + 7 * 32768 + 3 * kBT * 4 + 512;
 static_assert(kPRing * kPStageBytes + kPBytes == 7 * 32768, "producer shared-memory plan");
-static_assert(2 * kPBytes + kCRing * kCStageBytes == 7 * 32768, "consumer shared-memory plan");
+static_assert(2 * kPBytes + kCRing * kCStageBytes + kDrainBytes == 7 * 32768, "holder shared-memory plan");
 
 #ifdef PGICA_TRACE
 __device__ long long* g_sggf_trace = nullptr;
@@ -90,9 +95,9 @@ struct FLap {
 
 struct SggfParams {
   int mx, my, k;
-  int RB, J;              // row blocks of X, column tiles of Y
-  int R, Cw, S;           // row blocks per chunk, column tiles per pass, 512-column splits of k
-  int nH, nW, nP, D;      // CTAs per role; exchange double-slots per producer
+  int RB2, J2;            // row-block pairs of X, column-tile pairs of Y
+  int R2, C2, S;          // row pairs per chunk, column pairs per pass, 512-column splits of k
+  int nH, nW, nP, D;      // PAIRS per role; exchange double-slots per producer CTA
   int outx_bf16, outy_bf16;
   float c;                // scale * log2(e)
   const float* r_lse;
@@ -103,12 +108,45 @@ struct SggfParams {
   const int* c_tgt;
   void* out_x;
   void* out_y;
-  uint32_t* ready;        // [nP*D*2] use count + 1 of the tile that is complete in the slot
-  uint32_t* done;         // [nP*D*2] consumers that have pulled a tile out of the slot, ever
+  uint32_t* ready;        // [2*nP*D*2] use count + 1 of the tile that is complete in the slot
+  uint32_t* done;         // [2*nP*D*2] consumers that have pulled a tile out of the slot, ever
 };
 
+// ---- PTX pieces only this kernel uses
 __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// TMA load into THIS CTA's shared memory whose completion bytes are credited to a barrier that may live in the
+// pair's other CTA (`bar_cluster` is a shared::cluster address): how both halves of a cta_group::2 operand report
+// to the leader's barrier.
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tmap, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// all MMAs issued so far by this thread complete -> one arrival on the same-offset barrier of BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// fp32 tile shared -> global: plain store, or element-wise add into what is there
+__device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(tmap)),
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
@@ -121,8 +159,8 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
 __device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void red_relaxed_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 // Spin until *p >= v (monotonic counters); traps instead of hanging if the protocol is broken.
 __device__ __forceinline__ void wait_flag_ge(const uint32_t* p, uint32_t v) {
@@ -138,20 +176,19 @@ __device__ __forceinline__ void wait_flag_ge(const uint32_t* p, uint32_t v) {
   }
 }
 
-// Visits every double tile in production order.  f(q, chunk, pass, r0, r, c0, cp, Cc): sequence number q; the
-// tile pair covers row block r0 + r and column tiles c0 + 2cp and c0 + 2cp + 1 (the latter only if 2cp + 1 < Cc).
+// Visits every quad in production order.  f(q, r0, r, c0, c): sequence number q; the quad covers row pair r0 + r
+// (row blocks 2(r0+r), 2(r0+r)+1) and column pair c0 + c.
 template <class F>
-__device__ __forceinline__ void for_each_dt(const SggfParams& p, F&& f) {
+__device__ __forceinline__ void for_each_quad(const SggfParams& p, F&& f) {
   int q = 0;
-  for (int r0 = 0, chunk = 0; r0 < p.RB; r0 += p.R, ++chunk) {
-    const int Rc = min(p.R, p.RB - r0);
-    for (int c0 = 0, pass = 0; c0 < p.J; c0 += p.Cw, ++pass) {
-      const int Cc = min(p.Cw, p.J - c0);
-      const int Cwp = (Cc + 1) >> 1;
+  for (int r0 = 0; r0 < p.RB2; r0 += p.R2) {
+    const int Rc = min(p.R2, p.RB2 - r0);
+    for (int c0 = 0; c0 < p.J2; c0 += p.C2) {
+      const int Cc = min(p.C2, p.J2 - c0);
       for (int t = 0; t < Rc; ++t) {
-        int r = t;
-        for (int cp = 0; cp < Cwp; ++cp, ++q) {
-          f(q, chunk, pass, r0, r, c0, cp, Cc);
+        int r = t % Rc;
+        for (int c = 0; c < Cc; ++c, ++q) {
+          f(q, r0, r, c0, c);
           if (++r == Rc) r = 0;
         }
       }
@@ -159,25 +196,26 @@ __device__ __forceinline__ void for_each_dt(const SggfParams& p, F&& f) {
   }
 }
 
-// Visits, in production order, the tiles one consumer CTA accumulates.  is_y = false: X-holder of row block
-// `idx` (chunk-relative); true: Y-holder of column tile `idx` (pass-relative).  f(q, half, rblk, ctile, first,
-// period) with absolute block / tile numbers; `first` marks the first tile of an accumulation period.  g(period,
-// chunk, pass) is called after the last tile of every period that had tiles.
+// Visits, in production order, the pair-tiles one holder pair accumulates (two per quad).  is_y = false: X-holder of
+// row pair `idx` (chunk-relative); true: Y-holder of column pair `idx` (pass-relative).  f(q, sel, rp, cp, first,
+// period): quad q = (row pair rp, column pair cp), absolute; sel = 0/1 picks the column tile 2cp + sel (X-holder)
+// or the row block 2rp + sel (Y-holder); `first` marks the first pair-tile of an accumulation period.  g(period,
+// chunk, pass) is called after the last pair-tile of every period that had any.
 template <class F, class G>
-__device__ __forceinline__ void for_each_consumer_tile(const SggfParams& p, bool is_y, int idx, F&& f, G&& g) {
+__device__ __forceinline__ void for_each_holder_tile(const SggfParams& p, bool is_y, int idx, F&& f, G&& g) {
   int qbase = 0, period = 0;
-  for (int r0 = 0, chunk = 0; r0 < p.RB; r0 += p.R, ++chunk) {
-    const int Rc = min(p.R, p.RB - r0);
+  for (int r0 = 0, chunk = 0; r0 < p.RB2; r0 += p.R2, ++chunk) {
+    const int Rc = min(p.R2, p.RB2 - r0);
     bool first = true;
-    for (int c0 = 0, pass = 0; c0 < p.J; c0 += p.Cw, ++pass) {
-      const int Cc = min(p.Cw, p.J - c0);
-      const int Cwp = (Cc + 1) >> 1;
+    for (int c0 = 0, pass = 0; c0 < p.J2; c0 += p.C2, ++pass) {
+      const int Cc = min(p.C2, p.J2 - c0);
       if (is_y) {
         if (idx < Cc) {
-          const int cp = idx >> 1;
-          int r = cp % Rc;
+          int r = idx % Rc;
           for (int t = 0; t < Rc; ++t) {
-            f(qbase + t * Cwp + cp, idx & 1, r0 + r, c0 + idx, t == 0, period);
+            const int q = qbase + t * Cc + idx;
+            f(q, 0, r0 + r, c0 + idx, t == 0, period);
+            f(q, 1, r0 + r, c0 + idx, false, period);
             if (++r == Rc) r = 0;
           }
           g(period, chunk, pass);
@@ -185,17 +223,17 @@ __device__ __forceinline__ void for_each_consumer_tile(const SggfParams& p, bool
         }
       } else if (idx < Rc) {
         for (int t = 0; t < Rc; ++t) {
-          // column pairs cp with (cp + t) mod Rc == idx, increasing
-          int cp = idx - t;
-          if (cp < 0) cp += Rc;
-          for (; cp < Cwp; cp += Rc) {
-            f(qbase + t * Cwp + cp, 0, r0 + idx, c0 + 2 * cp, first, period);
+          int c = idx - t;  // column pairs c with (c + t) mod Rc == idx, increasing
+          if (c < 0) c += Rc;
+          for (; c < Cc; c += Rc) {
+            const int q = qbase + t * Cc + c;
+            f(q, 0, r0 + idx, c0 + c, first, period);
             first = false;
-            if (2 * cp + 1 < Cc) f(qbase + t * Cwp + cp, 1, r0 + idx, c0 + 2 * cp + 1, false, period);
+            f(q, 1, r0 + idx, c0 + c, false, period);
           }
         }
       }
-      qbase += Rc * Cwp;
+      qbase += Rc * Cc;
     }
     if (!is_y && idx < Rc) {
       g(period, chunk, 0);
@@ -207,8 +245,9 @@ __device__ __forceinline__ void for_each_consumer_tile(const SggfParams& p, bool
 template <bool kRow, bool kCol>
 __global__ void __launch_bounds__(kThreads, 1)
 sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__ CUtensorMap tm_y128,
-            const __grid_constant__ CUtensorMap tm_x32, const __grid_constant__ CUtensorMap tm_y32,
-            const __grid_constant__ CUtensorMap tm_s, const SggfParams p) {
+            const __grid_constant__ CUtensorMap tm_x64, const __grid_constant__ CUtensorMap tm_y64,
+            const __grid_constant__ CUtensorMap tm_s, const __grid_constant__ CUtensorMap tm_ox,
+            const __grid_constant__ CUtensorMap tm_oy, const SggfParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
   float* s_cl = reinterpret_cast<float*>(smem + 7 * 32768);
@@ -218,28 +257,36 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bid = (int)blockIdx.x;
-  const bool is_producer = bid >= p.nH + p.nW;
+  const uint32_t rho = cluster_ctarank();      // 0 = leader of the pair (issues the MMAs)
+  const int pair = (int)blockIdx.x >> 1;
+  const bool is_producer = pair >= p.nH + p.nW;
   const int num_kb = p.k / kBK;
   const uint32_t n_consumers = 2u * (uint32_t)p.S;  // CTAs that pull each G tile
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x128);
     tma_prefetch_desc(&tm_y128);
-    tma_prefetch_desc(&tm_x32);
-    tma_prefetch_desc(&tm_y32);
+    tma_prefetch_desc(&tm_x64);
+    tma_prefetch_desc(&tm_y64);
     tma_prefetch_desc(&tm_s);
+    tma_prefetch_desc(&tm_ox);
+    tma_prefetch_desc(&tm_oy);
   }
-  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
 
   if (is_producer) {
     // =================================================================================================== producer
     uint8_t* ring = smem;
     uint8_t* staging = smem + kPRing * kPStageBytes;
-    uint64_t* full_bar = bars;                 // [kPRing]
-    uint64_t* empty_bar = full_bar + kPRing;   // [kPRing]
-    uint64_t* zfull_bar = empty_bar + kPRing;  // [2]
-    uint64_t* zempty_bar = zfull_bar + 2;      // [2]
+    uint64_t* full_bar = bars;                 // [kPRing] leader's: both CTAs' halves of a stage have landed (the leader
+                                               //          expects the bytes of both, the peer's TMA credits it remotely)
+    uint64_t* empty_bar = full_bar + kPRing;   // [kPRing] per CTA (multicast commit)
+    uint64_t* zfull_bar = empty_bar + kPRing;  // [2] per CTA (multicast commit)
+    uint64_t* zempty_bar = zfull_bar + 2;      // [2] leader's: both CTAs' epilogues have read the Z buffer
     uint64_t* stfull_bar = zempty_bar + 2;
     uint64_t* stfree_bar = stfull_bar + 1;
     if (warp == 1 && lane == 0) {
@@ -249,7 +296,7 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&zfull_bar[i], 1);
-        mbar_init(&zempty_bar[i], 128);
+        mbar_init(&zempty_bar[i], 256);
       }
       mbar_init(stfull_bar, 128);
       mbar_init(stfree_bar, 1);
@@ -257,29 +304,32 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
     }
     tc_fence_before_sync();
     __syncthreads();
+    cluster_sync_all();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    const int pid = bid - p.nH - p.nW;
+    const int pp = pair - p.nH - p.nW;             // producer pair number
+    const uint32_t pcta = (uint32_t)pp * 2u + rho;  // producer CTA number (owns D double slots of the ring)
 
     if (warp == 0) {
-      // ---------------------------------------------------------------- TMA loads of the MMA1 operands
-      int slot = 0, mine = pid;
+      // ---------------------------------------------------------------- TMA loads of this CTA's MMA1 operand halves
+      int slot = 0, mine = pp;
       uint32_t phase = 0;
+      const uint32_t lbar0 = mapa_u32(smem_u32(&full_bar[0]), 0);  // the leader's full barriers (shared::cluster)
       LAP_DECL;
-      for_each_dt(p, [&](int q, int, int, int r0, int r, int c0, int cp, int) {
+      for_each_quad(p, [&](int q, int r0, int r, int c0, int c) {
         if (q != mine) return;
         mine += p.nP;
-        const int xrow = (r0 + r) * kBM, yrow = (c0 + 2 * cp) * kBT;
+        const int xrow = (2 * (r0 + r) + (int)rho) * kBM, yrow = (2 * (c0 + c) + (int)rho) * kBT;
         for (int kb = 0; kb < num_kb; ++kb) {
           LAP(0);
           mbar_wait(&empty_bar[slot], phase ^ 1);
           LAP(1);
           if (elect_one()) {
-            mbar_expect_tx(&full_bar[slot], kPStageBytes);
+            const uint32_t lbar = lbar0 + slot * 8;
+            if (rho == 0) mbar_expect_tx(&full_bar[slot], 2 * kPStageBytes);
             uint8_t* dst = ring + slot * kPStageBytes;
-            tma_load_2d(dst, &tm_x128, &full_bar[slot], kb * kBK, xrow);
-            tma_load_2d(dst + kChunkBytes, &tm_y128, &full_bar[slot], kb * kBK, yrow);
-            tma_load_2d(dst + 2 * kChunkBytes, &tm_y128, &full_bar[slot], kb * kBK, yrow + kBT);
+            tma_load_2d_pair(dst, &tm_x128, lbar, kb * kBK, xrow);
+            tma_load_2d_pair(dst + kChunkBytes, &tm_y128, lbar, kb * kBK, yrow);
           }
           __syncwarp();
           if (++slot == kPRing) {
@@ -290,25 +340,25 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
       });
       LAP(0);
       if (lane == 0) LAP_FLUSH(4, 2);
-    } else if (warp == 1) {
-      // ---------------------------------------------------------------- MMA1: Z[128 x 256] = X[r] Y[c, c+1]^T
-      constexpr uint32_t idesc1 = make_idesc_bf16(kBM, 2 * kBT, 0, 0);
+    } else if (warp == 1 && rho == 0) {
+      // ---------------------------------------------------------------- MMA1 (leader): Z[256 x 256] = X[2rp, 2rp+1] Y[2cp, 2cp+1]^T
+      constexpr uint32_t idesc1 = make_idesc_bf16(256, 256, 0, 0);
       const uint64_t desc_k = make_smem_desc(0, 16, 1024);
-      int slot = 0, mine = pid;
+      int slot = 0, mine = pp;
       uint32_t phase = 0, n = 0;
       LAP_DECL;
-      for_each_dt(p, [&](int q, int, int, int, int, int, int, int) {
+      for_each_quad(p, [&](int q, int, int, int, int) {
         if (q != mine) return;
         mine += p.nP;
         const uint32_t buf = n & 1u;
         LAP(0);
-        mbar_wait(&zempty_bar[buf], ((n >> 1) & 1u) ^ 1u);  // the epilogue has read this Z buffer's previous tile
+        mbar_wait_cluster(&zempty_bar[buf], ((n >> 1) & 1u) ^ 1u);  // both epilogues have read this Z buffer
         LAP(1);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + buf * 256u;
         for (int kb = 0; kb < num_kb; ++kb) {
           LAP(0);
-          mbar_wait(&full_bar[slot], phase);
+          mbar_wait_cluster(&full_bar[slot], phase);
           LAP(2);
           tc_fence_after_sync();
           if (elect_one()) {
@@ -316,9 +366,9 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
             const uint64_t da = desc_k | ((x_addr >> 4) & 0x3FFF);
             const uint64_t db = desc_k | (((x_addr + kChunkBytes) >> 4) & 0x3FFF);
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc1, (kb | k) != 0 ? 1u : 0u);
-            umma_commit(&empty_bar[slot]);
-            if (kb == num_kb - 1) umma_commit(&zfull_bar[buf]);
+            for (int k = 0; k < kBK / 16; ++k) umma2_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc1, (kb | k) != 0 ? 1u : 0u);
+            umma2_commit_both(&empty_bar[slot]);
+            if (kb == num_kb - 1) umma2_commit_both(&zfull_bar[buf]);
           }
           __syncwarp();
           if (++slot == kPRing) {
@@ -332,20 +382,15 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
       if (lane == 0) LAP_FLUSH(0, 3);
     } else if (warp == 3) {
       // ---------------------------------------------------------------- exchange: staging -> ring slot -> flag
-      int mine = pid;
+      int mine = pp;
       uint32_t n = 0, ntile = 0;
       LAP_DECL;
-      for_each_dt(p, [&](int q, int, int, int, int, int, int cp, int Cc) {
+      for_each_quad(p, [&](int q, int, int, int, int) {
         if (q != mine) return;
         mine += p.nP;
         const uint32_t ds = n % (uint32_t)p.D, use = n / (uint32_t)p.D;
         for (int half = 0; half < 2; ++half) {
-          const uint32_t tslot = ((uint32_t)pid * p.D + ds) * 2u + half;
-          if (2 * cp + half >= Cc) {
-            // a pass with an odd number of column tiles: nobody will pull this use of the slot; keep its counter in step
-            if (lane == 0) red_release_gpu_add(p.done + tslot, n_consumers);
-            break;
-          }
+          const uint32_t tslot = (pcta * p.D + ds) * 2u + half;
           LAP(0);
           mbar_wait(stfull_bar, ntile & 1u);
           LAP(1);
@@ -371,19 +416,19 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
       LAP(0);
       if (lane == 0) LAP_FLUSH(6, 4);
     } else if (warp >= 4) {
-      // ---------------------------------------------------------------- epilogue: Z -> G (bf16) -> staging
+      // ---------------------------------------------------------------- epilogue: this CTA's Z rows -> two G tiles
       const int quarter = warp & 3;
       const int et = threadIdx.x - 128;
       const int row_in_blk = quarter * 32 + lane;
       const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
       const uint32_t g_local = smem_u32(staging);
-      int mine = pid;
+      int mine = pp;
       uint32_t n = 0, ntile = 0;
       LAP_DECL;
-      for_each_dt(p, [&](int q, int, int, int r0, int r, int c0, int cp, int Cc) {
+      for_each_quad(p, [&](int q, int r0, int r, int c0, int c) {
         if (q != mine) return;
         mine += p.nP;
-        const int row = (r0 + r) * kBM + row_in_blk;
+        const int row = (2 * (r0 + r) + (int)rho) * kBM + row_in_blk;
         float rl = 0.f, rc = 0.f;
         int rt = -1;
         if (kRow && row < p.mx) {
@@ -397,8 +442,7 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
         LAP(1);
         tc_fence_after_sync();
         for (int half = 0; half < 2; ++half) {
-          if (2 * cp + half >= Cc) break;
-          const int col0 = (c0 + 2 * cp + half) * kBT;
+          const int col0 = (2 * (c0 + c) + half) * kBT;
           if (kCol) {
             const int col = col0 + et;
             float l = 0.f, cf = 0.f;
@@ -443,9 +487,9 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
 #pragma unroll
             for (int i = 0; i < 16; ++i) gp[ch * 16 + i] = pack_bf16x2(g[2 * i], g[2 * i + 1]);
           }
-          if (half == 1 || 2 * cp + 1 >= Cc) {
+          if (half == 1) {
             tc_fence_before_sync();
-            mbar_arrive(&zempty_bar[buf]);  // this Z buffer may be overwritten by the MMA1 after next
+            mbar_arrive_cluster(&zempty_bar[buf], 0);  // tell the leader: this CTA has read the Z buffer
           }
           LAP(2);
           mbar_wait(stfree_bar, (ntile & 1u) ^ 1u);  // the exchange warp's TMA store has read the previous tile
@@ -473,22 +517,24 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 2) tmem_dealloc<512>(tmem_base);
+    cluster_sync_all();  // the pair shares barriers and TMEM commits: nobody leaves early
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     return;
   }
 
-  // ===================================================================================================== consumers
-  const bool is_y = bid >= p.nH;
-  const int cidx = (is_y ? bid - p.nH : bid) / p.S;  // row block in chunk (X-holder) / column tile in pass (Y-holder)
-  const int split = (is_y ? bid - p.nH : bid) % p.S;  // which 512 output columns
+  // ======================================================================================================= holders
+  const bool is_y = pair >= p.nH;
+  const int hidx = (is_y ? pair - p.nH : pair) / p.S;   // row pair in chunk (X-holder) / column pair in pass (Y-holder)
+  const int split = (is_y ? pair - p.nH : pair) % p.S;  // which 512 output columns
   uint8_t* gbuf = smem;                       // two G tiles
   uint8_t* ring = smem + 2 * kPBytes;         // kCRing operand stages
-  uint64_t* full_bar = bars;                  // [kCRing]
-  uint64_t* empty_bar = full_bar + kCRing;    // [kCRing]
-  uint64_t* gfull_bar = empty_bar + kCRing;   // [2]
-  uint64_t* gempty_bar = gfull_bar + 2;       // [2]
-  uint64_t* outfull_bar = gempty_bar + 2;
-  uint64_t* outfree_bar = outfull_bar + 1;
+  uint8_t* drain_stage = ring + kCRing * kCStageBytes;
+  uint64_t* full_bar = bars;                  // [kCRing] leader's (expects both CTAs' bytes)
+  uint64_t* empty_bar = full_bar + kCRing;    // [kCRing] per CTA
+  uint64_t* gfull_bar = empty_bar + kCRing;   // [2] leader's (expects both CTAs' bytes)
+  uint64_t* gempty_bar = gfull_bar + 2;       // [2] per CTA
+  uint64_t* outfull_bar = gempty_bar + 2;     // per CTA
+  uint64_t* outfree_bar = outfull_bar + 1;    // leader's (count 256)
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kCRing; ++i) {
       mbar_init(&full_bar[i], 1);
@@ -499,51 +545,64 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
       mbar_init(&gempty_bar[i], 1);
     }
     mbar_init(outfull_bar, 1);
-    mbar_init(outfree_bar, 128);
+    mbar_init(outfree_bar, 256);
     fence_mbar_init();
   }
   tc_fence_before_sync();
   __syncthreads();
+  cluster_sync_all();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const CUtensorMap* tm_op = is_y ? &tm_x32 : &tm_y32;  // the other operand of this CTA's product
-  const int op_col0 = split * kNC;
+  const CUtensorMap* tm_op = is_y ? &tm_x64 : &tm_y64;  // the other operand of this pair's product
+  const int op_col0 = split * kNC + (int)rho * 128;     // this CTA's 128 of each 256-column instruction
+
+  // exchange slot of the tile (row block 2rp + a, column tile 2cp + b) of quad q
+  auto tile_slot = [&](int q, uint32_t a, uint32_t b, uint32_t& use) {
+    const uint32_t prod = (uint32_t)q % (uint32_t)p.nP, i = (uint32_t)q / (uint32_t)p.nP;
+    use = i / (uint32_t)p.D;
+    return ((prod * 2u + a) * p.D + i % (uint32_t)p.D) * 2u + b;
+  };
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA: G tiles from the ring + operand rows
+    // ------------------------------------------------------------------ TMA: own G tile + own half of the operand rows
     int slot = 0;
     uint32_t phase = 0, n = 0;
+    const uint32_t lbar0 = mapa_u32(smem_u32(&full_bar[0]), 0);   // the leader's barriers (shared::cluster)
+    const uint32_t gbar0 = mapa_u32(smem_u32(&gfull_bar[0]), 0);
     LAP_DECL;
-    for_each_consumer_tile(
-        p, is_y, cidx,
-        [&](int q, int half, int rblk, int ctile, bool, int) {
-          const uint32_t prod = (uint32_t)q % (uint32_t)p.nP, i = (uint32_t)q / (uint32_t)p.nP;
-          const uint32_t ds = i % (uint32_t)p.D, use = i / (uint32_t)p.D;
-          const uint32_t tslot = (prod * p.D + ds) * 2u + (uint32_t)half;
+    for_each_holder_tile(
+        p, is_y, hidx,
+        [&](int q, int sel, int rp, int cp, bool, int) {
+          // X-holder CTA rho: G(2rp + rho, 2cp + sel);  Y-holder CTA rho: G(2rp + sel, 2cp + rho)
+          uint32_t use;
+          const uint32_t tslot = is_y ? tile_slot(q, (uint32_t)sel, rho, use) : tile_slot(q, rho, (uint32_t)sel, use);
           const uint32_t gb = n & 1u;
           LAP(0);
-          mbar_wait(&gempty_bar[gb], ((n >> 1) & 1u) ^ 1u);  // the MMAs of the tile before last are complete
+          mbar_wait(&gempty_bar[gb], ((n >> 1) & 1u) ^ 1u);  // the MMAs of the pair-tile before last are complete
           LAP(1);
           wait_flag_ge(p.ready + tslot, use + 1u);           // the tile is complete in the ring
           LAP(2);
           if (elect_one()) {
             asm volatile("fence.proxy.async.global;" ::: "memory");  // acquire above before the async-proxy read
-            mbar_expect_tx(&gfull_bar[gb], kPBytes);
-            tma_load_2d(gbuf + gb * kPBytes, &tm_s, &gfull_bar[gb], 0, (int)tslot * kBM);
-            tma_load_2d(gbuf + gb * kPBytes + kChunkBytes, &tm_s, &gfull_bar[gb], kBK, (int)tslot * kBM);
+            const uint32_t lbar = gbar0 + gb * 8;
+            if (rho == 0) mbar_expect_tx(&gfull_bar[gb], 2 * kPBytes);
+            tma_load_2d_pair(gbuf + gb * kPBytes, &tm_s, lbar, 0, (int)tslot * kBM);
+            tma_load_2d_pair(gbuf + gb * kPBytes + kChunkBytes, &tm_s, lbar, kBK, (int)tslot * kBM);
           }
           __syncwarp();
-          const int op_row0 = (is_y ? rblk : ctile) * kBM;
+          const int op_row0 = (is_y ? 2 * rp + sel : 2 * cp + sel) * kBM;
           for (int st = 0; st < kStagesPerTile; ++st) {
             LAP(0);
             mbar_wait(&empty_bar[slot], phase ^ 1);
             LAP(3);
             if (elect_one()) {
-              mbar_expect_tx(&full_bar[slot], kCStageBytes);
+              const uint32_t lbar = lbar0 + slot * 8;
+              if (rho == 0) mbar_expect_tx(&full_bar[slot], 2 * kCStageBytes);
               uint8_t* dst = ring + slot * kCStageBytes;
 #pragma unroll
-              for (int b = 0; b < 8; ++b)
-                tma_load_2d(dst + b * kBox32Bytes, tm_op, &full_bar[slot], op_col0 + b * kBK, op_row0 + st * 32);
+              for (int b = 0; b < 4; ++b)  // box b: instruction h = b >> 1, 64-column chunk b & 1 of this CTA's 128
+                tma_load_2d_pair(dst + b * kBox64Bytes, tm_op, lbar, op_col0 + (b >> 1) * 256 + (b & 1) * kBK,
+                                 op_row0 + st * 64);
             }
             __syncwarp();
             if (++slot == kCRing) {
@@ -556,56 +615,50 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
         [&](int, int, int) {});
     LAP(0);
     if (lane == 0) LAP_FLUSH(4, 4);
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA2: Out[128 x 512] += G(^T) * operand rows
-    const uint32_t idesc2 = make_idesc_bf16(kBM, 256, is_y ? 1 : 0, 1);
+  } else if (warp == 1 && rho == 0) {
+    // ------------------------------------------------------------------ MMA2 (leader): Out[256 x 512] += G(^T) * operand rows
+    const uint32_t idesc2 = make_idesc_bf16(256, 256, is_y ? 1 : 0, 1);
     const uint64_t desc_ak = make_smem_desc(0, 16, 1024);              // G as A, K-major (X-holder)
     const uint64_t desc_amn = make_smem_desc(0, kChunkBytes, 1024);    // G^T as A: the same tile read MN-major
-    const uint64_t desc_b = make_smem_desc(0, kBox32Bytes, 1024);      // operand rows, MN-major, 64-col boxes 4 KB apart
+    const uint64_t desc_b = make_smem_desc(0, kBox64Bytes, 1024);      // operand rows, MN-major, 64-col boxes 8 KB apart
     int slot = 0;
     uint32_t phase = 0, n = 0;
     LAP_DECL;
-    for_each_consumer_tile(
-        p, is_y, cidx,
-        [&](int q, int half, int, int, bool first, int period) {
+    for_each_holder_tile(
+        p, is_y, hidx,
+        [&](int q, int sel, int, int, bool first, int period) {
           const uint32_t gb = n & 1u;
           if (first && period > 0) {
             LAP(0);
-            mbar_wait(outfree_bar, (uint32_t)(period - 1) & 1u);  // the previous accumulator has left TMEM
+            mbar_wait_cluster(outfree_bar, (uint32_t)(period - 1) & 1u);  // both accumulators have left TMEM
             LAP(1);
             tc_fence_after_sync();
           }
           LAP(0);
-          mbar_wait(&gfull_bar[gb], (n >> 1) & 1u);
+          mbar_wait_cluster(&gfull_bar[gb], (n >> 1) & 1u);
           LAP(2);
           tc_fence_after_sync();
-          if (elect_one()) {
-            // the ring slot may be overwritten: this CTA has its copy
-            const uint32_t prod = (uint32_t)q % (uint32_t)p.nP, i = (uint32_t)q / (uint32_t)p.nP;
-            red_release_gpu_add(p.done + (prod * p.D + i % (uint32_t)p.D) * 2u + (uint32_t)half, 1u);
-          }
-          __syncwarp();
           const uint32_t g_addr = smem_u32(gbuf + gb * kPBytes);
           const uint64_t dg = (is_y ? desc_amn : desc_ak) | ((g_addr >> 4) & 0x3FFF);
           for (int st = 0; st < kStagesPerTile; ++st) {
             LAP(0);
-            mbar_wait(&full_bar[slot], phase);
+            mbar_wait_cluster(&full_bar[slot], phase);
             LAP(3);
             tc_fence_after_sync();
             if (elect_one()) {
               const uint32_t y_addr = smem_u32(ring + slot * kCStageBytes);
               const uint64_t dy = desc_b | ((y_addr >> 4) & 0x3FFF);
 #pragma unroll
-              for (int kk = 0; kk < 2; ++kk) {
-                const int ks = st * 2 + kk;  // K step of 16 within the tile's 128
+              for (int kk = 0; kk < 4; ++kk) {
+                const int ks = st * 4 + kk;  // K step of 16 within the tile's 128
                 const uint64_t da = is_y ? dg + ks * (2048 >> 4) : dg + (ks >> 2) * (kChunkBytes >> 4) + (ks & 3) * 2;
                 const uint32_t acc = (first && ks == 0) ? 0u : 1u;
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
-                  umma_bf16_ss(tmem_base + h * 256u, da, dy + kk * (2048 >> 4) + h * (4 * kBox32Bytes >> 4), idesc2, acc);
+                  umma2_bf16_ss(tmem_base + h * 256u, da, dy + kk * (2048 >> 4) + h * (2 * kBox64Bytes >> 4), idesc2, acc);
               }
-              umma_commit(&empty_bar[slot]);
-              if (st == kStagesPerTile - 1) umma_commit(&gempty_bar[gb]);
+              umma2_commit_both(&empty_bar[slot]);
+              if (st == kStagesPerTile - 1) umma2_commit_both(&gempty_bar[gb]);
             }
             __syncwarp();
             if (++slot == kCRing) {
@@ -613,10 +666,18 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
               phase ^= 1;
             }
           }
+          if (elect_one()) {
+            // both tiles have landed in the pair's shared memory (gfull above): their ring slots may be overwritten.
+            // Relaxed and after the MMA issue: a release fence here would stall the issuing thread for an L2 round trip.
+            uint32_t use;
+            red_relaxed_gpu_add(p.done + (is_y ? tile_slot(q, (uint32_t)sel, 0u, use) : tile_slot(q, 0u, (uint32_t)sel, use)), 1u);
+            red_relaxed_gpu_add(p.done + (is_y ? tile_slot(q, (uint32_t)sel, 1u, use) : tile_slot(q, 1u, (uint32_t)sel, use)), 1u);
+          }
+          __syncwarp();
           ++n;
         },
         [&](int, int, int) {
-          if (elect_one()) umma_commit(outfull_bar);
+          if (elect_one()) umma2_commit_both(outfull_bar);
           __syncwarp();
         });
     LAP(0);
@@ -626,11 +687,12 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
     const int quarter = warp & 3;
     const int row_in_blk = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const int out_col0 = split * kNC;
     LAP_DECL;
-    for_each_consumer_tile(
-        p, is_y, cidx, [&](int, int, int, int, bool, int) {},
+    for_each_holder_tile(
+        p, is_y, hidx, [&](int, int, int, int, bool, int) {},
         [&](int period, int chunk, int pass) {
-          const int blk = is_y ? pass * p.Cw + cidx : chunk * p.R + cidx;
+          const int blk = 2 * (is_y ? pass * p.C2 + hidx : chunk * p.R2 + hidx) + (int)rho;
           const int row = blk * kBM + row_in_blk;
           const int limit = is_y ? p.my : p.mx;
           void* out = is_y ? p.out_y : p.out_x;
@@ -640,14 +702,46 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
           mbar_wait(outfull_bar, (uint32_t)period & 1u);
           LAP(1);
           tc_fence_after_sync();
+          if (!bf16) {
+            // fp32: 32 x 32 chunks go through a swizzled staging buffer and leave as TMA stores (or TMA add-reductions
+            // when OutY is accumulated over chunks): full 128-byte lines instead of 32 scattered 16-byte stores per
+            // instruction, and the rows past the end of the matrix are clipped by the tensor map.
+            const CUtensorMap* tm_o = is_y ? &tm_oy : &tm_ox;
+            uint8_t* stg = drain_stage + quarter * 8192;
+            const int row0 = blk * kBM + quarter * 32;
 #pragma unroll 1
-          for (int ch = 0; ch < kNC / 32; ++ch) {
-            uint32_t rr[32];
-            tmem_ld_32x32(tmem_base + lane_addr + ch * 32, rr);
-            tmem_ld_wait();
-            const int col = op_col0 + ch * 32;
-            if (row < limit) {
-              if (bf16) {
+            for (int ch = 0; ch < kNC / 32; ++ch) {
+              uint32_t rr[32];
+              tmem_ld_32x32(tmem_base + lane_addr + ch * 32, rr);
+              tmem_ld_wait();
+              if (ch >= 2) {
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // this buffer's last store has read it
+                __syncwarp();
+              }
+              const uint32_t sb = smem_u32(stg + (ch & 1) * 4096);
+#pragma unroll
+              for (int c4 = 0; c4 < 8; ++c4)
+                st_smem_v4(sb + sw128_offset(lane, c4), rr[c4 * 4], rr[c4 * 4 + 1], rr[c4 * 4 + 2], rr[c4 * 4 + 3]);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                if (accumulate)
+                  tma_reduce_add_2d(tm_o, stg + (ch & 1) * 4096, out_col0 + ch * 32, row0);
+                else
+                  tma_store_2d(tm_o, stg + (ch & 1) * 4096, out_col0 + ch * 32, row0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
+            }
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // written: a later chunk may add to it
+            __syncwarp();
+          } else {
+#pragma unroll 1
+            for (int ch = 0; ch < kNC / 32; ++ch) {
+              uint32_t rr[32];
+              tmem_ld_32x32(tmem_base + lane_addr + ch * 32, rr);
+              tmem_ld_wait();
+              const int col = out_col0 + ch * 32;
+              if (row < limit) {
                 uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out) + (size_t)row * p.k + col);
 #pragma unroll
                 for (int c4 = 0; c4 < 4; ++c4) {
@@ -658,131 +752,195 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
                   v.w = pack_bf16x2(__uint_as_float(rr[c4 * 8 + 6]), __uint_as_float(rr[c4 * 8 + 7]));
                   dst[c4] = v;
                 }
-              } else {
-                float4* dst = reinterpret_cast<float4*>(static_cast<float*>(out) + (size_t)row * p.k + col);
-#pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                  float4 v = make_float4(__uint_as_float(rr[c4 * 4]), __uint_as_float(rr[c4 * 4 + 1]),
-                                         __uint_as_float(rr[c4 * 4 + 2]), __uint_as_float(rr[c4 * 4 + 3]));
-                  if (accumulate) {
-                    const float4 o = dst[c4];
-                    v.x += o.x;
-                    v.y += o.y;
-                    v.z += o.z;
-                    v.w += o.w;
-                  }
-                  dst[c4] = v;
-                }
               }
             }
           }
           tc_fence_before_sync();
-          mbar_arrive(outfree_bar);
+          mbar_arrive_cluster(outfree_bar, 0);  // tell the leader: this CTA's accumulator may be overwritten
           LAP(2);
         });
     if (threadIdx.x == 128) LAP_FLUSH(10, 3);
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<512>(tmem_base);
+  cluster_sync_all();
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------- host side
 struct Plan {
-  int R, Cw, nH, nW, nP;
+  int R2, C2, nH, nW, nP;  // pairs
   double cost;
 };
 
-// Tensor-pipe time model in units of one 128 x 256 x 16 instruction (~171 cycles): a consumer spends 16 per tile,
-// a producer k/16 per double tile; a drain costs about 24.  The slowest role sets the pace of a chunk.
-Plan choose_plan(int RB, int J, int k, int nsm) {
+// Time model in units of one 256 x 256 x 16 pair instruction at the rate the holders sustain (~150 cycles): a holder
+// pair spends 16 per pair-tile (two per quad).  A producer pair would spend k/16 per quad if its operands always
+// arrived in time; measured on cfg2 it needs 1.5x that (profiles/r1_trace_sggf_v2_pairs.log: a quarter of its time
+// goes to waiting for TMA loads), and a drain of the 128 x 512 accumulator costs about 90.  The slowest role sets
+// the pace of a chunk.
+Plan choose_plan(int RB2, int J2, int k, int npairs) {
   const int S = k / kNC;
-  const double per_dt = k / 16.0;
+  const double per_quad = 1.5 * k / 16.0, drain = 90.0;
   Plan best{0, 0, 0, 0, 0, 1e300};
-  for (int R = 1; R <= RB && R * S <= nsm - S - 1; ++R) {
-    const int nH = R * S;
-    for (int Cw = 2; Cw * S <= nsm - nH - 1; Cw += 2) {
-      if (Cw > J + 1 && Cw > 2) break;
-      const int nW = Cw * S, nP = nsm - nH - nW;
-      const int passes = (J + Cw - 1) / Cw;
-      const int last = J - (passes - 1) * Cw;
-      const long pairs = (long)(passes - 1) * (Cw / 2) + (last + 1) / 2;
+  for (int R2 = 1; R2 <= RB2 && R2 * S <= npairs - S - 1; ++R2) {
+    const int nH = R2 * S;
+    for (int C2 = 1; C2 * S <= npairs - nH - 1 && C2 <= J2; ++C2) {
+      const int nW = C2 * S, nP = npairs - nH - nW;
+      const int passes = (J2 + C2 - 1) / C2;
       double total = 0;
-      for (int r0 = 0; r0 < RB; r0 += R) {
-        const int Rc = RB - r0 < R ? RB - r0 : R;
-        const double tH = 16.0 * J + 24;
-        const double tW = passes * (16.0 * Rc + 24);
-        const double tP = (double)((pairs * Rc + nP - 1) / nP) * per_dt;
+      for (int r0 = 0; r0 < RB2; r0 += R2) {
+        const int Rc = RB2 - r0 < R2 ? RB2 - r0 : R2;
+        const double tH = 32.0 * J2 + drain;
+        const double tW = passes * (32.0 * Rc + drain);
+        const double tP = (double)(((long)J2 * Rc + nP - 1) / nP) * per_quad;
         double t = tH > tW ? tH : tW;
         if (tP > t) t = tP;
-        total += t + per_dt + 48;  // pipeline fill / drain of a chunk
+        total += t + per_quad + 64;  // pipeline fill / drain of a chunk
       }
-      if (total < best.cost) best = Plan{R, Cw, nH, nW, nP, total};
+      if (total < best.cost) best = Plan{R2, C2, nH, nW, nP, total};
     }
   }
   return best;
 }
 
-int plan_override(Plan* pl, int nsm, int S) {
-  // PGICA_SGGF_PLAN="R,Cw" pins the role split (tuning / tests)
+int plan_override(Plan* pl, int npairs, int S) {
+  // PGICA_SGGF_PLAN="R2,C2" pins the role split in pairs (tuning / tests)
   const char* e = getenv("PGICA_SGGF_PLAN");
   if (!e) return 0;
-  int R = 0, Cw = 0;
-  if (sscanf(e, "%d,%d", &R, &Cw) != 2 || R < 1 || Cw < 1) return 0;
-  if (R * S + Cw * S >= nsm) return 0;
-  pl->R = R;
-  pl->Cw = Cw;
-  pl->nH = R * S;
-  pl->nW = Cw * S;
-  pl->nP = nsm - pl->nH - pl->nW;
+  int R2 = 0, C2 = 0;
+  if (sscanf(e, "%d,%d", &R2, &C2) != 2 || R2 < 1 || C2 < 1) return 0;
+  if (R2 * S + C2 * S >= npairs) return 0;
+  pl->R2 = R2;
+  pl->C2 = C2;
+  pl->nH = R2 * S;
+  pl->nW = C2 * S;
+  pl->nP = npairs - pl->nH - pl->nW;
   return 1;
 }
 
-constexpr int kSlotsPerProducer = 4;  // double slots (two G tiles each)
+constexpr int kSlotsPerProducer = 4;  // double slots (two G tiles each) per producer CTA
 
 template <bool kRow, bool kCol>
-int launch(const CUtensorMap& tm_x128, const CUtensorMap& tm_y128, const CUtensorMap& tm_x32,
-           const CUtensorMap& tm_y32, const CUtensorMap& tm_s, const SggfParams& p, int grid, cudaStream_t st) {
-  auto kern = sggf_kernel<kRow, kCol>;
-  static bool configured = false;
-  if (!configured) {
+int resident_pairs(int* out) {
+  static int cached = 0;
+  if (cached == 0) {
+    auto kern = sggf_kernel<kRow, kCol>;
     PGICA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
-    int per_sm = 0;
-    PGICA_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, kSmem));
-    if (per_sm < 1) {
-      set_error("softmax_grad_gemm_dual: the kernel does not fit on an SM");
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * 64);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    PGICA_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    if (n < 3) {
+      set_error("softmax_grad_gemm_dual: only %d CTA pairs of this kernel fit on the device", n);
       return PGICA_ERR_CUDA;
     }
-    configured = true;
+    cached = n;
   }
+  *out = cached;
+  return PGICA_OK;
+}
+
+template <bool kRow, bool kCol>
+int launch(const CUtensorMap& tm_x128, const CUtensorMap& tm_y128, const CUtensorMap& tm_x64,
+           const CUtensorMap& tm_y64, const CUtensorMap& tm_s, const CUtensorMap& tm_ox, const CUtensorMap& tm_oy,
+           const SggfParams& p, cudaStream_t st) {
+  auto kern = sggf_kernel<kRow, kCol>;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)grid);
+  cfg.gridDim = dim3((unsigned)(2 * (p.nH + p.nW + p.nP)));
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = kSmem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident or the launch fails: the roles wait on each other
-  attr[0].val.cooperative = 1;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeCooperative;  // all pairs co-resident or the launch fails: the roles wait on each other
+  attr[1].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  PGICA_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tm_x128, tm_y128, tm_x32, tm_y32, tm_s, p));
+  // PGICA_SGGF_COOP=0 drops the attribute (Nsight Compute cannot replay a cooperative cluster launch); the grid never
+  // exceeds the resident-cluster count, so on an otherwise idle device all pairs are co-resident anyway
+  static const bool coop = !(getenv("PGICA_SGGF_COOP") && atoi(getenv("PGICA_SGGF_COOP")) == 0);
+  cfg.numAttrs = coop ? 2 : 1;
+  PGICA_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tm_x128, tm_y128, tm_x64, tm_y64, tm_s, tm_ox, tm_oy, p));
   count_launches(1);
   return PGICA_OK;
+}
+
+template <bool kRow, bool kCol>
+int plan_and_launch(const void* x, const void* y, int64_t mx, int64_t my, int64_t k, SggfParams p, void* workspace,
+                    size_t workspace_bytes, cudaStream_t st) {
+  int npairs = 0;
+  int rc = resident_pairs<kRow, kCol>(&npairs);
+  if (rc != PGICA_OK) return rc;
+  const int S = p.S;
+  Plan pl = choose_plan(p.RB2, p.J2, (int)k, npairs);
+  plan_override(&pl, npairs, S);
+  PGICA_REQUIRE(pl.R2 >= 1 && pl.nP >= 1, "softmax_grad_gemm_dual: no role split for %d CTA pairs", npairs);
+  PGICA_REQUIRE(!(p.outy_bf16 && p.RB2 > pl.R2), "softmax_grad_gemm_dual: a bf16 OutY cannot be accumulated over chunks");
+  p.R2 = pl.R2;
+  p.C2 = pl.C2;
+  p.nH = pl.nH;
+  p.nW = pl.nW;
+  p.nP = pl.nP;
+  p.D = kSlotsPerProducer;
+  const size_t nslots = (size_t)2 * p.nP * p.D * 2;
+  const size_t ring_bytes = nslots * kPBytes;
+  const size_t flag_bytes = align_up(nslots * sizeof(uint32_t), 256);
+  if (workspace_bytes < ring_bytes + 2 * flag_bytes) {
+    set_error("softmax_grad_gemm_dual: workspace too small (%zu < %zu)", workspace_bytes, ring_bytes + 2 * flag_bytes);
+    return PGICA_ERR_WORKSPACE_TOO_SMALL;
+  }
+  uint8_t* w = static_cast<uint8_t*>(workspace);
+  p.ready = reinterpret_cast<uint32_t*>(w + ring_bytes);
+  p.done = reinterpret_cast<uint32_t*>(w + ring_bytes + flag_bytes);
+  PGICA_CUDA_OK(cudaMemsetAsync(p.ready, 0, 2 * flag_bytes, st));
+  CUtensorMap tm_x128, tm_y128, tm_x64, tm_y64, tm_s;
+  rc = make_tmap_bf16(&tm_x128, x, mx, k, k, 128);
+  if (rc != PGICA_OK) return rc;
+  rc = make_tmap_bf16(&tm_y128, y, my, k, k, 128);
+  if (rc != PGICA_OK) return rc;
+  rc = make_tmap_bf16(&tm_x64, x, mx, k, k, 64);
+  if (rc != PGICA_OK) return rc;
+  rc = make_tmap_bf16(&tm_y64, y, my, k, k, 64);
+  if (rc != PGICA_OK) return rc;
+  rc = make_tmap_bf16(&tm_s, workspace, nslots * kBM, kBT, kBT, 128);
+  if (rc != PGICA_OK) return rc;
+  // fp32 outputs leave through TMA (a bf16 output is written directly and its map stays unused)
+  CUtensorMap tm_ox = tm_s, tm_oy = tm_s;
+  if (!p.outx_bf16) {
+    rc = make_tmap_f32(&tm_ox, p.out_x, mx, k, k, 32);
+    if (rc != PGICA_OK) return rc;
+  }
+  if (!p.outy_bf16) {
+    rc = make_tmap_f32(&tm_oy, p.out_y, my, k, k, 32);
+    if (rc != PGICA_OK) return rc;
+  }
+  return launch<kRow, kCol>(tm_x128, tm_y128, tm_x64, tm_y64, tm_s, tm_ox, tm_oy, p, st);
 }
 
 }  // namespace
 
 bool sggf_supported(int64_t mx, int64_t my, int64_t k) {
-  // opt-in for now (PGICA_SGG_FUSED=1): on cfg2 the two single-product launches are still faster (1.34 vs 1.43 ms)
-  const char* e = getenv("PGICA_SGG_FUSED");
-  if (!e || atoi(e) == 0) return false;
-  return k % kNC == 0 && k / kNC <= 4 && mx >= 1 && my >= 1 && device_sm_count() >= 3 * (int)(k / kNC) + 1;
+  // PGICA_SGG_FUSED=0 falls back to one launch per product (sgg_x.cu)
+  if (const char* e = getenv("PGICA_SGG_FUSED"))
+    if (atoi(e) == 0) return false;
+  return k % kNC == 0 && k / kNC <= 4 && mx >= 1 && my >= 1;
 }
 
 size_t sggf_workspace_bytes() {
-  // exchange ring for the largest producer count + flags
-  const size_t np = 160;
-  return np * kSlotsPerProducer * 2 * (size_t)kPBytes + 2 * align_up(np * kSlotsPerProducer * 2 * sizeof(uint32_t), 256);
+  // exchange ring for the largest producer count (80 pairs) + flags
+  const size_t nslots = (size_t)2 * 80 * kSlotsPerProducer * 2;
+  return nslots * (size_t)kPBytes + 2 * align_up(nslots * sizeof(uint32_t), 256);
 }
 
 int sggf_dispatch(const void* x, const void* y, int64_t mx, int64_t my, int64_t k, float scale, const float* r_lse,
@@ -791,27 +949,15 @@ int sggf_dispatch(const void* x, const void* y, int64_t mx, int64_t my, int64_t 
                   void* workspace, size_t workspace_bytes, cudaStream_t st) {
   PGICA_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0,
                 "softmax_grad_gemm_dual: workspace missing or not 256-byte aligned");
-  const int nsm = device_sm_count();
-  const int S = (int)(k / kNC);
   const int RB = (int)ceil_div(mx, kBM), J = (int)ceil_div(my, kBT);
   PGICA_REQUIRE((int64_t)RB * J < (1ll << 30), "softmax_grad_gemm_dual: problem too large");
-  Plan pl = choose_plan(RB, J, (int)k, nsm);
-  plan_override(&pl, nsm, S);
-  PGICA_REQUIRE(pl.R >= 1 && pl.nP >= 1, "softmax_grad_gemm_dual: no role split for %d SMs", nsm);
-  PGICA_REQUIRE(!(out_y_is_bf16 && RB > pl.R), "softmax_grad_gemm_dual: a bf16 OutY cannot be accumulated over chunks");
   SggfParams p{};
   p.mx = (int)mx;
   p.my = (int)my;
   p.k = (int)k;
-  p.RB = RB;
-  p.J = J;
-  p.R = pl.R;
-  p.Cw = pl.Cw;
-  p.S = S;
-  p.nH = pl.nH;
-  p.nW = pl.nW;
-  p.nP = pl.nP;
-  p.D = kSlotsPerProducer;
+  p.RB2 = (RB + 1) / 2;
+  p.J2 = (J + 1) / 2;
+  p.S = (int)(k / kNC);
   p.outx_bf16 = out_x_is_bf16;
   p.outy_bf16 = out_y_is_bf16;
   p.c = scale * kLog2e;
@@ -823,33 +969,10 @@ int sggf_dispatch(const void* x, const void* y, int64_t mx, int64_t my, int64_t 
   p.c_tgt = c_tgt;
   p.out_x = out_x;
   p.out_y = out_y;
-  const size_t nslots = (size_t)p.nP * p.D * 2;
-  const size_t ring_bytes = nslots * kPBytes;
-  const size_t flag_bytes = align_up(nslots * sizeof(uint32_t), 256);
-  if (workspace_bytes < ring_bytes + 2 * flag_bytes) {
-    set_error("softmax_grad_gemm_dual: workspace too small (%zu < %zu)", workspace_bytes, ring_bytes + 2 * flag_bytes);
-    return PGICA_ERR_WORKSPACE_TOO_SMALL;
-  }
-  uint8_t* w = static_cast<uint8_t*>(workspace);
-  p.ready = reinterpret_cast<uint32_t*>(w + ring_bytes);
-  p.done = reinterpret_cast<uint32_t*>(w + ring_bytes + flag_bytes);
-  PGICA_CUDA_OK(cudaMemsetAsync(p.ready, 0, 2 * flag_bytes, st));
-  CUtensorMap tm_x128, tm_y128, tm_x32, tm_y32, tm_s;
-  int rc = make_tmap_bf16(&tm_x128, x, mx, k, k, 128);
-  if (rc != PGICA_OK) return rc;
-  rc = make_tmap_bf16(&tm_y128, y, my, k, k, 128);
-  if (rc != PGICA_OK) return rc;
-  rc = make_tmap_bf16(&tm_x32, x, mx, k, k, 32);
-  if (rc != PGICA_OK) return rc;
-  rc = make_tmap_bf16(&tm_y32, y, my, k, k, 32);
-  if (rc != PGICA_OK) return rc;
-  rc = make_tmap_bf16(&tm_s, workspace, nslots * kBM, kBT, kBT, 128);
-  if (rc != PGICA_OK) return rc;
-  const int grid = p.nH + p.nW + p.nP;
   const bool row = r_lse != nullptr, col = c_lse != nullptr;
-  if (row && col) return launch<true, true>(tm_x128, tm_y128, tm_x32, tm_y32, tm_s, p, grid, st);
-  if (row) return launch<true, false>(tm_x128, tm_y128, tm_x32, tm_y32, tm_s, p, grid, st);
-  return launch<false, true>(tm_x128, tm_y128, tm_x32, tm_y32, tm_s, p, grid, st);
+  if (row && col) return plan_and_launch<true, true>(x, y, mx, my, k, p, workspace, workspace_bytes, st);
+  if (row) return plan_and_launch<true, false>(x, y, mx, my, k, p, workspace, workspace_bytes, st);
+  return plan_and_launch<false, true>(x, y, mx, my, k, p, workspace, workspace_bytes, st);
 }
 
 }  // namespace pgica

@@ -50,13 +50,16 @@ S = k // 512
 plan = os.environ.get("PGICA_SGGF_PLAN")
 print(f"shape {mx}x{my}x{k} plan {plan}: {ms:.3f} ms")
 if plan:
-    R, Cw = (int(v) for v in plan.split(","))
-    nH, nW = R * S, Cw * S
+    R2, C2 = (int(v) for v in plan.split(","))
+    nH, nW = 2 * R2 * S, 2 * C2 * S  # CTAs (the plan counts pairs)
+    used = int((t.abs().sum(1) > 0).nonzero().max().item()) + 1
     groups = (("X-holders", t[:nH], CONSUMER), ("Y-holders", t[nH:nH + nW], CONSUMER),
-              ("producers", t[nH + nW:148], PRODUCER))
-    out = {"ms": ms, "plan": plan}
+              ("producers", t[nH + nW:used], PRODUCER))
+    out = {"ms": ms, "plan": plan, "ctas": used}
     for name, rows, names in groups:
+        lead = rows[0::2]  # leaders issue the MMAs; TMA / epilogue / drain columns are averaged over both CTAs
         mean = rows.mean(0) / 1e3
+        mean[:4] = lead.mean(0)[:4] / 1e3
         d = {n: round(mean[i].item(), 1) for i, n in enumerate(names) if n != "-"}
         out[name] = d
         print(name, json.dumps(d))
