@@ -300,21 +300,33 @@ def run_ours(args, rank, world, local_rank):
     value = pair_tokens_step * world * args.steps / (elapsed_ms * 1e-3)
 
     # ------------------------------------------------------------------ end-to-end step (public module API)
+    # FusedDPOHead.forward_stacked and its backward, recorded once per input-buffer set into CUDA graphs
+    # (pg.GraphedDPOStep) and replayed: issued launch by launch from Python the step is host-bound.  Two buffer sets:
+    # while step k computes on one, the inputs of step k+1 are copied from pinned host memory into the other on a
+    # copy stream (every step still pays exactly one host->device copy of its inputs inside the timed region, and one
+    # device->host read of its loss).  PGICA_BENCH_E2E_GRAPH=0 times the eager module calls instead.
     head = pg.FusedDPOHead(beta=beta)
     Wp = W.clone().requires_grad_(True)
     h2d = sum(t.numel() * t.element_size() for t in (H_host, Hr_host, y_host, m_host))
-    # Two sets of device input buffers: while step k computes on one set, the inputs of step k+1 are copied from
-    # pinned host memory into the other on a copy stream (every step still pays exactly one host->device copy of
-    # its inputs inside the timed region, and one device->host read of its loss).
-    bufs = [tuple(torch.empty_like(t) for t in (H, Hr, y, m)) for _ in range(2)]
+    use_graph = os.environ.get("PGICA_BENCH_E2E_GRAPH", "1") != "0"
     copy_stream = torch.cuda.Stream(device=dev)
     copied = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
     state = {"k": 0}
+    if use_graph:
+        steps_g = [pg.GraphedDPOStep(head, Wp, Wr, H, y, m, Hr, n_global) for _ in range(2)]
+        bufs = [(g.hidden, g.ref_hidden, g.labels, g.mask) for g in steps_g]
+    else:
+        bufs = [tuple(torch.empty_like(t) for t in (H, Hr, y, m)) for _ in range(2)]
+
+    debug_nocopy = bool(os.environ.get("PGICA_BENCH_DEBUG_NOCOPY"))  # diagnosis only: invalidates the e2e number
 
     def issue_copy(slot):
+        if debug_nocopy:
+            copied[slot].record()
+            return
         copy_stream.wait_event(consumed[slot])  # the step that last used this buffer set has finished
-        with torch.cuda.stream(copy_stream):
+        with torch.cuda.stream(copy_stream), torch.no_grad():
             for dst, src in zip(bufs[slot], (H_host, Hr_host, y_host, m_host)):
                 dst.copy_(src, non_blocking=True)
             copied[slot].record()
@@ -328,16 +340,23 @@ def run_ours(args, rank, world, local_rank):
         state["k"] += 1
         issue_copy(slot ^ 1)  # prefetch the next step's inputs
         torch.cuda.current_stream().wait_event(copied[slot])
-        Hd, Hrd, yd, md = bufs[slot]
-        hin = Hd.requires_grad_(True)
-        Wp.grad = None
-        loss, metrics = head.forward_stacked(hin, Wp, yd, md, Hrd, Wr, n_global)
-        loss.backward()
+        if use_graph:
+            steps_g[slot].launch()
+            grad_w = steps_g[slot].dweight
+        else:
+            Hd, Hrd, yd, md = bufs[slot]
+            hin = Hd.requires_grad_(True)
+            Wp.grad = None
+            loss, metrics = head.forward_stacked(hin, Wp, yd, md, Hrd, Wr, n_global)
+            loss.backward()
+            hin.requires_grad_(False)
+            grad_w = Wp.grad
         if world > 1:
-            dist.all_reduce(Wp.grad)  # the module API hands back an ordinary autograd gradient: NCCL all-reduce
-        hin.requires_grad_(False)
+            dist.all_reduce(grad_w)  # the module API hands back an ordinary autograd gradient: NCCL all-reduce
         consumed[slot].record()
-        return loss.item()  # device -> host read of the step's result
+        # device -> host read of the step's result; the graphed step copies the loss to pinned memory at the end of its
+        # forward graph, so the host reads it while the backward is still running
+        return steps_g[slot].loss_value() if use_graph else loss.item()
 
     for _ in range(max(args.warmup, 3)):
         e2e_step()
@@ -392,7 +411,9 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "inputs larger than L2: the step streams 2x103 MB of bf16 LM-head weights and writes a "
                          "206 MB fp32 dW (L2 = 126 MB)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "ms_per_step": e2e_ms / args.steps, "last_loss": last_loss},
+                "ms_per_step": e2e_ms / args.steps, "last_loss": last_loss,
+                "api": "GraphedDPOStep.launch + loss_value (CUDA graphs of FusedDPOHead.forward_stacked and its backward)" if use_graph
+                       else "FusedDPOHead.forward_stacked + backward, eager"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

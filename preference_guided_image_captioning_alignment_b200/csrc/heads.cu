@@ -9,6 +9,7 @@ using namespace pgica;
 }
 namespace pgica {
 bool sggf_supported(int64_t mx, int64_t my, int64_t k);  // sgg_f.cu
+bool sggf_single_chunk(int64_t mx, int64_t my, int64_t k);
 size_t sggf_workspace_bytes();
 }  // namespace pgica
 extern "C" {
@@ -64,7 +65,8 @@ int pgica_lmhead_logprob_bwd(const void* hidden, const void* weight, const int32
   const size_t xws_bytes = xws ? workspace_bytes - coef_bytes : 0;
   int rc = pgica_row_coef(grad_seq, row_weight, nseq, seqlen, length_normalize, -1.0f, ncoef, stream);
   if (rc != PGICA_OK) return rc;
-  if (dhidden && dweight && !dweight_is_bf16 && sggf_supported(rows, vocab, d) && xws_bytes >= sggf_workspace_bytes())
+  if (dhidden && dweight && sggf_supported(rows, vocab, d) && xws_bytes >= sggf_workspace_bytes() &&
+      (!dweight_is_bf16 || sggf_single_chunk(rows, vocab, d)))
     // both gradients from one recomputation of the logits (sgg_f.cu)
     return pgica_softmax_grad_gemm_dual(hidden, weight, rows, vocab, d, 1.0f, lse, ncoef, row_label, nullptr, nullptr,
                                         nullptr, dhidden, dhidden_is_bf16, dweight, dweight_is_bf16, xws, xws_bytes,
@@ -137,7 +139,8 @@ int pgica_ntxent_bwd(const void* a, const void* b, int64_t rows_a, int64_t rows_
   if (rc != PGICA_OK) return rc;
   rc = pgica_ntxent_coef(grad_loss, grad_mult * inv_tau, rows_b, -diag_offset, rows_a, ccoef, ctgt, stream);
   if (rc != PGICA_OK) return rc;
-  if (da && db && !db_is_bf16 && sggf_supported(rows_a, rows_b, dim) && xws_bytes >= sggf_workspace_bytes())
+  if (da && db && sggf_supported(rows_a, rows_b, dim) && xws_bytes >= sggf_workspace_bytes() &&
+      (!db_is_bf16 || sggf_single_chunk(rows_a, rows_b, dim)))
     // dA and dB from one recomputation of the similarity tiles (sgg_f.cu)
     return pgica_softmax_grad_gemm_dual(a, b, rows_a, rows_b, dim, inv_tau, lse_row, rcoef, rtgt, lse_col, ccoef, ctgt,
                                         da, da_is_bf16, db, db_is_bf16, xws, xws_bytes, stream);

@@ -685,7 +685,6 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ drain: accumulator -> OutX / OutY
     const int quarter = warp & 3;
-    const int row_in_blk = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const int out_col0 = split * kNC;
     LAP_DECL;
@@ -693,68 +692,56 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
         p, is_y, hidx, [&](int, int, int, int, bool, int) {},
         [&](int period, int chunk, int pass) {
           const int blk = 2 * (is_y ? pass * p.C2 + hidx : chunk * p.R2 + hidx) + (int)rho;
-          const int row = blk * kBM + row_in_blk;
-          const int limit = is_y ? p.my : p.mx;
-          void* out = is_y ? p.out_y : p.out_x;
           const bool bf16 = (is_y ? p.outy_bf16 : p.outx_bf16) != 0;
           const bool accumulate = is_y && chunk > 0;
           LAP(0);
           mbar_wait(outfull_bar, (uint32_t)period & 1u);
           LAP(1);
           tc_fence_after_sync();
-          if (!bf16) {
-            // fp32: 32 x 32 chunks go through a swizzled staging buffer and leave as TMA stores (or TMA add-reductions
-            // when OutY is accumulated over chunks): full 128-byte lines instead of 32 scattered 16-byte stores per
-            // instruction, and the rows past the end of the matrix are clipped by the tensor map.
-            const CUtensorMap* tm_o = is_y ? &tm_oy : &tm_ox;
-            uint8_t* stg = drain_stage + quarter * 8192;
-            const int row0 = blk * kBM + quarter * 32;
+          // The accumulator leaves through a swizzled staging buffer and TMA stores (TMA add-reductions when OutY is
+          // accumulated over chunks): full 128-byte lines instead of 32 scattered 16-byte stores per instruction, and
+          // the rows past the end of the matrix are clipped by the tensor map.  One box = 32 rows x 128 bytes:
+          // 32 fp32 columns, or 64 bf16 columns.
+          const CUtensorMap* tm_o = is_y ? &tm_oy : &tm_ox;
+          uint8_t* stg = drain_stage + quarter * 8192;
+          const int row0 = blk * kBM + quarter * 32;
+          const int cols_per_box = bf16 ? 64 : 32;
 #pragma unroll 1
-            for (int ch = 0; ch < kNC / 32; ++ch) {
-              uint32_t rr[32];
-              tmem_ld_32x32(tmem_base + lane_addr + ch * 32, rr);
+          for (int bx = 0; bx < kNC / cols_per_box; ++bx) {
+            uint32_t rr[32];
+            if (bf16) {
+              uint32_t r2[32];
+              tmem_ld_32x32(tmem_base + lane_addr + bx * 64, rr);
+              tmem_ld_32x32(tmem_base + lane_addr + bx * 64 + 32, r2);
               tmem_ld_wait();
-              if (ch >= 2) {
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // this buffer's last store has read it
-                __syncwarp();
-              }
-              const uint32_t sb = smem_u32(stg + (ch & 1) * 4096);
 #pragma unroll
-              for (int c4 = 0; c4 < 8; ++c4)
-                st_smem_v4(sb + sw128_offset(lane, c4), rr[c4 * 4], rr[c4 * 4 + 1], rr[c4 * 4 + 2], rr[c4 * 4 + 3]);
-              fence_proxy_async_smem();
-              __syncwarp();
-              if (lane == 0) {
-                if (accumulate)
-                  tma_reduce_add_2d(tm_o, stg + (ch & 1) * 4096, out_col0 + ch * 32, row0);
-                else
-                  tma_store_2d(tm_o, stg + (ch & 1) * 4096, out_col0 + ch * 32, row0);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-              }
+              for (int i = 0; i < 16; ++i) rr[i] = pack_bf16x2(__uint_as_float(rr[2 * i]), __uint_as_float(rr[2 * i + 1]));
+#pragma unroll
+              for (int i = 0; i < 16; ++i) rr[16 + i] = pack_bf16x2(__uint_as_float(r2[2 * i]), __uint_as_float(r2[2 * i + 1]));
+            } else {
+              tmem_ld_32x32(tmem_base + lane_addr + bx * 32, rr);
+              tmem_ld_wait();
             }
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // written: a later chunk may add to it
-            __syncwarp();
-          } else {
-#pragma unroll 1
-            for (int ch = 0; ch < kNC / 32; ++ch) {
-              uint32_t rr[32];
-              tmem_ld_32x32(tmem_base + lane_addr + ch * 32, rr);
-              tmem_ld_wait();
-              const int col = out_col0 + ch * 32;
-              if (row < limit) {
-                uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out) + (size_t)row * p.k + col);
+            if (bx >= 2) {
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // this buffer's last store has read it
+              __syncwarp();
+            }
+            const uint32_t sb = smem_u32(stg + (bx & 1) * 4096);
 #pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                  uint4 v;
-                  v.x = pack_bf16x2(__uint_as_float(rr[c4 * 8 + 0]), __uint_as_float(rr[c4 * 8 + 1]));
-                  v.y = pack_bf16x2(__uint_as_float(rr[c4 * 8 + 2]), __uint_as_float(rr[c4 * 8 + 3]));
-                  v.z = pack_bf16x2(__uint_as_float(rr[c4 * 8 + 4]), __uint_as_float(rr[c4 * 8 + 5]));
-                  v.w = pack_bf16x2(__uint_as_float(rr[c4 * 8 + 6]), __uint_as_float(rr[c4 * 8 + 7]));
-                  dst[c4] = v;
-                }
-              }
+            for (int c4 = 0; c4 < 8; ++c4)
+              st_smem_v4(sb + sw128_offset(lane, c4), rr[c4 * 4], rr[c4 * 4 + 1], rr[c4 * 4 + 2], rr[c4 * 4 + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (accumulate)
+                tma_reduce_add_2d(tm_o, stg + (bx & 1) * 4096, out_col0 + bx * cols_per_box, row0);
+              else
+                tma_store_2d(tm_o, stg + (bx & 1) * 4096, out_col0 + bx * cols_per_box, row0);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
           }
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // written: a later chunk may add to it
+          __syncwarp();
           tc_fence_before_sync();
           mbar_arrive_cluster(outfree_bar, 0);  // tell the leader: this CTA's accumulator may be overwritten
           LAP(2);
@@ -778,11 +765,11 @@ struct Plan {
 // arrived in time; measured on cfg2 it needs 1.5x that (profiles/r1_trace_sggf_v2_pairs.log: a quarter of its time
 // goes to waiting for TMA loads), and a drain of the 128 x 512 accumulator costs about 90.  The slowest role sets
 // the pace of a chunk.
-Plan choose_plan(int RB2, int J2, int k, int npairs) {
+Plan choose_plan(int RB2, int J2, int k, int npairs, bool single_chunk) {
   const int S = k / kNC;
   const double per_quad = 1.5 * k / 16.0, drain = 90.0;
   Plan best{0, 0, 0, 0, 0, 1e300};
-  for (int R2 = 1; R2 <= RB2 && R2 * S <= npairs - S - 1; ++R2) {
+  for (int R2 = single_chunk ? RB2 : 1; R2 <= RB2 && R2 * S <= npairs - S - 1; ++R2) {
     const int nH = R2 * S;
     for (int C2 = 1; C2 * S <= npairs - nH - 1 && C2 <= J2; ++C2) {
       const int nW = C2 * S, nP = npairs - nH - nW;
@@ -883,9 +870,11 @@ int plan_and_launch(const void* x, const void* y, int64_t mx, int64_t my, int64_
   int rc = resident_pairs<kRow, kCol>(&npairs);
   if (rc != PGICA_OK) return rc;
   const int S = p.S;
-  Plan pl = choose_plan(p.RB2, p.J2, (int)k, npairs);
+  // a bf16 OutY cannot be accumulated over chunks: all of X must then fit one chunk of X-holders
+  Plan pl = choose_plan(p.RB2, p.J2, (int)k, npairs, p.outy_bf16 != 0);
   plan_override(&pl, npairs, S);
-  PGICA_REQUIRE(pl.R2 >= 1 && pl.nP >= 1, "softmax_grad_gemm_dual: no role split for %d CTA pairs", npairs);
+  PGICA_REQUIRE(pl.R2 >= 1 && pl.nP >= 1, "softmax_grad_gemm_dual: no role split of %d CTA pairs fits %d row blocks%s",
+                npairs, 2 * p.RB2, p.outy_bf16 ? " in one chunk (bf16 OutY)" : "");
   PGICA_REQUIRE(!(p.outy_bf16 && p.RB2 > pl.R2), "softmax_grad_gemm_dual: a bf16 OutY cannot be accumulated over chunks");
   p.R2 = pl.R2;
   p.C2 = pl.C2;
@@ -915,16 +904,12 @@ int plan_and_launch(const void* x, const void* y, int64_t mx, int64_t my, int64_
   if (rc != PGICA_OK) return rc;
   rc = make_tmap_bf16(&tm_s, workspace, nslots * kBM, kBT, kBT, 128);
   if (rc != PGICA_OK) return rc;
-  // fp32 outputs leave through TMA (a bf16 output is written directly and its map stays unused)
-  CUtensorMap tm_ox = tm_s, tm_oy = tm_s;
-  if (!p.outx_bf16) {
-    rc = make_tmap_f32(&tm_ox, p.out_x, mx, k, k, 32);
-    if (rc != PGICA_OK) return rc;
-  }
-  if (!p.outy_bf16) {
-    rc = make_tmap_f32(&tm_oy, p.out_y, my, k, k, 32);
-    if (rc != PGICA_OK) return rc;
-  }
+  // the outputs leave through TMA in boxes of 32 rows x 128 bytes
+  CUtensorMap tm_ox, tm_oy;
+  rc = p.outx_bf16 ? make_tmap_bf16(&tm_ox, p.out_x, mx, k, k, 32) : make_tmap_f32(&tm_ox, p.out_x, mx, k, k, 32);
+  if (rc != PGICA_OK) return rc;
+  rc = p.outy_bf16 ? make_tmap_bf16(&tm_oy, p.out_y, my, k, k, 32) : make_tmap_f32(&tm_oy, p.out_y, my, k, k, 32);
+  if (rc != PGICA_OK) return rc;
   return launch<kRow, kCol>(tm_x128, tm_y128, tm_x64, tm_y64, tm_s, tm_ox, tm_oy, p, st);
 }
 
@@ -935,6 +920,15 @@ bool sggf_supported(int64_t mx, int64_t my, int64_t k) {
   if (const char* e = getenv("PGICA_SGG_FUSED"))
     if (atoi(e) == 0) return false;
   return k % kNC == 0 && k / kNC <= 4 && mx >= 1 && my >= 1;
+}
+
+// true when x fits one chunk of X-holders, i.e. OutY is written once and may therefore be bf16
+bool sggf_single_chunk(int64_t mx, int64_t my, int64_t k) {
+  int npairs = 0;
+  if (k % kNC != 0 || k / kNC > 4 || resident_pairs<true, false>(&npairs) != PGICA_OK) return false;
+  const int RB2 = (int)((ceil_div(mx, kBM) + 1) / 2), J2 = (int)((ceil_div(my, kBT) + 1) / 2);
+  Plan pl = choose_plan(RB2, J2, (int)k, npairs, true);
+  return pl.R2 >= RB2 && pl.nP >= 1;
 }
 
 size_t sggf_workspace_bytes() {

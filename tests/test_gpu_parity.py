@@ -563,6 +563,10 @@ def test_softmax_grad_gemm_dual(pg, cuda_device, monkeypatch, mx, my, k, mode, p
     assert rel(ox, sx) < 1e-3 and rel(oy, sy) < 1e-3
     bx, _ = F.softmax_grad_gemm_dual(x, y, 1.0, row=row, col=col, out_x_dtype=torch.bfloat16)
     assert rel(bx.float(), exact_x) < GRAD_RTOL
+    if plan is None:  # one chunk: OutY is written once and may be bf16 as well
+        bx, by = F.softmax_grad_gemm_dual(x, y, 1.0, row=row, col=col, out_x_dtype=torch.bfloat16,
+                                          out_y_dtype=torch.bfloat16)
+        assert rel(bx.float(), exact_x) < GRAD_RTOL and rel(by.float(), exact_y) < GRAD_RTOL
 
 
 def test_lmhead_backward_dual_matches_split(pg, cuda_device, monkeypatch):
@@ -584,3 +588,28 @@ def test_lmhead_backward_dual_matches_split(pg, cuda_device, monkeypatch):
     dh0, dw0 = F.lmhead_logprob_bwd(H, W, rl, rw, lse, gseq, False)
     assert rel(dh1.float(), dh0.float()) < 2e-3 and rel(dw1, dw0) < 2e-3
     assert torch.count_nonzero(dh1[:, T - 10:]).item() == 0  # rows that score nothing get exactly zero
+
+
+def test_graphed_dpo_step_matches_eager(pg, cuda_device):
+    """GraphedDPOStep (CUDA graph of FusedDPOHead.forward_stacked + backward) replays to the eager result, also after
+    the static inputs are overwritten."""
+    dev = cuda_device
+    B, T, d, V = 3, 32, 512, 3001
+    g = torch.Generator().manual_seed(11)
+    W = (torch.randn(V, d, generator=g) * 0.05).to(torch.bfloat16).to(dev)
+    Wr = (torch.randn(V, d, generator=g) * 0.05).to(torch.bfloat16).to(dev)
+    hs = [torch.randn(2 * B, T, d, generator=g).to(torch.bfloat16).to(dev) for _ in range(4)]
+    ys = [torch.randint(0, V, (2 * B, T), generator=g).to(dev) for _ in range(2)]
+    m = torch.ones(2 * B, T, dtype=torch.long, device=dev)
+    head = pg.FusedDPOHead(beta=0.1)
+    step = pg.GraphedDPOStep(head, W.clone().requires_grad_(True), Wr, hs[0], ys[0], m, hs[1])
+    for h, hr, y in ((hs[0], hs[1], ys[0]), (hs[2], hs[3], ys[1])):
+        step.copy_inputs(h, y, m, hr)
+        step.launch()
+        value = step.loss_value()
+        loss = step.loss
+        Wg, hg = W.clone().requires_grad_(True), h.clone().requires_grad_(True)
+        ref_loss, _ = head.forward_stacked(hg, Wg, y, m, hr, Wr)
+        ref_loss.backward()
+        assert loss.item() == pytest.approx(ref_loss.item(), rel=1e-6) and value == loss.item()
+        assert torch.equal(step.dweight, Wg.grad) and torch.equal(step.dhidden, hg.grad)

@@ -99,3 +99,25 @@ if what in ("cfg2", "all"):
     e1.record()
     torch.cuda.synchronize()
     print(f"cfg2 split: {e0.elapsed_time(e1) / 10:.3f} ms/bwd")
+
+if what in ("bf16dw",):
+    os.environ.pop("PGICA_SGGF_PLAN", None)
+    os.environ["PGICA_SGG_FUSED"] = "1"
+    B, T, d, V = 16, 128, 1024, 50257
+    g = torch.Generator().manual_seed(1234)
+    W = (torch.randn(V, d, generator=g) * 0.02).to(torch.bfloat16).to(dev)
+    H = torch.randn(2 * B, T, d, generator=g).to(torch.bfloat16).to(dev)
+    y = torch.randint(0, V, (2 * B, T), generator=g).to(dev)
+    m = torch.ones(2 * B, T, dtype=torch.long, device=dev)
+    seq, lse, _, rl, rw, _ = F.lmhead_logprob_fwd(H, W, y, m, False)
+    gseq = torch.randn(2 * B, device=dev)
+    for dt in (torch.float32, torch.bfloat16):
+        for _ in range(3):
+            F.lmhead_logprob_bwd(H, W, rl, rw, lse, gseq, False, dweight_dtype=dt)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            F.lmhead_logprob_bwd(H, W, rl, rw, lse, gseq, False, dweight_dtype=dt)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"cfg2 dual dW {dt}: {e0.elapsed_time(e1) / 10:.3f} ms/bwd")
