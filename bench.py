@@ -212,7 +212,13 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     reducer = None
+    fused_reduce = None
     state_r = {}
+    if world > 1 and fused and os.environ.get("PGICA_DW_ALLREDUCE", "fused") == "fused":
+        # reduce-scatter of dW inside the backward kernel (TMA add-reductions into the owners' symmetric-memory
+        # buffers over NVLink) + copy-engine all-gather
+        from preference_guided_image_captioning_alignment_b200 import distributed as D
+        fused_reduce = D.FusedDWReduce(V, d, dev)
     if world > 1 and not fused and os.environ.get("PGICA_DW_ALLREDUCE", "peer") == "peer":
         from preference_guided_image_captioning_alignment_b200 import distributed as D
         reducer = D.PeerAllReduce((V, d), dev)
@@ -233,7 +239,11 @@ def run_ours(args, rank, world, local_rank):
         loss, metrics, dpc = F.dpo_loss_fwd(seq_p[:B], seq_p[B:], seq_r[:B], seq_r[B:], beta, 0.0, n_global)
         gseq = F.dpo_grad_seq(dpc, one)
         mark(3)
-        if fused:
+        if fused_reduce is not None:
+            dh, dw = fused_reduce.backward(H, W, rl, rw, lse_p, gseq, False)
+            mark(4)
+            mark(5)
+        elif fused:
             dh, dw = F.lmhead_logprob_bwd(H, W, rl, rw, lse_p, gseq, False)
             mark(4)
             mark(5)
@@ -254,7 +264,7 @@ def run_ours(args, rank, world, local_rank):
                 # clusters are resident first; the peer copies use no SM and overlap dH
                 state_r["done"] = reducer.all_reduce(after=dw_ready)
                 torch.cuda.current_stream().wait_event(state_r["done"])
-            else:
+            elif fused_reduce is None:
                 dist.all_reduce(dw)
             packed = torch.cat([loss.reshape(1), metrics])
             dist.all_reduce(packed)
@@ -374,6 +384,37 @@ def run_ours(args, rank, world, local_rank):
         e2e_ms = t.item()
     e2e_value = pair_tokens_step * world * args.steps / (e2e_ms * 1e-3)
 
+    # ------------------------------------------------------------------ NT-Xent with global negatives (cfg3 scheme)
+    dist_ntxent = None
+    if world > 1:
+        from preference_guided_image_captioning_alignment_b200 import distributed as D
+        bl = 4096  # rows per rank (cfg3: 32768 over 8 GPUs)
+        ga = torch.Generator().manual_seed(77 + rank)
+        a_l = torch.nn.functional.normalize(torch.randn(bl, 512, generator=ga), dim=-1).to(dev).requires_grad_(True)
+        b_l = torch.nn.functional.normalize(torch.randn(bl, 512, generator=ga), dim=-1).to(dev).requires_grad_(True)
+
+        def nt_step():
+            a_l.grad = b_l.grad = None
+            loss = D.global_ntxent(a_l, b_l, 0.5)
+            loss.backward()
+            return loss
+
+        for _ in range(3):
+            nt_step()
+        barrier()
+        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0.record()
+        for _ in range(10):
+            nt_loss = nt_step()
+        n1.record()
+        barrier()
+        t = torch.tensor([n0.elapsed_time(n1) / 10], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        Bg = bl * world
+        dist_ntxent = {"global_batch": Bg, "rows_per_gpu": bl, "ms_per_step": t.item(),
+                       "pairs_per_s": Bg / (t.item() * 1e-3), "algorithmic_tflops": 6.0 * Bg * Bg * 512 / t.item() / 1e9,
+                       "loss": nt_loss.item(),
+                       "collectives": "all-gather of text rows, all-gather of column-LSE partials, reduce-scatter of dB"}
     if rank != 0:
         return
     pk = peaks()
@@ -398,6 +439,8 @@ def run_ours(args, rank, world, local_rank):
                 "step_frac": FLOP_PER_PAIR_TOKEN * pair_tokens_step / (elapsed_ms / args.steps) / 1e9 / pk["burst"]}
     cpu_val, cpu_sec, cpu_threads = time_cpu_reference(4, 2, 1)
     extras = ntxent_extras(torch, F, dev)
+    if dist_ntxent is not None:
+        extras["global_negatives"] = dist_ntxent
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -407,7 +450,10 @@ def run_ours(args, rank, world, local_rank):
                    "backward": "dual kernel: dH and dW from one recomputation of the logits" if fused
                                else "one launch per product",
                    "dw_allreduce": ("none" if world == 1 else "copy-engine peer all-reduce overlapping dH"
-                                    if reducer is not None else "nccl fp32 all-reduce after the backward"),
+                                    if reducer is not None else
+                                    "reduce-scatter inside the backward kernel (TMA add into the owners' buffers over "
+                                    "NVLink) + copy-engine all-gather, fp32" if fused_reduce is not None
+                                    else "nccl fp32 all-reduce after the backward"),
                    "l2": "inputs larger than L2: the step streams 2x103 MB of bf16 LM-head weights and writes a "
                          "206 MB fp32 dW (L2 = 126 MB)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

@@ -108,6 +108,8 @@ struct SggfParams {
   const int* c_tgt;
   void* out_x;
   void* out_y;
+  const CUtensorMap* oy_maps;  // reduce-scatter mode: one fp32 map per owner rank's OutY buffer (device array), else null
+  int own_blocks;              // ... column tiles (128 rows of OutY) per owner
   uint32_t* ready;        // [2*nP*D*2] use count + 1 of the tile that is complete in the slot
   uint32_t* done;         // [2*nP*D*2] consumers that have pulled a tile out of the slot, ever
 };
@@ -693,7 +695,10 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
         [&](int period, int chunk, int pass) {
           const int blk = 2 * (is_y ? pass * p.C2 + hidx : chunk * p.R2 + hidx) + (int)rho;
           const bool bf16 = (is_y ? p.outy_bf16 : p.outx_bf16) != 0;
-          const bool accumulate = is_y && chunk > 0;
+          // reduce-scatter mode: OutY tiles are ADDED into the buffer of the rank that owns their rows (peer memory over
+          // NVLink, zeroed by the owner beforehand), from every chunk of every rank
+          const bool scatter = is_y && p.oy_maps != nullptr;
+          const bool accumulate = scatter || (is_y && chunk > 0);
           LAP(0);
           mbar_wait(outfull_bar, (uint32_t)period & 1u);
           LAP(1);
@@ -702,7 +707,7 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
           // accumulated over chunks): full 128-byte lines instead of 32 scattered 16-byte stores per instruction, and
           // the rows past the end of the matrix are clipped by the tensor map.  One box = 32 rows x 128 bytes:
           // 32 fp32 columns, or 64 bf16 columns.
-          const CUtensorMap* tm_o = is_y ? &tm_oy : &tm_ox;
+          const CUtensorMap* tm_o = scatter ? p.oy_maps + blk / p.own_blocks : is_y ? &tm_oy : &tm_ox;
           uint8_t* stg = drain_stage + quarter * 8192;
           const int row0 = blk * kBM + quarter * 32;
           const int cols_per_box = bf16 ? 64 : 32;
@@ -863,9 +868,16 @@ int launch(const CUtensorMap& tm_x128, const CUtensorMap& tm_y128, const CUtenso
   return PGICA_OK;
 }
 
+struct ScatterSpec {
+  const void* const* peers_host = nullptr;  // base of every rank's fp32 [>= my][k] OutY buffer
+  int n_peers = 0;
+  int64_t rows_per_owner = 0;               // multiple of 128
+  void* tmaps_device = nullptr;             // >= 128 * n_peers bytes, 128-byte aligned
+};
+
 template <bool kRow, bool kCol>
 int plan_and_launch(const void* x, const void* y, int64_t mx, int64_t my, int64_t k, SggfParams p, void* workspace,
-                    size_t workspace_bytes, cudaStream_t st) {
+                    size_t workspace_bytes, const ScatterSpec& sc, cudaStream_t st) {
   int npairs = 0;
   int rc = resident_pairs<kRow, kCol>(&npairs);
   if (rc != PGICA_OK) return rc;
@@ -908,8 +920,22 @@ int plan_and_launch(const void* x, const void* y, int64_t mx, int64_t my, int64_
   CUtensorMap tm_ox, tm_oy;
   rc = p.outx_bf16 ? make_tmap_bf16(&tm_ox, p.out_x, mx, k, k, 32) : make_tmap_f32(&tm_ox, p.out_x, mx, k, k, 32);
   if (rc != PGICA_OK) return rc;
-  rc = p.outy_bf16 ? make_tmap_bf16(&tm_oy, p.out_y, my, k, k, 32) : make_tmap_f32(&tm_oy, p.out_y, my, k, k, 32);
-  if (rc != PGICA_OK) return rc;
+  if (sc.n_peers > 0) {
+    // one tensor map per owner's buffer, copied to the device ahead of the launch (the copy stages its pageable
+    // source synchronously, so the host array may die when this function returns)
+    CUtensorMap maps[16];
+    for (int r = 0; r < sc.n_peers; ++r) {
+      rc = make_tmap_f32(&maps[r], sc.peers_host[r], my, k, k, 32);
+      if (rc != PGICA_OK) return rc;
+    }
+    PGICA_CUDA_OK(cudaMemcpyAsync(sc.tmaps_device, maps, sizeof(CUtensorMap) * sc.n_peers, cudaMemcpyHostToDevice, st));
+    p.oy_maps = static_cast<const CUtensorMap*>(sc.tmaps_device);
+    p.own_blocks = (int)(sc.rows_per_owner / kBM);
+    tm_oy = maps[0];
+  } else {
+    rc = p.outy_bf16 ? make_tmap_bf16(&tm_oy, p.out_y, my, k, k, 32) : make_tmap_f32(&tm_oy, p.out_y, my, k, k, 32);
+    if (rc != PGICA_OK) return rc;
+  }
   return launch<kRow, kCol>(tm_x128, tm_y128, tm_x64, tm_y64, tm_s, tm_ox, tm_oy, p, st);
 }
 
@@ -940,9 +966,23 @@ size_t sggf_workspace_bytes() {
 int sggf_dispatch(const void* x, const void* y, int64_t mx, int64_t my, int64_t k, float scale, const float* r_lse,
                   const float* r_coef, const int32_t* r_tgt, const float* c_lse, const float* c_coef,
                   const int32_t* c_tgt, void* out_x, int out_x_is_bf16, void* out_y, int out_y_is_bf16,
-                  void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                  void* workspace, size_t workspace_bytes, cudaStream_t st, const void* const* peers_host = nullptr,
+                  int n_peers = 0, int64_t rows_per_owner = 0, void* tmaps_device = nullptr) {
   PGICA_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0,
                 "softmax_grad_gemm_dual: workspace missing or not 256-byte aligned");
+  ScatterSpec sc;
+  if (n_peers > 0) {
+    PGICA_REQUIRE(peers_host && n_peers <= 16 && tmaps_device && (reinterpret_cast<uintptr_t>(tmaps_device) & 127u) == 0,
+                  "softmax_grad_gemm_dual_scatter: bad peer list / tensor-map scratch");
+    PGICA_REQUIRE(rows_per_owner > 0 && rows_per_owner % kBM == 0 && rows_per_owner * n_peers >= my,
+                  "softmax_grad_gemm_dual_scatter: rows_per_owner %lld x %d ranks must be a multiple of 128 covering %lld rows",
+                  (long long)rows_per_owner, n_peers, (long long)my);
+    PGICA_REQUIRE(!out_y_is_bf16, "softmax_grad_gemm_dual_scatter: the scattered OutY is fp32");
+    sc.peers_host = peers_host;
+    sc.n_peers = n_peers;
+    sc.rows_per_owner = rows_per_owner;
+    sc.tmaps_device = tmaps_device;
+  }
   const int RB = (int)ceil_div(mx, kBM), J = (int)ceil_div(my, kBT);
   PGICA_REQUIRE((int64_t)RB * J < (1ll << 30), "softmax_grad_gemm_dual: problem too large");
   SggfParams p{};
@@ -964,9 +1004,9 @@ int sggf_dispatch(const void* x, const void* y, int64_t mx, int64_t my, int64_t 
   p.out_x = out_x;
   p.out_y = out_y;
   const bool row = r_lse != nullptr, col = c_lse != nullptr;
-  if (row && col) return plan_and_launch<true, true>(x, y, mx, my, k, p, workspace, workspace_bytes, st);
-  if (row) return plan_and_launch<true, false>(x, y, mx, my, k, p, workspace, workspace_bytes, st);
-  return plan_and_launch<false, true>(x, y, mx, my, k, p, workspace, workspace_bytes, st);
+  if (row && col) return plan_and_launch<true, true>(x, y, mx, my, k, p, workspace, workspace_bytes, sc, st);
+  if (row) return plan_and_launch<true, false>(x, y, mx, my, k, p, workspace, workspace_bytes, sc, st);
+  return plan_and_launch<false, true>(x, y, mx, my, k, p, workspace, workspace_bytes, sc, st);
 }
 
 }  // namespace pgica
@@ -1008,4 +1048,26 @@ extern "C" int pgica_softmax_grad_gemm_dual(const void* x, const void* y, int64_
   PGICA_REQUIRE(scale > 0.f, "softmax_grad_gemm_dual: scale must be positive");
   return sggf_dispatch(x, y, mx, my, k, scale, r_lse, r_coef, r_tgt, c_lse, c_coef, c_tgt, out_x, out_x_is_bf16, out_y,
                        out_y_is_bf16, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int pgica_softmax_grad_gemm_dual_scatter(const void* x, const void* y, int64_t mx, int64_t my, int64_t k,
+                                                    float scale, const float* r_lse, const float* r_coef,
+                                                    const int32_t* r_tgt, const float* c_lse, const float* c_coef,
+                                                    const int32_t* c_tgt, void* out_x, int out_x_is_bf16,
+                                                    const void* const* out_y_peers_host, int n_peers,
+                                                    int64_t rows_per_owner, void* tmaps_device, void* workspace,
+                                                    size_t workspace_bytes, void* stream) {
+  using namespace pgica;
+  int rc = pgica_device_check();
+  if (rc != PGICA_OK) return rc;
+  PGICA_REQUIRE(x && y && out_x && out_y_peers_host && n_peers >= 1, "softmax_grad_gemm_dual_scatter: null operand");
+  PGICA_REQUIRE(mx > 0 && my > 0 && k > 0 && k % kNC == 0 && k / kNC <= 4,
+                "softmax_grad_gemm_dual_scatter: bad shape (mx %lld my %lld k %lld)", (long long)mx, (long long)my,
+                (long long)k);
+  const bool row = r_lse != nullptr, col = c_lse != nullptr;
+  PGICA_REQUIRE(row || col, "softmax_grad_gemm_dual_scatter: need row statistics, column statistics or both");
+  PGICA_REQUIRE((!row || r_coef) && (!col || c_coef) && scale > 0.f, "softmax_grad_gemm_dual_scatter: bad statistics");
+  return sggf_dispatch(x, y, mx, my, k, scale, r_lse, r_coef, r_tgt, c_lse, c_coef, c_tgt, out_x, out_x_is_bf16,
+                       const_cast<void*>(out_y_peers_host[0]), 0, workspace, workspace_bytes,
+                       static_cast<cudaStream_t>(stream), out_y_peers_host, n_peers, rows_per_owner, tmaps_device);
 }

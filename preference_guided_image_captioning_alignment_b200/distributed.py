@@ -223,3 +223,55 @@ class PeerAllReduce:
         if trace is not None:
             self.last_trace = trace
         return done
+
+
+class FusedDWReduce:
+    """Data-parallel sum of the LM-head weight gradient with the REDUCE-SCATTER done by the backward kernel itself.
+
+    The dual backward kernel (csrc/sgg_f.cu) keeps 128-row tiles of dW resident in TMEM; in scatter mode it drains
+    every finished tile with a TMA add-reduction straight into the buffer of the rank that owns those rows — peer
+    memory over NVLink / NVSwitch, mapped through torch symmetric memory.  When the kernels of all ranks have ended,
+    rank r holds the fully reduced rows [r * own, (r+1) * own); the all-gather that completes the all-reduce is W-1
+    peer copies of 1/W of the buffer on the copy engines.  Per GPU the kernel sends (W-1)/W of dW spread over its
+    whole run time (~0.2 TB/s at W=8, a fraction of NVLink), and only the all-gather is exposed:
+
+        zero my rows -> barrier -> backward kernel (dH local, dW tiles -> owners) -> barrier -> push my rows -> barrier
+
+    `backward(...)` returns (dhidden, dweight_view); dweight_view is this rank's copy of the reduced (V, d) fp32
+    gradient inside the symmetric buffer, valid on the current stream when the call returns."""
+
+    def __init__(self, vocab: int, d: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = _world(group)
+        self.vocab, self.d = int(vocab), int(d)
+        blocks = (self.vocab + 127) // 128
+        self.own_rows = 128 * ((blocks + self.world - 1) // self.world)
+        self.rows = self.own_rows * self.world
+        self.buf = symm.empty(self.rows * self.d, dtype=torch.float32, device=device)
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        self.peers = [self.hdl.get_buffer(p, (self.rows, self.d), torch.float32) for p in range(self.world)]
+        self.peer_ptrs = [t.data_ptr() for t in self.peers]
+        self.tmaps = torch.empty(128 * self.world + 128, dtype=torch.uint8, device=device)
+        off = (-self.tmaps.data_ptr()) % 128
+        self.tmaps = self.tmaps[off: off + 128 * self.world]
+        self.local = self.peers[self.rank]
+        self.local.zero_()
+
+    @property
+    def view(self):
+        return self.local[: self.vocab]
+
+    def backward(self, hidden, weight, row_label, row_weight, lse, grad_seq, length_normalize=False,
+                 dhidden_dtype=torch.bfloat16):
+        lo, hi = self.rank * self.own_rows, (self.rank + 1) * self.own_rows
+        self.local[lo:hi].zero_()
+        self.hdl.barrier(channel=0)  # every owner's rows are zero; last step's all-gather has been consumed
+        dh = F.lmhead_logprob_bwd_scatter(hidden, weight, row_label, row_weight, lse, grad_seq, self.peer_ptrs,
+                                          self.own_rows, self.tmaps, length_normalize, dhidden_dtype)
+        self.hdl.barrier(channel=1)  # every rank's tiles have been added: my rows are final
+        for p in range(self.world):
+            if p != self.rank:
+                self.peers[p][lo:hi].copy_(self.local[lo:hi])
+        self.hdl.barrier(channel=2)  # everybody's rows have arrived here
+        return dh, self.view

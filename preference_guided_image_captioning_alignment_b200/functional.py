@@ -309,6 +309,29 @@ def rownorm_bwd(x, inv_norm, g, second=-1):
 
 
 # ----------------------------------------------------------------------------------------- logits path
+def lmhead_logprob_bwd_scatter(hidden, weight, row_label, row_weight, lse, grad_seq, peer_ptrs, rows_per_owner,
+                               tmaps, length_normalize=False, dhidden_dtype=torch.bfloat16):
+    """Backward of the LM head with the weight gradient reduce-scattered inside the kernel: dhidden is returned,
+    dweight tiles are added into the fp32 buffers at `peer_ptrs` (one device pointer per rank, rank r owning rows
+    [r * rows_per_owner, ...)).  `tmaps`: uint8 device scratch of >= 128 * len(peer_ptrs) bytes."""
+    _need_cuda(hidden, weight, grad_seq, tmaps)
+    lib = _lib.load()
+    nseq, T, d = hidden.shape
+    V = weight.shape[0]
+    dev = hidden.device
+    need = ctypes.c_size_t(0)
+    _lib.check(lib.pgica_lmhead_logprob_workspace_bytes(nseq, T, d, V, ctypes.byref(need)))
+    ws = _ws(need.value, dev)
+    dh = torch.empty(nseq, T, d, dtype=dhidden_dtype, device=dev)
+    arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(q) for q in peer_ptrs])
+    _lib.check(lib.pgica_lmhead_logprob_bwd_scatter(_p(hidden), _p(weight), _p(row_label), _p(row_weight), _p(lse),
+                                                    _p(grad_seq.float().contiguous()), nseq, T, d, V,
+                                                    1 if length_normalize else 0, _p(dh),
+                                                    1 if dhidden_dtype == torch.bfloat16 else 0, arr, len(peer_ptrs),
+                                                    int(rows_per_owner), _p(tmaps), _p(ws), ws.numel(), _stream()))
+    return dh
+
+
 def prep_rows(labels, mask, vocab):
     _need_cuda(labels, mask)
     lib = _lib.load()

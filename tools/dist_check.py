@@ -112,6 +112,31 @@ def main():
         ok &= res["ok"]
         if rank == 0:
             print(json.dumps(res), flush=True)
+    # ---------------------------------------------------------------- in-kernel reduce-scatter of dW == NCCL all-reduce
+    from preference_guided_image_captioning_alignment_b200 import functional as Fn
+    for (B2, T2, d2, V2) in ((4, 48, 512, 3001), (6, 64, 1024, 5003)):
+        gen2 = torch.Generator().manual_seed(200 + rank)
+        gw = torch.Generator().manual_seed(7)
+        W2 = (torch.randn(V2, d2, generator=gw) * 0.05).to(torch.bfloat16).to(dev)
+        H2 = torch.randn(B2, T2, d2, generator=gen2).to(torch.bfloat16).to(dev)
+        y2 = torch.randint(0, V2, (B2, T2), generator=gen2).to(dev)
+        m2 = torch.ones(B2, T2, dtype=torch.long, device=dev)
+        gs = torch.randn(B2, generator=gen2).to(dev)
+        _, lse2, _, rl2, rw2, _ = Fn.lmhead_logprob_fwd(H2, W2, y2, m2, False)
+        dh_ref, dw_ref = Fn.lmhead_logprob_bwd(H2, W2, rl2, rw2, lse2, gs, False)
+        dw_ref = dw_ref.clone()
+        dist.all_reduce(dw_ref)
+        fr = D2.FusedDWReduce(V2, d2, dev)
+        for trial in range(2):
+            dh2, dw2 = fr.backward(H2, W2, rl2, rw2, lse2, gs, False)
+            torch.cuda.synchronize()
+            e_w = rel(dw2.cpu().numpy(), dw_ref.cpu().numpy())
+            e_h = rel(dh2.float().cpu().numpy(), dh_ref.float().cpu().numpy())
+            res = {"check": "fused_dw_reduce", "world": world, "shape": [B2, T2, d2, V2], "trial": trial, "dw_rel": e_w,
+                   "dh_rel": e_h, "ok": bool(e_w < 1e-5 and e_h < 1e-5)}
+            ok &= res["ok"]
+            if rank == 0:
+                print(json.dumps(res), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
