@@ -214,9 +214,10 @@ def run_ours(args, rank, world, local_rank):
     reducer = None
     fused_reduce = None
     state_r = {}
-    if world > 1 and fused and os.environ.get("PGICA_DW_ALLREDUCE", "fused") == "fused":
-        # reduce-scatter of dW inside the backward kernel (TMA add-reductions into the owners' symmetric-memory
-        # buffers over NVLink) + copy-engine all-gather
+    if world > 1 and fused and os.environ.get("PGICA_DW_ALLREDUCE", "nccl") == "fused":
+        # opt-in: scatter of dW inside the backward kernel (TMA stores into the owners' symmetric-memory slots over
+        # NVLink) + local sum + copy-engine all-gather.  Measured slower than NCCL after the kernel at N >= 4
+        # (profiles/r1_scaling_notes.md), so NCCL is the default.
         from preference_guided_image_captioning_alignment_b200 import distributed as D
         fused_reduce = D.FusedDWReduce(V, d, dev)
     if world > 1 and not fused and os.environ.get("PGICA_DW_ALLREDUCE", "peer") == "peer":
@@ -451,8 +452,8 @@ def run_ours(args, rank, world, local_rank):
                                else "one launch per product",
                    "dw_allreduce": ("none" if world == 1 else "copy-engine peer all-reduce overlapping dH"
                                     if reducer is not None else
-                                    "reduce-scatter inside the backward kernel (TMA add into the owners' buffers over "
-                                    "NVLink) + copy-engine all-gather, fp32" if fused_reduce is not None
+                                    "scatter inside the backward kernel (TMA stores into the owners' slots over NVLink) + "
+                                    "local sum + copy-engine all-gather, fp32" if fused_reduce is not None
                                     else "nccl fp32 all-reduce after the backward"),
                    "l2": "inputs larger than L2: the step streams 2x103 MB of bf16 LM-head weights and writes a "
                          "206 MB fp32 dW (L2 = 126 MB)"},

@@ -129,15 +129,16 @@ int pgica_softmax_grad_gemm_dual(const void* x, const void* y, int64_t mx, int64
                                  void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Dual softmax-gradient GEMM fused with the REDUCE-SCATTER of out_y over the GPUs of an NVLink node (the data-
- * parallel all-reduce of the LM-head weight gradient, SURVEY 8(e), first half): instead of writing out_y locally,
- * every 128-row tile of out_y is ADDED (TMA add-reduction, fp32) into the buffer of the rank that owns those rows —
- * peer memory mapped into this process (e.g. torch symmetric memory).  out_y_peers_host[r] is the base of rank r's
- * fp32 [>= my][k] buffer (same layout everywhere; HOST array of n_peers <= 16 device pointers, entry `own rank` is
- * the local buffer); rank r owns rows [r * rows_per_owner, (r+1) * rows_per_owner), rows_per_owner a multiple of 128.
- * The caller zeroes its own row range and synchronises the ranks before the launch, synchronises them again after
- * it, and then owns the reduced rows (an all-gather completes the all-reduce).  tmaps_device: 128 * n_peers bytes
- * of device scratch, 128-byte aligned.  Workspace as for pgica_softmax_grad_gemm_dual.
+ * Dual softmax-gradient GEMM fused with the SCATTER half of the data-parallel all-reduce of out_y (the LM-head
+ * weight gradient) over the GPUs of an NVLink node: instead of writing out_y locally, every 128-row tile
+ * of out_y is stored (TMA, fp32) into THIS rank's slot in the memory of the rank that owns those rows — peer memory
+ * mapped into this process (e.g. torch symmetric memory).  Rank r owns rows [r * rows_per_owner, (r+1) *
+ * rows_per_owner), rows_per_owner a multiple of 128; out_y_peers_host[r] is the base of the fp32 [rows_per_owner][k]
+ * slot that rank r reserves for the caller's tiles (HOST array of n_peers <= 16 device pointers).  After the launch
+ * and a barrier across the ranks every owner sums its n_peers slots (pgica_sum_into_f32) and holds the reduced rows;
+ * an all-gather completes the all-reduce.  x must fit one chunk of the kernel (<= ~32 row blocks at k = 1024), else
+ * PGICA_ERR_INVALID_ARGUMENT.  tmaps_device: 128 * n_peers bytes of device scratch, 128-byte aligned.  Workspace as
+ * for pgica_softmax_grad_gemm_dual.
  * ---------------------------------------------------------------------------------------------- */
 int pgica_softmax_grad_gemm_dual_scatter(const void* x, const void* y, int64_t mx, int64_t my, int64_t k, float scale,
                                          const float* r_lse, const float* r_coef, const int32_t* r_tgt,
@@ -174,9 +175,9 @@ int pgica_lmhead_logprob_bwd(const void* hidden, const void* weight, const int32
                              int64_t seqlen, int64_t d, int64_t vocab, int length_normalize, void* dhidden,
                              int dhidden_is_bf16, void* dweight, int dweight_is_bf16, void* workspace,
                              size_t workspace_bytes, void* stream);
-/* pgica_lmhead_logprob_bwd with the weight gradient reduce-scattered over the node's GPUs inside the kernel (see
- * pgica_softmax_grad_gemm_dual_scatter): dhidden is written locally, dweight tiles are added into their owners'
- * buffers.  workspace: pgica_lmhead_logprob_workspace_bytes() bytes. */
+/* pgica_lmhead_logprob_bwd with the weight gradient scattered to its owners inside the kernel (see
+ * pgica_softmax_grad_gemm_dual_scatter): dhidden is written locally, dweight tiles are stored into the caller's
+ * slots at their owners.  workspace: pgica_lmhead_logprob_workspace_bytes() bytes. */
 int pgica_lmhead_logprob_bwd_scatter(const void* hidden, const void* weight, const int32_t* row_label,
                                      const float* row_weight, const float* lse, const float* grad_seq, int64_t nseq,
                                      int64_t seqlen, int64_t d, int64_t vocab, int length_normalize, void* dhidden,

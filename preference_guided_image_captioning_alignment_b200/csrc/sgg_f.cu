@@ -108,7 +108,7 @@ struct SggfParams {
   const int* c_tgt;
   void* out_x;
   void* out_y;
-  const CUtensorMap* oy_maps;  // reduce-scatter mode: one fp32 map per owner rank's OutY buffer (device array), else null
+  const CUtensorMap* oy_maps;  // scatter mode: one fp32 map per owner rank's slot for THIS rank's tiles (device array), else null
   int own_blocks;              // ... column tiles (128 rows of OutY) per owner
   uint32_t* ready;        // [2*nP*D*2] use count + 1 of the tile that is complete in the slot
   uint32_t* done;         // [2*nP*D*2] consumers that have pulled a tile out of the slot, ever
@@ -695,10 +695,11 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
         [&](int period, int chunk, int pass) {
           const int blk = 2 * (is_y ? pass * p.C2 + hidx : chunk * p.R2 + hidx) + (int)rho;
           const bool bf16 = (is_y ? p.outy_bf16 : p.outx_bf16) != 0;
-          // reduce-scatter mode: OutY tiles are ADDED into the buffer of the rank that owns their rows (peer memory over
-          // NVLink, zeroed by the owner beforehand), from every chunk of every rank
+          // scatter mode: an OutY tile is STORED into this rank's slot in the memory of the rank that owns its rows (peer
+          // memory over NVLink; plain stores — remote add-reductions run an order of magnitude slower); the owner sums
+          // the slots afterwards.  One chunk only (the planner is pinned), so nothing is ever accumulated remotely.
           const bool scatter = is_y && p.oy_maps != nullptr;
-          const bool accumulate = scatter || (is_y && chunk > 0);
+          const bool accumulate = !scatter && is_y && chunk > 0;
           LAP(0);
           mbar_wait(outfull_bar, (uint32_t)period & 1u);
           LAP(1);
@@ -707,10 +708,16 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
           // accumulated over chunks): full 128-byte lines instead of 32 scattered 16-byte stores per instruction, and
           // the rows past the end of the matrix are clipped by the tensor map.  One box = 32 rows x 128 bytes:
           // 32 fp32 columns, or 64 bf16 columns.
-          const CUtensorMap* tm_o = scatter ? p.oy_maps + blk / p.own_blocks : is_y ? &tm_oy : &tm_ox;
+          const int owner = scatter ? blk / p.own_blocks : 0;
+          const CUtensorMap* tm_o = scatter ? p.oy_maps + owner : is_y ? &tm_oy : &tm_ox;
           uint8_t* stg = drain_stage + quarter * 8192;
-          const int row0 = blk * kBM + quarter * 32;
+          const int row0 = (blk - owner * p.own_blocks) * kBM + quarter * 32;  // row inside the owner's slot
           const int cols_per_box = bf16 ? 64 : 32;
+          // The stores of the previous period had a whole period to complete; waiting for them HERE (not at the end of
+          // their own drain) keeps a drain as short as its shared-memory traffic even when the destination is a peer
+          // GPU, and still orders a tile's plain store before the add-reduction a later chunk makes into it.
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+          __syncwarp();
 #pragma unroll 1
           for (int bx = 0; bx < kNC / cols_per_box; ++bx) {
             uint32_t rr[32];
@@ -745,12 +752,12 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
           }
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // written: a later chunk may add to it
-          __syncwarp();
           tc_fence_before_sync();
           mbar_arrive_cluster(outfree_bar, 0);  // tell the leader: this CTA's accumulator may be overwritten
           LAP(2);
         });
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the last period's stores are complete
+    __syncwarp();
     if (threadIdx.x == 128) LAP_FLUSH(10, 3);
   }
   tc_fence_before_sync();
@@ -883,11 +890,13 @@ int plan_and_launch(const void* x, const void* y, int64_t mx, int64_t my, int64_
   if (rc != PGICA_OK) return rc;
   const int S = p.S;
   // a bf16 OutY cannot be accumulated over chunks: all of X must then fit one chunk of X-holders
-  Plan pl = choose_plan(p.RB2, p.J2, (int)k, npairs, p.outy_bf16 != 0);
+  Plan pl = choose_plan(p.RB2, p.J2, (int)k, npairs, p.outy_bf16 != 0 || sc.n_peers > 0);
   plan_override(&pl, npairs, S);
   PGICA_REQUIRE(pl.R2 >= 1 && pl.nP >= 1, "softmax_grad_gemm_dual: no role split of %d CTA pairs fits %d row blocks%s",
                 npairs, 2 * p.RB2, p.outy_bf16 ? " in one chunk (bf16 OutY)" : "");
-  PGICA_REQUIRE(!(p.outy_bf16 && p.RB2 > pl.R2), "softmax_grad_gemm_dual: a bf16 OutY cannot be accumulated over chunks");
+  PGICA_REQUIRE(!((p.outy_bf16 || sc.n_peers > 0) && p.RB2 > pl.R2),
+                "softmax_grad_gemm_dual: a bf16 or scattered OutY cannot be accumulated over chunks (x has %d row blocks)",
+                2 * p.RB2);
   p.R2 = pl.R2;
   p.C2 = pl.C2;
   p.nH = pl.nH;
@@ -925,7 +934,9 @@ int plan_and_launch(const void* x, const void* y, int64_t mx, int64_t my, int64_
     // source synchronously, so the host array may die when this function returns)
     CUtensorMap maps[16];
     for (int r = 0; r < sc.n_peers; ++r) {
-      rc = make_tmap_f32(&maps[r], sc.peers_host[r], my, k, k, 32);
+      int64_t rows_r = my - r * sc.rows_per_owner;  // valid rows of owner r (the map clips the rest)
+      rows_r = rows_r < 1 ? 1 : rows_r > sc.rows_per_owner ? sc.rows_per_owner : rows_r;
+      rc = make_tmap_f32(&maps[r], sc.peers_host[r], rows_r, k, k, 32);
       if (rc != PGICA_OK) return rc;
     }
     PGICA_CUDA_OK(cudaMemcpyAsync(sc.tmaps_device, maps, sizeof(CUtensorMap) * sc.n_peers, cudaMemcpyHostToDevice, st));

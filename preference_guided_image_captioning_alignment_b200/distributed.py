@@ -226,16 +226,22 @@ class PeerAllReduce:
 
 
 class FusedDWReduce:
-    """Data-parallel sum of the LM-head weight gradient with the REDUCE-SCATTER done by the backward kernel itself.
+    """Data-parallel sum of the LM-head weight gradient with the SCATTER done by the backward kernel itself.
 
     The dual backward kernel (csrc/sgg_f.cu) keeps 128-row tiles of dW resident in TMEM; in scatter mode it drains
-    every finished tile with a TMA add-reduction straight into the buffer of the rank that owns those rows — peer
-    memory over NVLink / NVSwitch, mapped through torch symmetric memory.  When the kernels of all ranks have ended,
-    rank r holds the fully reduced rows [r * own, (r+1) * own); the all-gather that completes the all-reduce is W-1
-    peer copies of 1/W of the buffer on the copy engines.  Per GPU the kernel sends (W-1)/W of dW spread over its
-    whole run time (~0.2 TB/s at W=8, a fraction of NVLink), and only the all-gather is exposed:
+    every finished tile with a TMA store straight into this rank's slot in the memory of the rank that OWNS those rows
+    — peer memory over NVLink / NVSwitch, mapped through torch symmetric memory — while the tensor cores are already
+    on the next tiles.  When the kernels of all ranks have ended, rank r holds W partial copies of its rows
+    [r * own, (r+1) * own), sums them (pgica_sum_into_f32, HBM-bound, 1/W of dW), and the all-gather that completes
+    the all-reduce is W-1 peer copies of 1/W of the buffer on the copy engines:
 
-        zero my rows -> barrier -> backward kernel (dH local, dW tiles -> owners) -> barrier -> push my rows -> barrier
+        barrier -> backward kernel (dH local, dW tiles -> owners' slots) -> barrier -> sum my slots
+                -> push my rows to every peer -> barrier
+
+    Per GPU the kernel sends (W-1)/W of dW spread over its whole run time (~0.2 TB/s at W=8, a fraction of NVLink)
+    and only the sum and the all-gather are exposed.  (Remote TMA add-reductions instead of per-source slots were
+    measured an order of magnitude slower: 2.5 ms instead of 1.0 ms for the kernel at W=8.)  Needs a problem whose
+    rows fit one chunk of the kernel (<= 32 row blocks at d = 1024); larger ones accumulate dW locally and all-reduce.
 
     `backward(...)` returns (dhidden, dweight_view); dweight_view is this rank's copy of the reduced (V, d) fp32
     gradient inside the symmetric buffer, valid on the current stream when the call returns."""
@@ -248,15 +254,22 @@ class FusedDWReduce:
         blocks = (self.vocab + 127) // 128
         self.own_rows = 128 * ((blocks + self.world - 1) // self.world)
         self.rows = self.own_rows * self.world
-        self.buf = symm.empty(self.rows * self.d, dtype=torch.float32, device=device)
+        n_own = self.own_rows * self.d
+        # one symmetric allocation: [reduced gradient: rows x d][slots: world x own_rows x d]
+        self.buf = symm.empty(self.rows * self.d + self.world * n_own, dtype=torch.float32, device=device)
         self.hdl = symm.rendezvous(self.buf, self.group)
-        self.peers = [self.hdl.get_buffer(p, (self.rows, self.d), torch.float32) for p in range(self.world)]
-        self.peer_ptrs = [t.data_ptr() for t in self.peers]
-        self.tmaps = torch.empty(128 * self.world + 128, dtype=torch.uint8, device=device)
-        off = (-self.tmaps.data_ptr()) % 128
-        self.tmaps = self.tmaps[off: off + 128 * self.world]
-        self.local = self.peers[self.rank]
-        self.local.zero_()
+        total = self.buf.numel()
+        flat = [self.hdl.get_buffer(p, (total,), torch.float32) for p in range(self.world)]
+        self.out_peers = [f[: self.rows * self.d].view(self.rows, self.d) for f in flat]
+        self.local = self.out_peers[self.rank]
+        self.slots = flat[self.rank][self.rows * self.d:].view(self.world, self.own_rows, self.d)
+        # where rank p keeps the slot for MY tiles
+        base = self.rows * self.d + self.rank * n_own
+        self.peer_ptrs = [f[base: base + n_own].data_ptr() for f in flat]
+        raw = torch.empty(128 * self.world + 128, dtype=torch.uint8, device=device)
+        off = (-raw.data_ptr()) % 128
+        self.tmaps = raw[off: off + 128 * self.world]
+        self.buf.zero_()
 
     @property
     def view(self):
@@ -265,13 +278,15 @@ class FusedDWReduce:
     def backward(self, hidden, weight, row_label, row_weight, lse, grad_seq, length_normalize=False,
                  dhidden_dtype=torch.bfloat16):
         lo, hi = self.rank * self.own_rows, (self.rank + 1) * self.own_rows
-        self.local[lo:hi].zero_()
-        self.hdl.barrier(channel=0)  # every owner's rows are zero; last step's all-gather has been consumed
+        self.hdl.barrier(channel=0)  # every owner has summed last step's slots: they may be overwritten
         dh = F.lmhead_logprob_bwd_scatter(hidden, weight, row_label, row_weight, lse, grad_seq, self.peer_ptrs,
                                           self.own_rows, self.tmaps, length_normalize, dhidden_dtype)
-        self.hdl.barrier(channel=1)  # every rank's tiles have been added: my rows are final
+        self.hdl.barrier(channel=1)  # every rank's tiles have landed in my slots
+        mine = self.local[lo:hi]
+        mine.zero_()
+        F.sum_into(mine, [self.slots[s] for s in range(self.world)])
         for p in range(self.world):
             if p != self.rank:
-                self.peers[p][lo:hi].copy_(self.local[lo:hi])
+                self.out_peers[p][lo:hi].copy_(mine)
         self.hdl.barrier(channel=2)  # everybody's rows have arrived here
         return dh, self.view
