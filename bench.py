@@ -416,6 +416,8 @@ def run_ours(args, rank, world, local_rank):
                        "pairs_per_s": Bg / (t.item() * 1e-3), "algorithmic_tflops": 6.0 * Bg * Bg * 512 / t.item() / 1e9,
                        "loss": nt_loss.item(),
                        "collectives": "all-gather of text rows, all-gather of column-LSE partials, reduce-scatter of dB"}
+    # ------------------------------------------------------------------ BASELINE config 4, this GPU's share
+    cfg4 = cfg4_extra(torch, dist, F, dev, rank, world, W, Wr, barrier)
     if rank != 0:
         return
     pk = peaks()
@@ -469,8 +471,53 @@ def run_ours(args, rank, world, local_rank):
         "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cpu_threads, "kind": "port",
                          "sample": f"2 steps of 4 pairs (of 16; linear in pairs), fp32 torch ops, {cpu_model_name()}"},
         "ntxent": extras,
+        "cfg4": cfg4,
     }
     emit(line)
+
+
+def cfg4_extra(torch, dist, F, dev, rank, world, W, Wr, barrier):
+    """BASELINE config 4 (seq 512, 256 preference pairs over 8 GPUs = 32 pairs per GPU, policy + frozen reference):
+    the same resident step as the headline, 32 pairs per GPU at every N, dW all-reduced with NCCL when N > 1."""
+    B, T, d, V, beta = 32, 512, CFG["d"], CFG["vocab"], CFG["beta"]
+    gen = torch.Generator().manual_seed(4321 + rank)
+    H = torch.randn(2 * B, T, d, generator=gen).to(torch.bfloat16).to(dev)
+    Hr = torch.randn(2 * B, T, d, generator=gen).to(torch.bfloat16).to(dev)
+    y = torch.randint(0, V, (2 * B, T), generator=gen).to(dev)
+    m = torch.ones(2 * B, T, dtype=torch.long, device=dev)
+    one = torch.ones((), device=dev)
+
+    def step():
+        seq_p, lse_p, _, rl, rw, _ = F.lmhead_logprob_fwd(H, W, y, m, False)
+        seq_r = F.lmhead_logprob_fwd(Hr, Wr, y, m, False)[0]
+        loss, metrics, dpc = F.dpo_loss_fwd(seq_p[:B], seq_p[B:], seq_r[:B], seq_r[B:], beta, 0.0, B * world)
+        gseq = F.dpo_grad_seq(dpc, one)
+        dh, dw = F.lmhead_logprob_bwd(H, W, rl, rw, lse_p, gseq, False)
+        if world > 1:
+            dist.all_reduce(dw)
+            dist.all_reduce(torch.cat([loss.reshape(1), metrics]))
+        return loss
+
+    for _ in range(3):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 5
+    e0.record()
+    for _ in range(iters):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / iters
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    tokens = B * (T - 1) * world
+    return {"workload": f"cfg4: seq 512, {B} pairs per GPU ({B * world} global), policy fwd+bwd + reference fwd"
+                        + (", NCCL fp32 all-reduce of dW" if world > 1 else ""),
+            "ms_per_step": ms, "pair_tokens_per_s": tokens / (ms * 1e-3),
+            "algorithmic_tflops_per_gpu": 16.0 * d * V * B * (T - 1) / ms / 1e9}
 
 
 def ntxent_extras(torch, F, dev):

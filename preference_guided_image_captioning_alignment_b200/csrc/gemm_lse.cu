@@ -1,12 +1,18 @@
 // K1/K3: z = scale * A B^T on tcgen05 tensor cores with the softmax statistics taken straight out of
 // TMEM — running max / sum-of-exp per row and the target logit — so the (rows x cols) logit matrix is
-// never written anywhere.  Persistent, warp-specialised:
-//   warp 0      TMA producer (A tile 128x64, B tile 256x64 per k-step, SWIZZLE_128B, 4-stage ring)
-//   warp 1      tcgen05.mma issuer (one elected thread), accumulators 128x256 fp32, double-buffered in TMEM
+// never written anywhere.  Persistent CTA PAIRS (2-CTA clusters, tcgen05 cta_group::2): a pair owns a 256-row x
+// 256-column tile, CTA rho holds the accumulator of row block 2mp + rho and loads only ITS half of the B tile —
+// 32 KB per k-step and SM instead of 48 KB, which is what the tensor pipe was waiting for in the single-CTA form
+// (shared-memory fill + operand reads exceeded the SM's shared-memory bandwidth).  Warp-specialised:
+//   warp 0      TMA producer (A tile 128x64, B half tile 128x64 per k-step, SWIZZLE_128B, 6-stage ring; completion
+//               bytes of both CTAs are credited to the leader's barrier)
+//   warp 1      tcgen05.mma issuer (one elected thread of the LEADER CTA), M = 256, N = 256; accumulators 128x256 fp32
+//               per CTA, double-buffered in TMEM; commits multicast to both CTAs' barriers
 //   warp 2      TMEM allocator
-//   warps 4..7  epilogue: tcgen05.ld 32 columns at a time, online log-sum-exp in the log2 domain
-// Tiles are linearised column-tile-major (all row blocks of column tile 0, then of column tile 1, ...) and dealt
-// round-robin to the persistent CTAs, so at any moment the whole grid works on the same four or five B tiles:
+//   warps 4..7  epilogue (each CTA its own 128 rows): tcgen05.ld 32 columns at a time, online log-sum-exp in the
+//               log2 domain
+// Tiles are linearised column-tile-major (all row-block pairs of column tile 0, then of column tile 1, ...) and dealt
+// round-robin to the persistent pairs, so at any moment the whole grid works on the same four or five B tiles:
 // B (the 103 MB LM-head weight) is then read from HBM once instead of once per row block.  Every tile writes its
 // rows' (max, sum, target) as a partial; lse_merge_kernel folds the column tiles of a row (deterministic, no atomics).
 #include "common.h"
@@ -20,10 +26,10 @@ constexpr int kBlockM = 128;
 constexpr int kBlockN = 256;
 constexpr int kBlockK = 64;
 constexpr int kUmmaK = 16;
-constexpr int kStages = 4;
+constexpr int kStages = 7;
 constexpr int kAccStages = 2;
 constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
-constexpr uint32_t kBBytes = kBlockN * kBlockK * 2;
+constexpr uint32_t kBBytes = (kBlockN / 2) * kBlockK * 2;  // this CTA's half of the B tile
 constexpr int kThreads = 256;
 constexpr int kEpilogueWarp0 = 4;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -31,7 +37,7 @@ constexpr float kLn2 = 0.6931471805599453f;
 
 struct GemmLseParams {
   int rows, cols, k;
-  int num_m_blocks, num_n_tiles, rows_pad;
+  int num_m_blocks, num_m_pairs, num_n_tiles, rows_pad;
   float scale;
   const int* labels;
   int diag_offset;
@@ -40,6 +46,28 @@ struct GemmLseParams {
   float* part_tgt;  // [num_n_tiles][rows_pad]  scale*z at the label column, -inf if it is not in this tile
   float* z_out;     // optional dense [rows][cols] copy of scale*z (similarity-matrix API only)
 };
+
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tmap, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
 
 constexpr size_t kSmemBytes = 1024 /*align slack*/ + kStages * (kABytes + kBBytes) + 256 /*barriers*/;
 
@@ -58,8 +86,9 @@ gemm_lse_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.num_m_blocks * p.num_n_tiles;
-  const int t_begin = blockIdx.x, t_step = gridDim.x, t_end = total_tiles;
+  const uint32_t rho = cluster_ctarank();  // 0 = leader of the pair
+  const int total_tiles = p.num_m_pairs * p.num_n_tiles;
+  const int t_begin = (int)blockIdx.x >> 1, t_step = (int)gridDim.x >> 1, t_end = total_tiles;
   const int num_kb = (p.k + kBlockK - 1) / kBlockK;
 
   if (warp == 0 && lane == 0) {
@@ -73,13 +102,19 @@ gemm_lse_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     }
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], 256);  // leader's: the epilogue threads of both CTAs
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<kAccStages * kBlockN>(tmem_slot);
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kAccStages * kBlockN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
   tc_fence_before_sync();
   __syncthreads();
+  cluster_sync_all();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -87,15 +122,17 @@ gemm_lse_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     // TMA producer: the whole warp walks the tile schedule, one elected lane issues the copies
     int stage = 0;
     uint32_t phase = 0;
+    const uint32_t lbar0 = mapa_u32(smem_u32(&full_bar[0]), 0);  // the leader's full barriers (shared::cluster)
     for (int t = t_begin; t < t_end; t += t_step) {
-      const int n_tile = t / p.num_m_blocks;
-      const int m_blk = t - n_tile * p.num_m_blocks;
+      const int n_tile = t / p.num_m_pairs;
+      const int m_blk = 2 * (t - n_tile * p.num_m_pairs) + (int)rho;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
-          mbar_expect_tx(&full_bar[stage], kABytes + kBBytes);
-          tma_load_2d(smem_a + stage * kABytes, &tm_a, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
-          tma_load_2d(smem_b + stage * kBBytes, &tm_b, &full_bar[stage], kb * kBlockK, n_tile * kBlockN);
+          if (rho == 0) mbar_expect_tx(&full_bar[stage], 2 * (kABytes + kBBytes));  // both CTAs' bytes
+          const uint32_t lbar = lbar0 + stage * 8;
+          tma_load_2d_pair(smem_a + stage * kABytes, &tm_a, lbar, kb * kBlockK, m_blk * kBlockM);
+          tma_load_2d_pair(smem_b + stage * kBBytes, &tm_b, lbar, kb * kBlockK, n_tile * kBlockN + (int)rho * (kBlockN / 2));
         }
         __syncwarp();
         if (++stage == kStages) {
@@ -104,28 +141,28 @@ gemm_lse_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && rho == 0) {
     // Whole warp walks the pipeline (warp-uniform control flow keeps descriptors in uniform registers); one elected
-    // lane issues the tcgen05 instructions.
-    constexpr uint32_t idesc = make_idesc_bf16(kBlockM, kBlockN, 0, 0);
+    // lane of the leader CTA issues the tcgen05 instructions for the pair.
+    constexpr uint32_t idesc = make_idesc_bf16(2 * kBlockM, kBlockN, 0, 0);
     const uint64_t desc_hi = make_smem_desc(0, 16, 1024);  // everything but the start address
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
     for (int t = t_begin; t < t_end; t += t_step) {
-      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      mbar_wait_cluster(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + acc * kBlockN;
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+        mbar_wait_cluster(&full_bar[stage], phase);
         tc_fence_after_sync();
         if (elect_one()) {
           const uint64_t da = desc_hi | ((smem_u32(smem_a + stage * kABytes) >> 4) & 0x3FFF);
           const uint64_t db = desc_hi | ((smem_u32(smem_b + stage * kBBytes) >> 4) & 0x3FFF);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k)
-            umma_bf16_ss(d_tmem, da + k * (kUmmaK * 2 / 16), db + k * (kUmmaK * 2 / 16), idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);
-          if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
+            umma2_bf16_ss(d_tmem, da + k * (kUmmaK * 2 / 16), db + k * (kUmmaK * 2 / 16), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma2_commit_both(&empty_bar[stage]);
+          if (kb == num_kb - 1) umma2_commit_both(&tfull_bar[acc]);
         }
         __syncwarp();
         if (++stage == kStages) {
@@ -145,8 +182,8 @@ gemm_lse_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = t_begin; t < t_end; t += t_step) {
-      const int n_tile = t / p.num_m_blocks;
-      const int m_blk = t - n_tile * p.num_m_blocks;
+      const int n_tile = t / p.num_m_pairs;
+      const int m_blk = 2 * (t - n_tile * p.num_m_pairs) + (int)rho;  // may be one past the end (odd block count)
       const int row = m_blk * kBlockM + row_in_blk;
       float run_m = -INFINITY, run_s = 0.f, run_t = -INFINITY;
       int label = -1;
@@ -203,21 +240,26 @@ gemm_lse_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         }
       }
       tc_fence_before_sync();
-      mbar_arrive(&tempty_bar[acc]);
+      mbar_arrive_cluster(&tempty_bar[acc], 0);  // tell the leader: this CTA has read the accumulator
       if (++acc == kAccStages) {
         acc = 0;
         acc_phase ^= 1;
       }
-      const size_t o = static_cast<size_t>(n_tile) * p.rows_pad + m_blk * kBlockM + row_in_blk;
-      p.part_max[o] = run_m;
-      p.part_sum[o] = run_s;
-      p.part_tgt[o] = run_t;
+      if (m_blk < p.num_m_blocks) {
+        const size_t o = static_cast<size_t>(n_tile) * p.rows_pad + m_blk * kBlockM + row_in_blk;
+        p.part_max[o] = run_m;
+        p.part_sum[o] = run_s;
+        p.part_tgt[o] = run_t;
+      }
     }
   }
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<kAccStages * kBlockN>(tmem_base);
+  cluster_sync_all();  // the pair shares barriers and TMEM commits: nobody leaves early
+  if (warp == 2)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kAccStages * kBlockN)
+                 : "memory");
 }
 
 // Fold the column-tile partials of every row into lse (natural log) and the target logit.  A block handles 32 rows
@@ -274,12 +316,13 @@ int plan(int64_t rows, int64_t cols, int64_t k, GemmLseParams* p, int* grid, siz
   p->cols = (int)cols;
   p->k = (int)k;
   p->num_m_blocks = (int)ceil_div(rows, kBlockM);
+  p->num_m_pairs = (p->num_m_blocks + 1) / 2;
   p->num_n_tiles = (int)ceil_div(cols, kBlockN);
   p->rows_pad = p->num_m_blocks * kBlockM;
-  const int64_t total = (int64_t)p->num_m_blocks * p->num_n_tiles;
-  PGICA_REQUIRE(total < (1ll << 31), "gemm_lse: too many tiles");
-  const int sms = device_sm_count();
-  *grid = (int)(total < sms ? total : sms);
+  const int64_t total = (int64_t)p->num_m_pairs * p->num_n_tiles;  // 256 x 256 tiles, one CTA pair each
+  PGICA_REQUIRE(total < (1ll << 30), "gemm_lse: too many tiles");
+  const int pairs = device_sm_count() / 2;
+  *grid = 2 * (int)(total < pairs ? total : pairs);
   *ws_bytes = 3 * align_up((size_t)p->num_n_tiles * p->rows_pad * sizeof(float), 256);
   return PGICA_OK;
 }
@@ -324,13 +367,24 @@ static int gemm_lse_impl(const void* a, const void* b, int64_t rows, int64_t col
   CUtensorMap tm_a, tm_b;
   rc = make_tmap_bf16(&tm_a, a, rows, k, k, kBlockM);
   if (rc != PGICA_OK) return rc;
-  rc = make_tmap_bf16(&tm_b, b, cols, k, k, kBlockN);
+  rc = make_tmap_bf16(&tm_b, b, cols, k, k, kBlockN / 2);
   if (rc != PGICA_OK) return rc;
 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   PGICA_CUDA_OK(cudaFuncSetAttribute(gemm_lse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-  gemm_lse_kernel<<<grid, kThreads, kSmemBytes, st>>>(tm_a, tm_b, p);
-  PGICA_CUDA_OK(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PGICA_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_lse_kernel, tm_a, tm_b, p));
   count_launches(1);
   lse_merge_kernel<<<(unsigned)ceil_div(rows, kMergeRows), kMergeRows * kMergeGroups, 0, st>>>(p, lse, tgt);
   PGICA_CUDA_OK(cudaGetLastError());
