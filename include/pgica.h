@@ -122,6 +122,10 @@ int pgica_softmax_grad_gemm(const void* x, const void* y, int64_t mx, int64_t my
  * out_y must be fp32 when x has more row blocks than fit one chunk (it is then accumulated in place).
  * ---------------------------------------------------------------------------------------------- */
 int pgica_softmax_grad_gemm_dual_workspace_bytes(int64_t mx, int64_t my, int64_t k, size_t* bytes_host);
+/* The role split the kernel's planner picks when `npairs` CTA pairs are resident (74 on a B200): plan_host[0..4] =
+ * row pairs per chunk, column pairs per pass, X-holder pairs, Y-holder pairs, producer pairs.  Host arithmetic only. */
+int pgica_softmax_grad_gemm_dual_plan(int64_t mx, int64_t my, int64_t k, int npairs, int single_chunk,
+                                      int32_t* plan_host);
 int pgica_softmax_grad_gemm_dual(const void* x, const void* y, int64_t mx, int64_t my, int64_t k, float scale,
                                  const float* r_lse, const float* r_coef, const int32_t* r_tgt, const float* c_lse,
                                  const float* c_coef, const int32_t* c_tgt, void* out_x, int out_x_is_bf16,

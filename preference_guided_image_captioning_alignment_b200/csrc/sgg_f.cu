@@ -866,11 +866,22 @@ int launch(const CUtensorMap& tm_x128, const CUtensorMap& tm_y128, const CUtenso
   attr[1].id = cudaLaunchAttributeCooperative;  // all pairs co-resident or the launch fails: the roles wait on each other
   attr[1].val.cooperative = 1;
   cfg.attrs = attr;
-  // PGICA_SGGF_COOP=0 drops the attribute (Nsight Compute cannot replay a cooperative cluster launch); the grid never
-  // exceeds the resident-cluster count, so on an otherwise idle device all pairs are co-resident anyway
-  static const bool coop = !(getenv("PGICA_SGGF_COOP") && atoi(getenv("PGICA_SGGF_COOP")) == 0);
+  // The cooperative attribute is dropped with PGICA_SGGF_COOP=0, under Nsight Compute (which cannot replay a
+  // cooperative cluster launch) and when the cooperative launch is refused: the grid never exceeds the resident-
+  // cluster count, so on an otherwise idle device all pairs are co-resident anyway.
+  static const bool coop = !(getenv("PGICA_SGGF_COOP") && atoi(getenv("PGICA_SGGF_COOP")) == 0) &&
+                           !getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") && !getenv("CUDA_INJECTION64_PATH");
   cfg.numAttrs = coop ? 2 : 1;
-  PGICA_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tm_x128, tm_y128, tm_x64, tm_y64, tm_s, tm_ox, tm_oy, p));
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm_x128, tm_y128, tm_x64, tm_y64, tm_s, tm_ox, tm_oy, p);
+  if (e != cudaSuccess && coop) {
+    (void)cudaGetLastError();
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, tm_x128, tm_y128, tm_x64, tm_y64, tm_s, tm_ox, tm_oy, p);
+  }
+  if (e != cudaSuccess) {
+    set_error("softmax_grad_gemm_dual: launch failed: %s", cudaGetErrorString(e));
+    return PGICA_ERR_CUDA;
+  }
   count_launches(1);
   return PGICA_OK;
 }
@@ -968,6 +979,17 @@ bool sggf_single_chunk(int64_t mx, int64_t my, int64_t k) {
   return pl.R2 >= RB2 && pl.nP >= 1;
 }
 
+// Role split the planner picks for `npairs` resident CTA pairs (host arithmetic only; no device needed).
+void sggf_plan(int64_t mx, int64_t my, int64_t k, int npairs, int single_chunk, int out[5]) {
+  const int RB2 = (int)((ceil_div(mx, kBM) + 1) / 2), J2 = (int)((ceil_div(my, kBT) + 1) / 2);
+  const Plan pl = choose_plan(RB2, J2, (int)k, npairs, single_chunk != 0);
+  out[0] = pl.R2;
+  out[1] = pl.C2;
+  out[2] = pl.nH;
+  out[3] = pl.nW;
+  out[4] = pl.nP;
+}
+
 size_t sggf_workspace_bytes() {
   // exchange ring for the largest producer count (80 pairs) + flags
   const size_t nslots = (size_t)2 * 80 * kSlotsPerProducer * 2;
@@ -1028,6 +1050,19 @@ extern "C" int pgica_debug_set_sggf_trace(void* buf) {
   return cudaMemcpyToSymbol(pgica::g_sggf_trace, &p, sizeof(p)) == cudaSuccess ? 0 : -1;
 }
 #endif
+
+namespace pgica {
+void sggf_plan(int64_t mx, int64_t my, int64_t k, int npairs, int single_chunk, int out[5]);
+}
+extern "C" int pgica_softmax_grad_gemm_dual_plan(int64_t mx, int64_t my, int64_t k, int npairs, int single_chunk,
+                                                 int32_t* plan_host) {
+  PGICA_REQUIRE(plan_host && mx > 0 && my > 0 && k > 0 && k % 512 == 0 && k / 512 <= 4 && npairs >= 3,
+                "softmax_grad_gemm_dual_plan: bad argument");
+  int out[5];
+  pgica::sggf_plan(mx, my, k, npairs, single_chunk, out);
+  for (int i = 0; i < 5; ++i) plan_host[i] = out[i];
+  return PGICA_OK;
+}
 
 extern "C" int pgica_softmax_grad_gemm_dual_workspace_bytes(int64_t mx, int64_t my, int64_t k, size_t* bytes_host) {
   PGICA_REQUIRE(bytes_host, "workspace query: null result pointer");

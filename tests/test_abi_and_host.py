@@ -187,3 +187,29 @@ def test_shard_pairs():
         assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
         sizes = [b - a for a, b in spans]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_dual_backward_planner_host_side():
+    """pgica_softmax_grad_gemm_dual_plan is host arithmetic: the role split uses every resident CTA pair, respects the
+    TMEM capacity of the holders, and keeps X in one chunk when asked to (bf16 / scattered OutY)."""
+    import ctypes
+
+    from preference_guided_image_captioning_alignment_b200 import _lib
+    lib = _lib.load()
+    out = (ctypes.c_int32 * 5)()
+    for mx, my, k in ((4096, 50257, 1024), (32768, 50257, 1024), (64, 64, 512), (4096, 4096, 512), (32768, 32768, 512),
+                      (4096, 32768, 1536), (300, 1000, 2048)):
+        S = k // 512
+        rb2, j2 = ((mx + 127) // 128 + 1) // 2, ((my + 127) // 128 + 1) // 2
+        for npairs in (74, 66, 8):
+            for single in (0, 1):
+                assert lib.pgica_softmax_grad_gemm_dual_plan(mx, my, k, npairs, single, out) == 0
+                r2, c2, nh, nw, npr = list(out)
+                if npairs < 2 * S + 1 or (single and rb2 * S > npairs - S - 1):
+                    assert r2 == 0  # no split / not in one chunk: the caller falls back to one launch per product
+                    continue
+                assert nh == r2 * S and nw == c2 * S and nh + nw + npr == npairs and npr >= 1
+                assert 1 <= r2 <= rb2 and 1 <= c2 <= j2
+                if single:
+                    assert r2 == rb2
+    assert lib.pgica_softmax_grad_gemm_dual_plan(4096, 50257, 1000, 74, 0, out) != 0  # k must be a multiple of 512
