@@ -418,6 +418,7 @@ def run_ours(args, rank, world, local_rank):
                        "collectives": "all-gather of text rows, all-gather of column-LSE partials, reduce-scatter of dB"}
     # ------------------------------------------------------------------ BASELINE config 4, this GPU's share
     cfg4 = cfg4_extra(torch, dist, F, dev, rank, world, W, Wr, barrier)
+    gradclip = gradclip_extra(torch, F, dev) if rank == 0 else None
     if rank != 0:
         return
     pk = peaks()
@@ -472,6 +473,7 @@ def run_ours(args, rank, world, local_rank):
                          "sample": f"2 steps of 4 pairs (of 16; linear in pairs), fp32 torch ops, {cpu_model_name()}"},
         "ntxent": extras,
         "cfg4": cfg4,
+        "grad_norm_clip": gradclip,
     }
     emit(line)
 
@@ -518,6 +520,34 @@ def cfg4_extra(torch, dist, F, dev, rank, world, W, Wr, barrier):
                         + (", NCCL fp32 all-reduce of dW" if world > 1 else ""),
             "ms_per_step": ms, "pair_tokens_per_s": tokens / (ms * 1e-3),
             "algorithmic_tflops_per_gpu": 16.0 * d * V * B * (T - 1) / ms / 1e9}
+
+
+def gradclip_extra(torch, F, dev):
+    """finite check + global norm + clip over GPT-2-Medium-sized fp32 gradients (355 M elements in
+    the tensor shapes of the decoder: wte, 24 x {attn, mlp, ln}), HBM roofline: the norm pass reads every gradient
+    once, the clip pass reads and writes it."""
+    d, V, L = 1024, CFG["vocab"], 24
+    shapes = [(V, d), (1024, d)] + [s for _ in range(L) for s in ((d, 3 * d), (3 * d,), (d, d), (d,), (d, 4 * d),
+                                                                   (4 * d,), (4 * d, d), (d,), (d,), (d,), (d,), (d,))]
+    grads = [torch.randn(*s, device=dev) * 0.02 for s in shapes]
+    nbytes = sum(g.numel() * 4 for g in grads)
+    out = {"tensors": len(grads), "elements": nbytes // 4, "dtype": "f32"}
+    pk = peaks()
+    for name, max_norm, passes in (("norm_only", 1e9, 1), ("norm_and_clip", 1.0, 3)):
+        # max_norm halves on every call so that every call of the second variant really clips
+        for it in range(2):
+            F.grad_norm_clip(grads, max_norm * 0.5 ** it)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for it in range(2, 7):
+            F.grad_norm_clip(grads, max_norm * 0.5 ** it)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        out[name] = {"ms": ms, "algorithmic_bytes": passes * nbytes, "gb_per_s": passes * nbytes / ms / 1e6,
+                     "frac_of_hbm_peak": passes * nbytes / ms / 1e6 / pk["hbm"]}
+    return out
 
 
 def ntxent_extras(torch, F, dev):

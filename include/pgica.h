@@ -263,6 +263,21 @@ int pgica_logits_lse(const void* logits, int logits_is_bf16, const int32_t* row_
 int pgica_logits_grad(const void* logits, int logits_is_bf16, const int32_t* row_label, const float* lse,
                       const float* coef, int64_t nseq, int64_t seqlen, int64_t vocab, void* dlogits, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * SURVEY 8(f) row 2 — finite-check + global L2 gradient norm + clip over ALL gradient tensors at once:
+ * NaNSafeGradientNorm.forward (pkg/models/components.py:283-318) and the per-parameter isfinite() scan +
+ * clip_grad_norm_ of the trainer (pkg/training/trainer.py:494-515, 619-628).
+ *   grads_host[i]: device pointer of gradient i (fp32, or bf16 when is_bf16_host[i] != 0), numels_host[i] elements;
+ *   stats (device, 3 floats): total_norm, clip_coef = min(1, max_norm / (total_norm + 1e-6)), is_finite (1 / 0).
+ *   clip != 0: gradients are multiplied by clip_coef in place when the norm is finite and clip_coef < 1 (a non-finite
+ *   norm leaves them untouched, like the reference).  Three launches, no host synchronisation; deterministic.
+ * workspace: pgica_grad_norm_clip_workspace_bytes() bytes (chunk table + per-chunk partial sums).
+ * ---------------------------------------------------------------------------------------------- */
+int pgica_grad_norm_clip_workspace_bytes(const int64_t* numels_host, int n_tensors, size_t* bytes_host);
+int pgica_grad_norm_clip(const void* const* grads_host, const int64_t* numels_host, const int32_t* is_bf16_host,
+                         int n_tensors, float max_norm, int clip, float* stats, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

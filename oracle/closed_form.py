@@ -195,3 +195,16 @@ def dpo_head(hc, hr, W, yc, yr, mc=None, mr=None, ref=None, beta=0.1, length_nor
     gr = lmhead_sequence_logprobs(hr, W, yr, mr, length_normalize, grad_seq=head["d_pr"])
     return dict(loss=head["loss"], metrics=head["metrics"], pc=fc["seq_logp"], pr=fr["seq_logp"], rc=rc, rr=rr,
                 dhc=gc["dhidden"], dhr=gr["dhidden"], dW=gc["dweight"] + gr["dweight"])
+
+
+def grad_norm_clip(grads, max_norm):
+    """NaNSafeGradientNorm.forward (pkg/models/components.py:283-318) + torch.nn.utils.clip_grad_norm_ in float64:
+    total L2 norm over all gradients (norm of the per-tensor norms, :300-303), finite flag (:306), and the gradients
+    multiplied by min(1, max_norm / (total + 1e-6)) when finite, untouched otherwise (:308-315)."""
+    grads = [np.asarray(g, dtype=np.float64) for g in grads]
+    with np.errstate(over="ignore", invalid="ignore"):
+        total = float(np.sqrt(sum(float(np.sum(g * g)) for g in grads)))
+    finite = bool(np.isfinite(total))
+    coef = min(1.0, max_norm / (total + 1e-6)) if finite else 1.0
+    return {"total_norm": total, "is_finite": finite, "clip_coef": coef,
+            "clipped": [g * coef if finite else g.copy() for g in grads]}

@@ -14,12 +14,13 @@ Everything computes in hand-written CUDA (csrc/, exported through the C ABI in i
 CPU or PyTorch fallback: on a machine without a B200 the ops raise.
 """
 from . import _lib  # noqa: F401  (ctypes binding; the library itself is loaded on first use)
-from .components import (DPOPreferenceLoss, FusedDPOHead, TemperatureScaledSimilarity,  # noqa: F401
+from .components import (DPOPreferenceLoss, FusedDPOHead, NaNSafeGradientNorm, TemperatureScaledSimilarity,  # noqa: F401
                          compute_sequence_logprobs, lmhead_sequence_logprobs)
 from .graphs import GraphedDPOStep  # noqa: F401
 from .install import install, uninstall  # noqa: F401
 from .losses import ContrastiveLoss, LazyLogits, PreferenceLoss  # noqa: F401
 
 __all__ = ["ContrastiveLoss", "PreferenceLoss", "DPOPreferenceLoss", "FusedDPOHead", "TemperatureScaledSimilarity",
-           "compute_sequence_logprobs", "lmhead_sequence_logprobs", "LazyLogits", "GraphedDPOStep", "install",
+           "compute_sequence_logprobs", "lmhead_sequence_logprobs", "LazyLogits", "GraphedDPOStep", "NaNSafeGradientNorm",
+           "install",
            "uninstall"]

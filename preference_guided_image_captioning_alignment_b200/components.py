@@ -41,15 +41,45 @@ class TemperatureScaledSimilarity(nn.Module):
         return float(min(max(float(self.temperature), self.min_temp), self.max_temp))
 
     def forward(self, vision_embeds: torch.Tensor, text_embeds: torch.Tensor) -> torch.Tensor:
+        return _DenseSimilarity.apply(vision_embeds, text_embeds, self.temperature, self.min_temp, self.max_temp)
+
+
+class _DenseSimilarity(torch.autograd.Function):
+    """S = normalize(v) normalize(t)^T / clamp(tau) as a dense matrix, differentiable like the reference's module
+    (components.py:61-83).  Forward: `pgica_rownorm_fwd` + `pgica_similarity`.  Backward of a DENSE upstream gradient
+    is two plain GEMMs (dS t_hat, dS^T v_hat: library matmuls — there is no softmax to fuse and nothing to recompute)
+    followed by `pgica_rownorm_bwd`; d tau = -sum(dS * S) / tau inside the clamp range.  Training goes through
+    ContrastiveLoss, which never forms S; this path exists for callers that score with the matrix."""
+
+    @staticmethod
+    def forward(ctx, v, t, temperature, min_temp, max_temp):
         from . import functional as F
-        if torch.is_grad_enabled() and (vision_embeds.requires_grad or text_embeds.requires_grad
-                                        or self.temperature.requires_grad):
-            raise NotImplementedError(
-                "TemperatureScaledSimilarity returns the dense similarity matrix for scoring only; for training use "
-                "ContrastiveLoss, whose fused kernels never materialise it")
-        v, _ = ops.l2_normalize(vision_embeds, 1e-12)
-        t, _ = ops.l2_normalize(text_embeds, 1e-12)
-        return F.similarity(v, t, 1.0 / self.effective_temperature())
+        tau = float(temperature)
+        tau_eff = float(min(max(tau, min_temp), max_temp))
+        vn, vinv = ops.l2_normalize(v.detach(), 1e-12)
+        tn, tinv = ops.l2_normalize(t.detach(), 1e-12)
+        S = F.similarity(vn, tn, 1.0 / tau_eff)
+        ctx.save_for_backward(v, t, vn, tn, vinv, tinv, S)
+        ctx.tau_eff = tau_eff
+        ctx.tau_inside = min_temp < tau < max_temp  # clamp passes the gradient only strictly inside its range
+        ctx.temp_dtype = temperature.dtype
+        return S
+
+    @staticmethod
+    def backward(ctx, dS):
+        v, t, vn, tn, vinv, tinv, S = ctx.saved_tensors
+        dS = dS.float().contiguous()
+        dv = dt = dtau = None
+        if ctx.needs_input_grad[0]:
+            dvn = torch.matmul(dS, tn.float()) / ctx.tau_eff
+            dv = ops.l2_normalize_bwd(v.detach(), vinv, dvn.contiguous()).to(v.dtype)
+        if ctx.needs_input_grad[1]:
+            dtn = torch.matmul(dS.t(), vn.float()) / ctx.tau_eff
+            dt = ops.l2_normalize_bwd(t.detach(), tinv, dtn.contiguous()).to(t.dtype)
+        if ctx.needs_input_grad[2]:
+            dtau = (-(dS * S).sum() / ctx.tau_eff if ctx.tau_inside else torch.zeros((), device=dS.device))
+            dtau = dtau.to(ctx.temp_dtype)
+        return dv, dt, dtau, None, None
 
 
 class ContrastiveLoss(nn.Module):
@@ -168,3 +198,31 @@ class FusedDPOHead(nn.Module):
                     rc = lmhead_sequence_logprobs(ref_hidden_chosen, ref_weight, labels_chosen, mask_chosen, ln)
                     rr = lmhead_sequence_logprobs(ref_hidden_rejected, ref_weight, labels_rejected, mask_rejected, ln)
         return self.loss.forward_tensors(pc, pr, rc, rr, n_global)
+
+
+class NaNSafeGradientNorm(nn.Module):
+    """Gradient clipping with the non-finite check folded in (components.py:252-318), one multi-tensor pass on the GPU:
+    `forward(parameters) -> (total_norm, is_finite)`; gradients are clipped in place to `max_norm` when the norm is
+    finite, left untouched (and `is_finite` False) otherwise.  Replaces, in one call, the per-parameter
+    `torch.isfinite(p.grad).all()` scan and `clip_grad_norm_` of the trainer (trainer.py:494-515, 619-628).
+    Only the L2 norm (the reference's default and the trainer's choice) is implemented on the device."""
+
+    def __init__(self, max_norm: float = 1.0, norm_type: float = 2.0, error_if_nonfinite: bool = False):
+        super().__init__()
+        if float(norm_type) != 2.0:
+            raise ValueError("NaNSafeGradientNorm: only norm_type=2.0 is implemented by the fused kernel")
+        self.max_norm = max_norm
+        self.norm_type = norm_type
+        self.error_if_nonfinite = error_if_nonfinite
+
+    def forward(self, parameters) -> Tuple[torch.Tensor, bool]:
+        from . import functional as F
+        grads = [p.grad for p in parameters if p.grad is not None]
+        if len(grads) == 0:
+            return torch.tensor(0.0), True
+        stats = F.grad_norm_clip(grads, self.max_norm, clip=True)
+        total_norm = stats[0]
+        is_finite = bool(stats[2].item() != 0.0)  # the one host read the reference makes too (components.py:307)
+        if not is_finite and self.error_if_nonfinite:
+            raise RuntimeError("Non-finite gradient norm detected")
+        return total_norm, is_finite

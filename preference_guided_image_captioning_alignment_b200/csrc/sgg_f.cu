@@ -98,6 +98,7 @@ struct SggfParams {
   int RB2, J2;            // row-block pairs of X, column-tile pairs of Y
   int R2, C2, S;          // row pairs per chunk, column pairs per pass, 512-column splits of k
   int nH, nW, nP, D;      // PAIRS per role; exchange double-slots per producer CTA
+  int spread;             // 1: spread an X-holder's quads evenly over a pass (StepOffsets)
   int outx_bf16, outy_bf16;
   float c;                // scale * log2(e)
   const float* r_lse;
@@ -178,6 +179,28 @@ __device__ __forceinline__ void wait_flag_ge(const uint32_t* p, uint32_t v) {
   }
 }
 
+// Production order.  A pass covers Rc row pairs x Cc column pairs in Rc time steps; in step t column pair c meets row
+// pair (off(c) + t) mod Rc with off(c) = floor(c * Rc / Cc): every Y-holder consumes one quad per step, and the steps
+// in which a given X-holder is served are spread evenly over the pass (with off(c) = c they would come in one burst
+// of Cc consecutive steps, which the exchange ring would have to absorb).  StepOffsets walks off(c) for c = 0, 1, ...
+struct StepOffsets {
+  int off, acc, Rc, Cc;
+  int step;
+  __device__ StepOffsets(int rc, int cc, int spread) : off(0), acc(0), Rc(rc), Cc(cc), step(spread ? rc : cc) {}
+  __device__ void next() {
+    acc += step;
+    while (acc >= Cc) {
+      acc -= Cc;
+      ++off;
+    }
+  }
+  __device__ int row(int t) const {  // (off + t) mod Rc; off may reach Rc when Cc < Rc is false, hence the loop
+    int r = off + t;
+    while (r >= Rc) r -= Rc;
+    return r;
+  }
+};
+
 // Visits every quad in production order.  f(q, r0, r, c0, c): sequence number q; the quad covers row pair r0 + r
 // (row blocks 2(r0+r), 2(r0+r)+1) and column pair c0 + c.
 template <class F>
@@ -188,10 +211,10 @@ __device__ __forceinline__ void for_each_quad(const SggfParams& p, F&& f) {
     for (int c0 = 0; c0 < p.J2; c0 += p.C2) {
       const int Cc = min(p.C2, p.J2 - c0);
       for (int t = 0; t < Rc; ++t) {
-        int r = t % Rc;
+        StepOffsets so(Rc, Cc, p.spread);
         for (int c = 0; c < Cc; ++c, ++q) {
-          f(q, r0, r, c0, c);
-          if (++r == Rc) r = 0;
+          f(q, r0, so.row(t), c0, c);
+          so.next();
         }
       }
     }
@@ -213,25 +236,28 @@ __device__ __forceinline__ void for_each_holder_tile(const SggfParams& p, bool i
       const int Cc = min(p.C2, p.J2 - c0);
       if (is_y) {
         if (idx < Cc) {
-          int r = idx % Rc;
+          StepOffsets so(Rc, Cc, p.spread);
+          for (int c = 0; c < idx; ++c) so.next();
           for (int t = 0; t < Rc; ++t) {
             const int q = qbase + t * Cc + idx;
+            const int r = so.row(t);
             f(q, 0, r0 + r, c0 + idx, t == 0, period);
             f(q, 1, r0 + r, c0 + idx, false, period);
-            if (++r == Rc) r = 0;
           }
           g(period, chunk, pass);
           ++period;
         }
       } else if (idx < Rc) {
         for (int t = 0; t < Rc; ++t) {
-          int c = idx - t;  // column pairs c with (c + t) mod Rc == idx, increasing
-          if (c < 0) c += Rc;
-          for (; c < Cc; c += Rc) {
-            const int q = qbase + t * Cc + c;
-            f(q, 0, r0 + idx, c0 + c, first, period);
-            first = false;
-            f(q, 1, r0 + idx, c0 + c, false, period);
+          StepOffsets so(Rc, Cc, p.spread);
+          for (int c = 0; c < Cc; ++c) {  // column pairs that meet this row pair in step t, increasing
+            if (so.row(t) == idx) {
+              const int q = qbase + t * Cc + c;
+              f(q, 0, r0 + idx, c0 + c, first, period);
+              first = false;
+              f(q, 1, r0 + idx, c0 + c, false, period);
+            }
+            so.next();
           }
         }
       }
@@ -914,6 +940,11 @@ int plan_and_launch(const void* x, const void* y, int64_t mx, int64_t my, int64_
   p.nW = pl.nW;
   p.nP = pl.nP;
   p.D = kSlotsPerProducer;
+  p.spread = (getenv("PGICA_SGGF_SPREAD") && atoi(getenv("PGICA_SGGF_SPREAD")) != 0) ? 1 : 0;
+  if (const char* e = getenv("PGICA_SGGF_SLOTS")) {  // tuning: exchange double-slots per producer CTA (<= the reserved 4 x 2)
+    const int v = atoi(e);
+    if (v >= 1 && v <= 2 * kSlotsPerProducer) p.D = v;
+  }
   const size_t nslots = (size_t)2 * p.nP * p.D * 2;
   const size_t ring_bytes = nslots * kPBytes;
   const size_t flag_bytes = align_up(nslots * sizeof(uint32_t), 256);
@@ -991,8 +1022,8 @@ void sggf_plan(int64_t mx, int64_t my, int64_t k, int npairs, int single_chunk, 
 }
 
 size_t sggf_workspace_bytes() {
-  // exchange ring for the largest producer count (80 pairs) + flags
-  const size_t nslots = (size_t)2 * 80 * kSlotsPerProducer * 2;
+  // exchange ring for the largest producer count (80 pairs, twice the default depth for tuning) + flags
+  const size_t nslots = (size_t)2 * 80 * 2 * kSlotsPerProducer * 2;
   return nslots * (size_t)kPBytes + 2 * align_up(nslots * sizeof(uint32_t), 256);
 }
 

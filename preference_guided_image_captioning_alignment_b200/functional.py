@@ -382,3 +382,28 @@ def logits_grad(logits, row_label, lse, coef):
     _lib.check(lib.pgica_logits_grad(_p(logits), 1 if logits.dtype == torch.bfloat16 else 0, _p(row_label), _p(lse),
                                      _p(coef), nseq, T, V, _p(dlogits), _stream()))
     return dlogits
+
+
+# ----------------------------------------------------------------------------------------- SURVEY 8(f) row 2
+def grad_norm_clip(grads, max_norm, clip=True):
+    """Global L2 norm of a list of gradient tensors (fp32 / bf16, contiguous), finite check and in-place clip in three
+    launches (pgica_grad_norm_clip).  Returns a (3,) fp32 device tensor: total_norm, clip_coef, is_finite."""
+    grads = [g for g in grads if g is not None and g.numel() > 0]
+    if not grads:
+        raise ValueError("grad_norm_clip: no gradients")
+    _need_cuda(*grads)
+    for g in grads:
+        if g.dtype not in (torch.float32, torch.bfloat16) or not g.is_contiguous():
+            raise ValueError("grad_norm_clip: gradients must be contiguous fp32 or bf16 tensors")
+    lib = _lib.load()
+    n = len(grads)
+    ptrs = (ctypes.c_void_p * n)(*[g.data_ptr() for g in grads])
+    numels = (ctypes.c_int64 * n)(*[g.numel() for g in grads])
+    kinds = (ctypes.c_int32 * n)(*[1 if g.dtype == torch.bfloat16 else 0 for g in grads])
+    need = ctypes.c_size_t(0)
+    _lib.check(lib.pgica_grad_norm_clip_workspace_bytes(numels, n, ctypes.byref(need)))
+    ws = _ws(need.value, grads[0].device)
+    stats = torch.empty(3, dtype=torch.float32, device=grads[0].device)
+    _lib.check(lib.pgica_grad_norm_clip(ptrs, numels, kinds, n, float(max_norm), 1 if clip else 0, _p(stats), _p(ws),
+                                        ws.numel(), _stream()))
+    return stats

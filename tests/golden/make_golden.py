@@ -11,6 +11,7 @@ Reference code paths exercised (relative to the reference root, pkg/ = src/prefe
   pkg/models/components.py:321-362  compute_sequence_logprobs
   pkg/models/model.py:1003-1085     PreferenceLoss / _compute_log_probs
   pkg/models/components.py:148-249  DPOPreferenceLoss
+  pkg/models/components.py:252-318  NaNSafeGradientNorm
 """
 import os
 import sys
@@ -154,6 +155,40 @@ def make_dpo_head(comp):
     np.savez_compressed(os.path.join(HERE, "dpo_head.npz"), **out)
 
 
+def make_grad_clip(comp):
+    """pkg/models/components.py:252-318 NaNSafeGradientNorm on a handful of 'parameters' of odd sizes (fp32)."""
+    out = {}
+    g = torch.Generator().manual_seed(77)
+    shapes = [(3, 5), (1000,), (65, 33), (9001,), (8, 8, 8)]
+    for tag, scale, max_norm in (("clip", 1.0, 1.0), ("noclip", 1e-3, 1.0), ("big", 30.0, 0.5)):
+        params = []
+        for i, sh in enumerate(shapes):
+            p = torch.nn.Parameter(torch.zeros(*sh, dtype=torch.float32))
+            p.grad = (torch.randn(*sh, generator=g, dtype=torch.float32) * scale)
+            out[f"{tag}_g{i}"] = p.grad.numpy().copy()
+            params.append(p)
+        total, finite = comp.NaNSafeGradientNorm(max_norm=max_norm)(params)
+        out[f"{tag}_max_norm"] = np.float64(max_norm)
+        out[f"{tag}_total"] = np64(total)
+        out[f"{tag}_finite"] = np.int64(bool(finite))
+        for i, p in enumerate(params):
+            out[f"{tag}_c{i}"] = p.grad.numpy().copy()
+    # a non-finite gradient: reported, nothing clipped
+    params = []
+    for i, sh in enumerate(shapes[:2]):
+        p = torch.nn.Parameter(torch.zeros(*sh, dtype=torch.float32))
+        p.grad = torch.randn(*sh, generator=g, dtype=torch.float32) * 5
+        params.append(p)
+    params[1].grad[17] = float("nan")
+    for i, p in enumerate(params):
+        out[f"nan_g{i}"] = p.grad.numpy().copy()
+    total, finite = comp.NaNSafeGradientNorm(max_norm=1.0)(params)
+    out["nan_finite"] = np.int64(bool(finite))
+    for i, p in enumerate(params):
+        out[f"nan_c{i}"] = p.grad.numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "grad_clip.npz"), **out)
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit("reference not found at " + ref_loader.REFERENCE_ROOT)
@@ -163,6 +198,7 @@ def main():
     make_seq_logprobs(comp, TrainerPL)
     make_dpo(comp)
     make_dpo_head(comp)
+    make_grad_clip(comp)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -398,6 +398,29 @@ def test_similarity_matrix(pg, cuda_device):
     assert "temperature" in pg.TemperatureScaledSimilarity().state_dict()
 
 
+def test_similarity_matrix_is_differentiable(pg, cuda_device):
+    """a1: the dense similarity module is differentiable w.r.t. both inputs and a learnable temperature, like the
+    reference's (components.py:45-83); checked against fp64 autograd of the same formula with a random upstream
+    gradient."""
+    dev = cuda_device
+    g = torch.Generator().manual_seed(3)
+    v0, t0 = torch.randn(70, 96, generator=g), torch.randn(50, 96, generator=g)
+    up = torch.randn(70, 50, generator=g)
+    mod = pg.TemperatureScaledSimilarity(temperature=0.5, learnable=True).to(dev)
+    v, t = v0.to(dev).requires_grad_(True), t0.to(dev).requires_grad_(True)
+    (mod(v, t) * up.to(dev)).sum().backward()
+    vd, td = v0.double().requires_grad_(True), t0.double().requires_grad_(True)
+    tau = torch.tensor(0.5, dtype=torch.float64, requires_grad=True)
+    S = torch.nn.functional.normalize(vd, dim=-1) @ torch.nn.functional.normalize(td, dim=-1).T / tau.clamp(0.1, 2.0)
+    (S * up.double()).sum().backward()
+    assert rel(v.grad, vd.grad) < GRAD_RTOL and rel(t.grad, td.grad) < GRAD_RTOL
+    assert abs(mod.temperature.grad.item() - tau.grad.item()) <= GRAD_RTOL * abs(tau.grad.item())
+    # outside the clamp range the temperature gets no gradient (torch.clamp semantics)
+    mod2 = pg.TemperatureScaledSimilarity(temperature=0.05, learnable=True).to(dev)
+    mod2(v.detach(), t.detach()).sum().backward()
+    assert mod2.temperature.grad.item() == 0.0
+
+
 def test_opcheck(pg, cuda_device):
     from preference_guided_image_captioning_alignment_b200 import ops
     dev = cuda_device
@@ -613,3 +636,80 @@ def test_graphed_dpo_step_matches_eager(pg, cuda_device):
         ref_loss.backward()
         assert loss.item() == pytest.approx(ref_loss.item(), rel=1e-6) and value == loss.item()
         assert torch.equal(step.dweight, Wg.grad) and torch.equal(step.dhidden, hg.grad)
+
+
+def test_causal_lm_loss_from_hidden_states(pg, cuda_device):
+    """the HF causal-LM cross-entropy that GPT2LMHeadModel computes from `labels`
+    (transformers loss_utils.py:45-67, reached from pkg/models/model.py:604-610) out of the fused LM-head kernel:
+    mean over the shifted positions whose label is not -100, and its gradients, against torch cross_entropy on the
+    materialised logits (fp64, same bf16-rounded inputs)."""
+    from preference_guided_image_captioning_alignment_b200.install import lazy_causal_lm_loss
+    dev = cuda_device
+    B, T, d, V = 3, 40, 256, 5003
+    g = torch.Generator().manual_seed(21)
+    W = (torch.randn(V, d, generator=g) * 0.05).to(torch.bfloat16)
+    H = torch.randn(B, T, d, generator=g).to(torch.bfloat16)
+    y = torch.randint(0, V, (B, T), generator=g)
+    y[0, 25:] = -100   # padded tail, HF convention
+    y[2, :5] = -100    # ignored prefix
+    Wg, Hg = W.to(dev).requires_grad_(True), H.to(dev).requires_grad_(True)
+    loss = lazy_causal_lm_loss(pg.LazyLogits(Hg, Wg), y.to(dev))
+    loss.backward()
+    Wd, Hd = W.double().requires_grad_(True), H.double().requires_grad_(True)
+    logits = Hd @ Wd.t()
+    ref = torch.nn.functional.cross_entropy(logits[:, :-1].reshape(-1, V), y[:, 1:].reshape(-1), ignore_index=-100)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= LOSS_RTOL * abs(ref.item())
+    assert rel(Hg.grad.float(), Hd.grad) < GRAD_RTOL and rel(Wg.grad.float(), Wd.grad) < GRAD_RTOL
+    assert torch.count_nonzero(Hg.grad[0, 25:]).item() == 0  # positions that score nothing get exactly zero
+
+
+# ================================================================================ SURVEY 8(f) row 2: grad norm + clip
+@pytest.mark.parametrize("tag", ["clip", "noclip", "big", "nan"])
+def test_grad_norm_clip_golden(pg, cuda_device, golden_dir, tag):
+    """pg.NaNSafeGradientNorm (one multi-tensor pass) against the outputs of the real reference module."""
+    g = np.load(os.path.join(golden_dir, "grad_clip.npz"))
+    n = 2 if tag == "nan" else 5
+    params = []
+    for i in range(n):
+        p = torch.nn.Parameter(torch.zeros(g[f"{tag}_g{i}"].shape, device=cuda_device))
+        p.grad = torch.from_numpy(g[f"{tag}_g{i}"]).to(cuda_device)
+        params.append(p)
+    max_norm = 1.0 if tag == "nan" else float(g[f"{tag}_max_norm"])
+    total, finite = pg.NaNSafeGradientNorm(max_norm=max_norm)(params)
+    assert finite == bool(g[f"{tag}_finite"])
+    if tag != "nan":
+        assert abs(total.item() - float(g[f"{tag}_total"])) <= 2e-6 * float(g[f"{tag}_total"])
+    for i, p in enumerate(params):
+        np.testing.assert_allclose(p.grad.cpu().numpy(), g[f"{tag}_c{i}"], rtol=3e-6, atol=0, equal_nan=True)
+
+
+def test_grad_norm_clip_large_mixed(pg, cuda_device):
+    """Many chunks, bf16 and fp32 gradients, unaligned views, against the float64 oracle; deterministic; Inf detected."""
+    from preference_guided_image_captioning_alignment_b200 import functional as F
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(9)
+    shapes = [(50257, 64), (3 * 32768 + 5,), (1023, 513), (7,), (32768,)]
+    grads = [torch.randn(*s, generator=gen).to(dev) * 0.01 for s in shapes]
+    grads[2] = grads[2].to(torch.bfloat16)
+    base = torch.randn(100003, generator=gen).to(dev)
+    grads.append(base[3:])  # 4-byte aligned only: the scalar path of the kernel
+    ref = cf.grad_norm_clip([x.double().cpu().numpy() for x in grads], 0.25)
+    work = [x.clone() for x in grads[:-1]] + [base.clone()[3:]]
+    s1 = F.grad_norm_clip(work, 0.25)
+    assert abs(s1[0].item() - ref["total_norm"]) <= 2e-6 * ref["total_norm"]
+    assert abs(s1[1].item() - ref["clip_coef"]) <= 2e-6 * ref["clip_coef"] and s1[2].item() == 1.0
+    for w, r in zip(work, ref["clipped"]):
+        tol = 1e-2 if w.dtype == torch.bfloat16 else 1e-5
+        assert rel(w.float(), r) < tol
+    s2 = F.grad_norm_clip([x.clone() for x in grads[:-1]] + [base.clone()[3:]], 0.25)
+    assert torch.equal(s1, s2)
+    small = [x.clone() * 1e-4 for x in grads[:2]]
+    keep = [x.clone() for x in small]
+    s3 = F.grad_norm_clip(small, 1.0)  # below max_norm: untouched, bit for bit
+    assert s3[1].item() == 1.0 and all(torch.equal(a, b) for a, b in zip(small, keep))
+    bad = [x.clone() for x in grads[:2]]
+    bad[1][12345] = float("inf")
+    keep = [x.clone() for x in bad]
+    s4 = F.grad_norm_clip(bad, 0.25)
+    assert s4[2].item() == 0.0 and all(torch.equal(a, b) for a, b in zip(bad, keep))

@@ -254,3 +254,20 @@ def test_against_live_reference():
     mask = torch.ones(2, 6, dtype=torch.float64)
     np.testing.assert_allclose(PL(0.1)._compute_log_probs(logits, labels, mask).numpy(),
                                cf.sequence_logprobs(logits.numpy(), labels.numpy(), mask.numpy(), True), rtol=1e-12)
+
+
+# ================================================================================ SURVEY 8(f) row 2: grad norm + clip
+@pytest.mark.parametrize("tag", ["clip", "noclip", "big", "nan"])
+def test_grad_norm_clip_closed_form(golden_dir, tag):
+    """oracle.closed_form.grad_norm_clip against the real NaNSafeGradientNorm (components.py:252-318) outputs."""
+    g = np.load(os.path.join(golden_dir, "grad_clip.npz"))
+    n = 2 if tag == "nan" else 5
+    grads = [g[f"{tag}_g{i}"] for i in range(n)]
+    max_norm = 1.0 if tag == "nan" else float(g[f"{tag}_max_norm"])
+    o = cf.grad_norm_clip(grads, max_norm)
+    assert o["is_finite"] == bool(g[f"{tag}_finite"])
+    if tag != "nan":
+        assert abs(o["total_norm"] - float(g[f"{tag}_total"])) <= 1e-6 * float(g[f"{tag}_total"])  # reference is fp32
+        assert (o["clip_coef"] < 1.0) == (tag != "noclip")
+    for i in range(n):
+        np.testing.assert_allclose(o["clipped"][i], g[f"{tag}_c{i}"], rtol=2e-6, atol=0, equal_nan=True)
