@@ -269,8 +269,10 @@ int pgica_logits_grad(const void* logits, int logits_is_bf16, const int32_t* row
  * clip_grad_norm_ of the trainer (pkg/training/trainer.py:494-515, 619-628).
  *   grads_host[i]: device pointer of gradient i (fp32, or bf16 when is_bf16_host[i] != 0), numels_host[i] elements;
  *   stats (device, 3 floats): total_norm, clip_coef = min(1, max_norm / (total_norm + 1e-6)), is_finite (1 / 0).
- *   clip != 0: gradients are multiplied by clip_coef in place when the norm is finite and clip_coef < 1 (a non-finite
- *   norm leaves them untouched, like the reference).  Three launches, no host synchronisation; deterministic.
+ *   clip bit 0: gradients are multiplied by clip_coef in place when the norm is finite and clip_coef < 1 (a non-finite
+ *   norm leaves them untouched, like the reference).  clip bit 1: the chunk table the previous call uploaded into
+ *   this very workspace for these very tensors is still there (skips a host->device copy per step).
+ *   Three launches, no host synchronisation; deterministic.
  * workspace: pgica_grad_norm_clip_workspace_bytes() bytes (chunk table + per-chunk partial sums).
  * ---------------------------------------------------------------------------------------------- */
 int pgica_grad_norm_clip_workspace_bytes(const int64_t* numels_host, int n_tensors, size_t* bytes_host);

@@ -67,14 +67,22 @@ __global__ void __launch_bounds__(kThreads) grad_sumsq_kernel(const GradChunk* _
     const float* g = static_cast<const float*>(c.ptr);
     const int n4 = ((reinterpret_cast<uintptr_t>(g) & 15u) == 0) ? c.count / 4 : 0;
     const float4* g4 = reinterpret_cast<const float4*>(g);
-    for (int i = threadIdx.x; i < n4; i += kThreads) {
-      const float4 v = g4[i];
-      acc = fmaf(v.x, v.x, acc);
-      acc = fmaf(v.y, v.y, acc);
-      acc = fmaf(v.z, v.z, acc);
-      acc = fmaf(v.w, v.w, acc);
+    // four independent 16-byte loads in flight per thread (a full chunk is 32 per thread)
+    float a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int i = threadIdx.x;
+    for (; i + 3 * kThreads < n4; i += 4 * kThreads) {
+      const float4 v0 = g4[i], v1 = g4[i + kThreads], v2 = g4[i + 2 * kThreads], v3 = g4[i + 3 * kThreads];
+      acc = fmaf(v0.x, v0.x, fmaf(v0.y, v0.y, fmaf(v0.z, v0.z, fmaf(v0.w, v0.w, acc))));
+      a1 = fmaf(v1.x, v1.x, fmaf(v1.y, v1.y, fmaf(v1.z, v1.z, fmaf(v1.w, v1.w, a1))));
+      a2 = fmaf(v2.x, v2.x, fmaf(v2.y, v2.y, fmaf(v2.z, v2.z, fmaf(v2.w, v2.w, a2))));
+      a3 = fmaf(v3.x, v3.x, fmaf(v3.y, v3.y, fmaf(v3.z, v3.z, fmaf(v3.w, v3.w, a3))));
     }
-    for (int i = n4 * 4 + threadIdx.x; i < c.count; i += kThreads) acc = fmaf(g[i], g[i], acc);
+    for (; i < n4; i += kThreads) {
+      const float4 v = g4[i];
+      acc = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, acc))));
+    }
+    acc = (acc + a1) + (a2 + a3);
+    for (int j = n4 * 4 + threadIdx.x; j < c.count; j += kThreads) acc = fmaf(g[j], g[j], acc);
   }
   const float t = block_sum(acc, s_red);
   if (threadIdx.x == 0) partial[blockIdx.x] = t;
@@ -112,15 +120,19 @@ __global__ void __launch_bounds__(kThreads) grad_scale_kernel(const GradChunk* _
     float* g = const_cast<float*>(static_cast<const float*>(c.ptr));
     const int n4 = ((reinterpret_cast<uintptr_t>(g) & 15u) == 0) ? c.count / 4 : 0;
     float4* g4 = reinterpret_cast<float4*>(g);
-    for (int i = threadIdx.x; i < n4; i += kThreads) {
-      float4 v = g4[i];
-      v.x *= coef;
-      v.y *= coef;
-      v.z *= coef;
-      v.w *= coef;
-      g4[i] = v;
+    int i = threadIdx.x;
+    for (; i + 3 * kThreads < n4; i += 4 * kThreads) {
+      float4 v0 = g4[i], v1 = g4[i + kThreads], v2 = g4[i + 2 * kThreads], v3 = g4[i + 3 * kThreads];
+      g4[i] = make_float4(v0.x * coef, v0.y * coef, v0.z * coef, v0.w * coef);
+      g4[i + kThreads] = make_float4(v1.x * coef, v1.y * coef, v1.z * coef, v1.w * coef);
+      g4[i + 2 * kThreads] = make_float4(v2.x * coef, v2.y * coef, v2.z * coef, v2.w * coef);
+      g4[i + 3 * kThreads] = make_float4(v3.x * coef, v3.y * coef, v3.z * coef, v3.w * coef);
     }
-    for (int i = n4 * 4 + threadIdx.x; i < c.count; i += kThreads) g[i] *= coef;
+    for (; i < n4; i += kThreads) {
+      float4 v = g4[i];
+      g4[i] = make_float4(v.x * coef, v.y * coef, v.z * coef, v.w * coef);
+    }
+    for (int j = n4 * 4 + threadIdx.x; j < c.count; j += kThreads) g[j] *= coef;
   }
 }
 
@@ -159,23 +171,26 @@ int pgica_grad_norm_clip(const void* const* grads_host, const int64_t* numels_ho
     set_error("grad_norm_clip: workspace too small");
     return PGICA_ERR_WORKSPACE_TOO_SMALL;
   }
-  // chunk table, built on the host and copied ahead of the launches (pageable source: staged synchronously)
-  GradChunk* table = static_cast<GradChunk*>(malloc((size_t)chunks * sizeof(GradChunk)));
-  PGICA_REQUIRE(table, "grad_norm_clip: out of host memory");
-  int64_t k = 0;
-  for (int i = 0; i < n_tensors; ++i) {
-    const size_t esz = is_bf16_host[i] ? 2 : 4;
-    for (int64_t off = 0; off < numels_host[i]; off += kChunk) {
-      table[k].ptr = static_cast<const uint8_t*>(grads_host[i]) + (size_t)off * esz;
-      table[k].count = (int)(numels_host[i] - off < kChunk ? numels_host[i] - off : kChunk);
-      table[k].is_bf16 = is_bf16_host[i] ? 1 : 0;
-      ++k;
-    }
-  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemcpyAsync(workspace, table, (size_t)chunks * sizeof(GradChunk), cudaMemcpyHostToDevice, st);
-  free(table);
-  PGICA_CUDA_OK(e);
+  if (!(clip & 2)) {
+    // chunk table, built on the host and copied ahead of the launches (pageable source: staged synchronously).
+    // Flag bit 1 of `clip` skips this when the caller kept the workspace of its previous call on the SAME tensors.
+    GradChunk* table = static_cast<GradChunk*>(malloc((size_t)chunks * sizeof(GradChunk)));
+    PGICA_REQUIRE(table, "grad_norm_clip: out of host memory");
+    int64_t k = 0;
+    for (int i = 0; i < n_tensors; ++i) {
+      const size_t esz = is_bf16_host[i] ? 2 : 4;
+      for (int64_t off = 0; off < numels_host[i]; off += kChunk) {
+        table[k].ptr = static_cast<const uint8_t*>(grads_host[i]) + (size_t)off * esz;
+        table[k].count = (int)(numels_host[i] - off < kChunk ? numels_host[i] - off : kChunk);
+        table[k].is_bf16 = is_bf16_host[i] ? 1 : 0;
+        ++k;
+      }
+    }
+    cudaError_t e = cudaMemcpyAsync(workspace, table, (size_t)chunks * sizeof(GradChunk), cudaMemcpyHostToDevice, st);
+    free(table);
+    PGICA_CUDA_OK(e);
+  }
   const GradChunk* d_table = static_cast<const GradChunk*>(workspace);
   float* partial = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + table_bytes);
   grad_sumsq_kernel<<<(unsigned)chunks, kThreads, 0, st>>>(d_table, partial);
@@ -183,7 +198,7 @@ int pgica_grad_norm_clip(const void* const* grads_host, const int64_t* numels_ho
   grad_norm_finalize_kernel<<<1, 1024, 0, st>>>(partial, (int)chunks, max_norm, stats);
   PGICA_CUDA_OK(cudaGetLastError());
   count_launches(2);
-  if (clip) {
+  if (clip & 1) {
     grad_scale_kernel<<<(unsigned)chunks, kThreads, 0, st>>>(d_table, stats);
     PGICA_CUDA_OK(cudaGetLastError());
     count_launches(1);

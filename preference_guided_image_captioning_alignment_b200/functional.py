@@ -400,10 +400,23 @@ def grad_norm_clip(grads, max_norm, clip=True):
     ptrs = (ctypes.c_void_p * n)(*[g.data_ptr() for g in grads])
     numels = (ctypes.c_int64 * n)(*[g.numel() for g in grads])
     kinds = (ctypes.c_int32 * n)(*[1 if g.dtype == torch.bfloat16 else 0 for g in grads])
-    need = ctypes.c_size_t(0)
-    _lib.check(lib.pgica_grad_norm_clip_workspace_bytes(numels, n, ctypes.byref(need)))
-    ws = _ws(need.value, grads[0].device)
+    # the workspace (chunk table + partial sums) is kept for the next call on the same tensors: optimiser steps
+    # clip the same gradient buffers every time, and the table then need not be rebuilt and uploaded
+    key = tuple((g.data_ptr(), g.numel(), g.dtype) for g in grads)
+    cached = _GRADCLIP_CACHE.get("entry")
+    flags = 1 if clip else 0
+    if cached is not None and cached[0] == key:
+        ws = cached[1]
+        flags |= 2
+    else:
+        need = ctypes.c_size_t(0)
+        _lib.check(lib.pgica_grad_norm_clip_workspace_bytes(numels, n, ctypes.byref(need)))
+        ws = _ws(need.value, grads[0].device)
+        _GRADCLIP_CACHE["entry"] = (key, ws)
     stats = torch.empty(3, dtype=torch.float32, device=grads[0].device)
-    _lib.check(lib.pgica_grad_norm_clip(ptrs, numels, kinds, n, float(max_norm), 1 if clip else 0, _p(stats), _p(ws),
+    _lib.check(lib.pgica_grad_norm_clip(ptrs, numels, kinds, n, float(max_norm), flags, _p(stats), _p(ws),
                                         ws.numel(), _stream()))
     return stats
+
+
+_GRADCLIP_CACHE = {}
