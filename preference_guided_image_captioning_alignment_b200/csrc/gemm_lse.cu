@@ -118,23 +118,28 @@ gemm_lse_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // TMA producer: the whole warp walks the tile schedule, one elected lane issues the copies
+  if (warp == 0 || warp == 2) {
+    // TMA producers: two warps, one per stage parity (a single warp's wait + expect_tx + two TMA issues per stage take
+    // most of the time the tensor pipe needs to consume a stage); each whole warp walks the tile schedule, one
+    // elected lane issues the copies
+    const int par = warp >> 1;
     int stage = 0;
-    uint32_t phase = 0;
+    uint32_t phase = 0, stage_no = 0;
     const uint32_t lbar0 = mapa_u32(smem_u32(&full_bar[0]), 0);  // the leader's full barriers (shared::cluster)
     for (int t = t_begin; t < t_end; t += t_step) {
       const int n_tile = t / p.num_m_pairs;
       const int m_blk = 2 * (t - n_tile * p.num_m_pairs) + (int)rho;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        if (elect_one()) {
-          if (rho == 0) mbar_expect_tx(&full_bar[stage], 2 * (kABytes + kBBytes));  // both CTAs' bytes
-          const uint32_t lbar = lbar0 + stage * 8;
-          tma_load_2d_pair(smem_a + stage * kABytes, &tm_a, lbar, kb * kBlockK, m_blk * kBlockM);
-          tma_load_2d_pair(smem_b + stage * kBBytes, &tm_b, lbar, kb * kBlockK, n_tile * kBlockN + (int)rho * (kBlockN / 2));
+      for (int kb = 0; kb < num_kb; ++kb, ++stage_no) {
+        if ((int)(stage_no & 1u) == par) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (elect_one()) {
+            if (rho == 0) mbar_expect_tx(&full_bar[stage], 2 * (kABytes + kBBytes));  // both CTAs' bytes
+            const uint32_t lbar = lbar0 + stage * 8;
+            tma_load_2d_pair(smem_a + stage * kABytes, &tm_a, lbar, kb * kBlockK, m_blk * kBlockM);
+            tma_load_2d_pair(smem_b + stage * kBBytes, &tm_b, lbar, kb * kBlockK, n_tile * kBlockN + (int)rho * (kBlockN / 2));
+          }
+          __syncwarp();
         }
-        __syncwarp();
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1;

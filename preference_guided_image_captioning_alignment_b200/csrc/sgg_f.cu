@@ -99,6 +99,7 @@ struct SggfParams {
   int R2, C2, S;          // row pairs per chunk, column pairs per pass, 512-column splits of k
   int nH, nW, nP, D;      // PAIRS per role; exchange double-slots per producer CTA
   int spread;             // 1: spread an X-holder's quads evenly over a pass (StepOffsets)
+  int debug_producers_only;  // diagnostics: holders exit at once, producers publish nothing (results are garbage)
   int outx_bf16, outy_bf16;
   float c;                // scale * log2(e)
   const float* r_lse;
@@ -338,28 +339,33 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
     const int pp = pair - p.nH - p.nW;             // producer pair number
     const uint32_t pcta = (uint32_t)pp * 2u + rho;  // producer CTA number (owns D double slots of the ring)
 
-    if (warp == 0) {
+    if (warp == 0 || warp == 2) {
       // ---------------------------------------------------------------- TMA loads of this CTA's MMA1 operand halves
+      // Two loader warps, one per stage parity: a single warp needs ~400 cycles per stage (barrier wait, expect_tx,
+      // two TMA issues) against the ~550 the tensor pipe takes to consume one, which left no slack for jitter.
+      const int par = warp >> 1;
       int slot = 0, mine = pp;
-      uint32_t phase = 0;
+      uint32_t phase = 0, stage_no = 0;
       const uint32_t lbar0 = mapa_u32(smem_u32(&full_bar[0]), 0);  // the leader's full barriers (shared::cluster)
       LAP_DECL;
       for_each_quad(p, [&](int q, int r0, int r, int c0, int c) {
         if (q != mine) return;
         mine += p.nP;
         const int xrow = (2 * (r0 + r) + (int)rho) * kBM, yrow = (2 * (c0 + c) + (int)rho) * kBT;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          LAP(0);
-          mbar_wait(&empty_bar[slot], phase ^ 1);
-          LAP(1);
-          if (elect_one()) {
-            const uint32_t lbar = lbar0 + slot * 8;
-            if (rho == 0) mbar_expect_tx(&full_bar[slot], 2 * kPStageBytes);
-            uint8_t* dst = ring + slot * kPStageBytes;
-            tma_load_2d_pair(dst, &tm_x128, lbar, kb * kBK, xrow);
-            tma_load_2d_pair(dst + kChunkBytes, &tm_y128, lbar, kb * kBK, yrow);
+        for (int kb = 0; kb < num_kb; ++kb, ++stage_no) {
+          if ((int)(stage_no & 1u) == par) {
+            LAP(0);
+            mbar_wait(&empty_bar[slot], phase ^ 1);
+            LAP(1);
+            if (elect_one()) {
+              const uint32_t lbar = lbar0 + slot * 8;
+              if (rho == 0) mbar_expect_tx(&full_bar[slot], 2 * kPStageBytes);
+              uint8_t* dst = ring + slot * kPStageBytes;
+              tma_load_2d_pair(dst, &tm_x128, lbar, kb * kBK, xrow);
+              tma_load_2d_pair(dst + kChunkBytes, &tm_y128, lbar, kb * kBK, yrow);
+            }
+            __syncwarp();
           }
-          __syncwarp();
           if (++slot == kPRing) {
             slot = 0;
             phase ^= 1;
@@ -367,7 +373,7 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
         }
       });
       LAP(0);
-      if (lane == 0) LAP_FLUSH(4, 2);
+      if (lane == 0 && warp == 0) LAP_FLUSH(4, 2);
     } else if (warp == 1 && rho == 0) {
       // ---------------------------------------------------------------- MMA1 (leader): Z[256 x 256] = X[2rp, 2rp+1] Y[2cp, 2cp+1]^T
       constexpr uint32_t idesc1 = make_idesc_bf16(256, 256, 0, 0);
@@ -422,9 +428,10 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
           LAP(0);
           mbar_wait(stfull_bar, ntile & 1u);
           LAP(1);
-          if (use > 0) wait_flag_ge(p.done + tslot, n_consumers * use);  // every consumer has pulled the old tile
+          if (use > 0 && !p.debug_producers_only) wait_flag_ge(p.done + tslot, n_consumers * use);  // every consumer has pulled the old tile
           LAP(2);
-          if (lane == 0) {
+          if (lane == 0 && p.debug_producers_only) mbar_arrive(stfree_bar);
+          if (lane == 0 && !p.debug_producers_only) {
             asm volatile("fence.proxy.async.global;" ::: "memory");  // acquire above before the async-proxy write
             tma_store_2d(&tm_s, staging, 0, (int)tslot * kBM);
             tma_store_2d(&tm_s, staging + kChunkBytes, kBK, (int)tslot * kBM);
@@ -581,6 +588,12 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
   cluster_sync_all();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  if (p.debug_producers_only) {
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    return;
+  }
   const CUtensorMap* tm_op = is_y ? &tm_x64 : &tm_y64;  // the other operand of this pair's product
   const int op_col0 = split * kNC + (int)rho * 128;     // this CTA's 128 of each 256-column instruction
 
@@ -941,6 +954,7 @@ int plan_and_launch(const void* x, const void* y, int64_t mx, int64_t my, int64_
   p.nP = pl.nP;
   p.D = kSlotsPerProducer;
   p.spread = (getenv("PGICA_SGGF_SPREAD") && atoi(getenv("PGICA_SGGF_SPREAD")) != 0) ? 1 : 0;
+  p.debug_producers_only = getenv("PGICA_SGGF_DEBUG_PRODUCERS_ONLY") ? 1 : 0;
   if (const char* e = getenv("PGICA_SGGF_SLOTS")) {  // tuning: exchange double-slots per producer CTA (<= the reserved 4 x 2)
     const int v = atoi(e);
     if (v >= 1 && v <= 2 * kSlotsPerProducer) p.D = v;
