@@ -52,14 +52,17 @@ tma_rate_kernel(const __grid_constant__ CUtensorMap tm, const uint8_t* base, int
       if (i < iters && elect_one()) {
         mbar_expect_tx(&bar[slot], kTile * batch);
         for (int b = 0; b < batch; ++b) {
-          const uint32_t tile = (t + b * 37u) % (uint32_t)(kbs * rbs);
+          // tile coordinates without divisions (kbs = 16, rbs = 32 are powers of two): the loop must cost what a
+          // GEMM's loader pays, not integer division
+          const uint32_t tt = t + b * 37u;
+          const int kb = (int)(tt & (uint32_t)(kbs - 1)), rb = (int)((tt >> 4) & (uint32_t)(rbs - 1));
           uint8_t* dst = smem + (size_t)(slot * batch + b) * kTile;
           if (mode == 0) {
-            tma_load_2d(dst, &tm, &bar[slot], (int)(tile % kbs) * 64, (int)(tile / kbs) * 128);
+            tma_load_2d(dst, &tm, &bar[slot], kb * 64, rb * 128);
           } else {
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                              smem_u32(dst)),
-                         "l"(base + (size_t)tile * kTile), "r"(kTile), "r"(smem_u32(&bar[slot]))
+                         "l"(base + (size_t)(rb * kbs + kb) * kTile), "r"(kTile), "r"(smem_u32(&bar[slot]))
                          : "memory");
           }
         }
