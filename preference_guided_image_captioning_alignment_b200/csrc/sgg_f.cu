@@ -341,8 +341,9 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
 
     if (warp == 0 || warp == 2) {
       // ---------------------------------------------------------------- TMA loads of this CTA's MMA1 operand halves
-      // Two loader warps, one per stage parity: a single warp needs ~400 cycles per stage (barrier wait, expect_tx,
-      // two TMA issues) against the ~550 the tensor pipe takes to consume one, which left no slack for jitter.
+      // Two loader warps, one per stage parity: a single warp needs ~500 cycles per stage (barrier wait, expect_tx,
+      // two TMA issues) against the ~550 the tensor pipe takes to consume one, which leaves no slack for jitter.
+      // (Four loader warps were measured too: no further gain.)
       const int par = warp >> 1;
       int slot = 0, mine = pp;
       uint32_t phase = 0, stage_no = 0;
@@ -450,7 +451,7 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
       });
       LAP(0);
       if (lane == 0) LAP_FLUSH(6, 4);
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 8) {
       // ---------------------------------------------------------------- epilogue: this CTA's Z rows -> two G tiles
       const int quarter = warp & 3;
       const int et = threadIdx.x - 128;
@@ -605,15 +606,14 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
   };
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA: own G tile + own half of the operand rows
-    int slot = 0;
-    uint32_t phase = 0, n = 0;
-    const uint32_t lbar0 = mapa_u32(smem_u32(&full_bar[0]), 0);   // the leader's barriers (shared::cluster)
-    const uint32_t gbar0 = mapa_u32(smem_u32(&gfull_bar[0]), 0);
+    // ------------------------------------------------------------------ TMA, G tiles: poll the exchange ring, pull this CTA's tile
+    // (its own warp: the flag poll is an L2 round trip per tile and must not hold up the operand loads below)
+    uint32_t n = 0;
+    const uint32_t gbar0 = mapa_u32(smem_u32(&gfull_bar[0]), 0);  // the leader's barriers (shared::cluster)
     LAP_DECL;
     for_each_holder_tile(
         p, is_y, hidx,
-        [&](int q, int sel, int rp, int cp, bool, int) {
+        [&](int q, int sel, int, int, bool, int) {
           // X-holder CTA rho: G(2rp + rho, 2cp + sel);  Y-holder CTA rho: G(2rp + sel, 2cp + rho)
           uint32_t use;
           const uint32_t tslot = is_y ? tile_slot(q, (uint32_t)sel, rho, use) : tile_slot(q, rho, (uint32_t)sel, use);
@@ -631,6 +631,21 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
             tma_load_2d_pair(gbuf + gb * kPBytes + kChunkBytes, &tm_s, lbar, kBK, (int)tslot * kBM);
           }
           __syncwarp();
+          ++n;
+        },
+        [&](int, int, int) {});
+    LAP(0);
+    if (lane == 0) LAP_FLUSH(4, 3);
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ TMA, operand rows: this CTA's half of X[r] / Y[c]
+    // (independent of the producers: runs ahead of the G tiles by the depth of the ring)
+    int slot = 0;
+    uint32_t phase = 0;
+    const uint32_t lbar0 = mapa_u32(smem_u32(&full_bar[0]), 0);
+    LAP_DECL;
+    for_each_holder_tile(
+        p, is_y, hidx,
+        [&](int, int sel, int rp, int cp, bool, int) {
           const int op_row0 = (is_y ? 2 * rp + sel : 2 * cp + sel) * kBM;
           for (int st = 0; st < kStagesPerTile; ++st) {
             LAP(0);
@@ -651,11 +666,12 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
               phase ^= 1;
             }
           }
-          ++n;
         },
         [&](int, int, int) {});
     LAP(0);
-    if (lane == 0) LAP_FLUSH(4, 4);
+#ifdef PGICA_TRACE
+    if (lane == 0 && g_sggf_trace) g_sggf_trace[(size_t)blockIdx.x * 24 + 7] = lap.acc[3];
+#endif
   } else if (warp == 1 && rho == 0) {
     // ------------------------------------------------------------------ MMA2 (leader): Out[256 x 512] += G(^T) * operand rows
     const uint32_t idesc2 = make_idesc_bf16(256, 256, is_y ? 1 : 0, 1);
@@ -723,7 +739,7 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
         });
     LAP(0);
     if (lane == 0) LAP_FLUSH(0, 4);
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     // ------------------------------------------------------------------ drain: accumulator -> OutX / OutY
     const int quarter = warp & 3;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
