@@ -126,6 +126,12 @@ int pgica_softmax_grad_gemm_dual_workspace_bytes(int64_t mx, int64_t my, int64_t
  * row pairs per chunk, column pairs per pass, X-holder pairs, Y-holder pairs, producer pairs.  Host arithmetic only. */
 int pgica_softmax_grad_gemm_dual_plan(int64_t mx, int64_t my, int64_t k, int npairs, int single_chunk,
                                       int32_t* plan_host);
+/* Host replay of the dual kernel's tile schedule (the same enumerators the device code runs; test hook, no device):
+ * role 0: every quad in production order, 3 ints each (q, row pair, column pair); role 1 / 2: the pair-tiles X- /
+ * Y-holder pair `idx` accumulates, 6 ints each (q, sel, row pair, column pair, first-of-period, period).  Returns the
+ * number of records (only the first `capacity` are written), -1 on a bad argument. */
+int64_t pgica_debug_dual_schedule(int row_pairs, int col_pairs, int row_pairs_per_chunk, int col_pairs_per_pass,
+                                  int spread, int role, int idx, int32_t* out_host, int64_t capacity);
 int pgica_softmax_grad_gemm_dual(const void* x, const void* y, int64_t mx, int64_t my, int64_t k, float scale,
                                  const float* r_lse, const float* r_coef, const int32_t* r_tgt, const float* c_lse,
                                  const float* c_coef, const int32_t* c_tgt, void* out_x, int out_x_is_bf16,

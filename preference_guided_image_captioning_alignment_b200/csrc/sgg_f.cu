@@ -187,15 +187,15 @@ __device__ __forceinline__ void wait_flag_ge(const uint32_t* p, uint32_t v) {
 struct StepOffsets {
   int off, acc, Rc, Cc;
   int step;
-  __device__ StepOffsets(int rc, int cc, int spread) : off(0), acc(0), Rc(rc), Cc(cc), step(spread ? rc : cc) {}
-  __device__ void next() {
+  __host__ __device__ StepOffsets(int rc, int cc, int spread) : off(0), acc(0), Rc(rc), Cc(cc), step(spread ? rc : cc) {}
+  __host__ __device__ void next() {
     acc += step;
     while (acc >= Cc) {
       acc -= Cc;
       ++off;
     }
   }
-  __device__ int row(int t) const {  // (off + t) mod Rc; off may reach Rc when Cc < Rc is false, hence the loop
+  __host__ __device__ int row(int t) const {  // (off + t) mod Rc; off may reach Rc when Cc < Rc is false, hence the loop
     int r = off + t;
     while (r >= Rc) r -= Rc;
     return r;
@@ -205,12 +205,12 @@ struct StepOffsets {
 // Visits every quad in production order.  f(q, r0, r, c0, c): sequence number q; the quad covers row pair r0 + r
 // (row blocks 2(r0+r), 2(r0+r)+1) and column pair c0 + c.
 template <class F>
-__device__ __forceinline__ void for_each_quad(const SggfParams& p, F&& f) {
+__host__ __device__ __forceinline__ void for_each_quad(const SggfParams& p, F&& f) {
   int q = 0;
   for (int r0 = 0; r0 < p.RB2; r0 += p.R2) {
-    const int Rc = min(p.R2, p.RB2 - r0);
+    const int Rc = p.R2 < p.RB2 - r0 ? p.R2 : p.RB2 - r0;
     for (int c0 = 0; c0 < p.J2; c0 += p.C2) {
-      const int Cc = min(p.C2, p.J2 - c0);
+      const int Cc = p.C2 < p.J2 - c0 ? p.C2 : p.J2 - c0;
       for (int t = 0; t < Rc; ++t) {
         StepOffsets so(Rc, Cc, p.spread);
         for (int c = 0; c < Cc; ++c, ++q) {
@@ -228,13 +228,13 @@ __device__ __forceinline__ void for_each_quad(const SggfParams& p, F&& f) {
 // or the row block 2rp + sel (Y-holder); `first` marks the first pair-tile of an accumulation period.  g(period,
 // chunk, pass) is called after the last pair-tile of every period that had any.
 template <class F, class G>
-__device__ __forceinline__ void for_each_holder_tile(const SggfParams& p, bool is_y, int idx, F&& f, G&& g) {
+__host__ __device__ __forceinline__ void for_each_holder_tile(const SggfParams& p, bool is_y, int idx, F&& f, G&& g) {
   int qbase = 0, period = 0;
   for (int r0 = 0, chunk = 0; r0 < p.RB2; r0 += p.R2, ++chunk) {
-    const int Rc = min(p.R2, p.RB2 - r0);
+    const int Rc = p.R2 < p.RB2 - r0 ? p.R2 : p.RB2 - r0;
     bool first = true;
     for (int c0 = 0, pass = 0; c0 < p.J2; c0 += p.C2, ++pass) {
-      const int Cc = min(p.C2, p.J2 - c0);
+      const int Cc = p.C2 < p.J2 - c0 ? p.C2 : p.J2 - c0;
       if (is_y) {
         if (idx < Cc) {
           StepOffsets so(Rc, Cc, p.spread);
@@ -1051,6 +1051,46 @@ void sggf_plan(int64_t mx, int64_t my, int64_t k, int npairs, int single_chunk, 
   out[4] = pl.nP;
 }
 
+// Host replay of the kernel's schedule (the very enumerators the device code runs), for the CPU test-suite:
+// role 0 = producers' view: out gets (q, row pair, column pair) per quad; role 1 / 2 = X- / Y-holder `idx`: out gets
+// (q, sel, row pair, column pair, first, period) per pair-tile.  Returns the number of records (written up to `cap`).
+int64_t sggf_schedule(int RB2, int J2, int R2, int C2, int spread, int role, int idx, int32_t* out, int64_t cap) {
+  SggfParams p{};
+  p.RB2 = RB2;
+  p.J2 = J2;
+  p.R2 = R2;
+  p.C2 = C2;
+  p.spread = spread;
+  int64_t n = 0;
+  if (role == 0) {
+    for_each_quad(p, [&](int q, int r0, int r, int c0, int c) {
+      if (n < cap) {
+        out[3 * n] = q;
+        out[3 * n + 1] = r0 + r;
+        out[3 * n + 2] = c0 + c;
+      }
+      ++n;
+    });
+  } else {
+    for_each_holder_tile(
+        p, role == 2, idx,
+        [&](int q, int sel, int rp, int cp, bool first, int period) {
+          if (n < cap) {
+            int32_t* o = out + 6 * n;
+            o[0] = q;
+            o[1] = sel;
+            o[2] = rp;
+            o[3] = cp;
+            o[4] = first ? 1 : 0;
+            o[5] = period;
+          }
+          ++n;
+        },
+        [&](int, int, int) {});
+  }
+  return n;
+}
+
 size_t sggf_workspace_bytes() {
   // exchange ring for the largest producer count (80 pairs, twice the default depth for tuning) + flags
   const size_t nslots = (size_t)2 * 80 * 2 * kSlotsPerProducer * 2;
@@ -1114,6 +1154,15 @@ extern "C" int pgica_debug_set_sggf_trace(void* buf) {
 
 namespace pgica {
 void sggf_plan(int64_t mx, int64_t my, int64_t k, int npairs, int single_chunk, int out[5]);
+int64_t sggf_schedule(int RB2, int J2, int R2, int C2, int spread, int role, int idx, int32_t* out, int64_t cap);
+}
+extern "C" int64_t pgica_debug_dual_schedule(int row_pairs, int col_pairs, int row_pairs_per_chunk, int col_pairs_per_pass,
+                                             int spread, int role, int idx, int32_t* out_host, int64_t capacity) {
+  if (row_pairs < 1 || col_pairs < 1 || row_pairs_per_chunk < 1 || col_pairs_per_pass < 1 || role < 0 || role > 2 ||
+      idx < 0 || !out_host || capacity < 0)
+    return -1;
+  return pgica::sggf_schedule(row_pairs, col_pairs, row_pairs_per_chunk, col_pairs_per_pass, spread, role, idx, out_host,
+                              capacity);
 }
 extern "C" int pgica_softmax_grad_gemm_dual_plan(int64_t mx, int64_t my, int64_t k, int npairs, int single_chunk,
                                                  int32_t* plan_host) {

@@ -213,3 +213,59 @@ def test_dual_backward_planner_host_side():
                 if single:
                     assert r2 == rb2
     assert lib.pgica_softmax_grad_gemm_dual_plan(4096, 50257, 1000, 74, 0, out) != 0  # k must be a multiple of 512
+
+
+@pytest.mark.parametrize("rb2,j2,r2,c2", [(16, 197, 16, 9), (16, 197, 8, 11), (3, 5, 2, 4), (7, 6, 3, 2), (1, 1, 1, 1),
+                                           (5, 40, 5, 3), (22, 22, 22, 22), (4, 9, 3, 9)])
+@pytest.mark.parametrize("spread", [0, 1])
+def test_dual_backward_schedule_is_consistent(rb2, j2, r2, c2, spread):
+    """The three roles of the dual backward kernel walk ONE schedule (replayed on the host by the enumerators the
+    device code runs): every (row pair, column pair) quad is produced exactly once; every X-holder consumes exactly the
+    quads of its row pair and every Y-holder exactly those of its column pair, both in increasing production order
+    (the kernel's deadlock-freedom argument); accumulation periods start where they must."""
+    import ctypes
+
+    import numpy as np
+
+    from preference_guided_image_captioning_alignment_b200 import _lib
+    lib = _lib.load()
+
+    def replay(role, idx, width):
+        dummy = np.zeros(1, np.int32)
+        n = lib.pgica_debug_dual_schedule(rb2, j2, r2, c2, spread, role, idx, ctypes.c_void_p(dummy.ctypes.data), 0)
+        assert n >= 0
+        buf = np.zeros((max(n, 1), width), dtype=np.int32)
+        assert lib.pgica_debug_dual_schedule(rb2, j2, r2, c2, spread, role, idx, ctypes.c_void_p(buf.ctypes.data), n) == n
+        return buf[:n]
+
+    quads = replay(0, 0, 3)
+    assert len(quads) == rb2 * j2
+    assert np.array_equal(quads[:, 0], np.arange(rb2 * j2))                       # q numbers every quad once, in order
+    assert len({(r, c) for _, r, c in quads}) == rb2 * j2                          # every (row pair, column pair) once
+    where = {(int(r), int(c)): int(q) for q, r, c in quads}
+    # X-holders: slot `idx` of a chunk serves row pairs idx, idx + r2, ... ; one accumulation period per chunk
+    seen_x = set()
+    for idx in range(min(r2, rb2)):
+        tiles = replay(1, idx, 6)
+        assert np.all(np.diff(tiles[:, 0]) >= 0)                                   # production order
+        assert np.array_equal(tiles[0::2, 1], np.zeros(len(tiles) // 2)) and np.array_equal(tiles[1::2, 1], np.ones(len(tiles) // 2))
+        for q, sel, rp, cp, first, period in tiles[0::2]:
+            assert where[(rp, cp)] == q and rp % r2 == idx and period == rp // r2
+            seen_x.add((int(rp), int(cp)))
+        starts = tiles[tiles[:, 4] == 1]
+        assert len(starts) == len({int(t[5]) for t in tiles}) and np.all(starts[:, 1] == 0)
+    assert seen_x == set(where)
+    # Y-holders: slot `idx` of a pass serves column pairs idx, idx + c2, ... ; one period per (chunk, pass)
+    seen_y = set()
+    for idx in range(min(c2, j2)):
+        tiles = replay(2, idx, 6)
+        assert np.all(np.diff(tiles[:, 0]) >= 0)
+        for q, sel, rp, cp, first, period in tiles[0::2]:
+            assert where[(rp, cp)] == q and cp % c2 == idx
+            seen_y.add((int(rp), int(cp)))
+        periods = {}
+        for q, sel, rp, cp, first, period in tiles:
+            periods.setdefault(int(period), []).append((int(rp // r2), int(cp), int(first)))
+        for recs in periods.values():
+            assert len({(ch, cp) for ch, cp, _ in recs}) == 1 and recs[0][2] == 1 and sum(f for _, _, f in recs) == 1
+    assert seen_y == set(where)
