@@ -32,7 +32,7 @@ UNIT = "pair-tokens/s"
 WORKLOAD = ("cfg2: Stage-2 DPO loss head, GPT-2 Medium LM head d=1024 V=50257, chosen/rejected seq 128, 16 pairs per "
             "GPU, beta=0.1, policy fwd+bwd + frozen-reference fwd, random-init, all-ones masks")
 FLOP_PER_PAIR_TOKEN = 16 * CFG["d"] * CFG["vocab"]  # policy fwd 4dV + ref fwd 4dV + policy bwd 8dV
-NCU_TRAFFIC_DUAL = 878.5e6  # dram read + write of one sggf_kernel launch on cfg2 (profiles/r1_ncu_full_sggf.txt)
+NCU_TRAFFIC_DUAL = 824.6e6  # dram read + write of one sggf_kernel launch on cfg2, two-chunk plan (profiles/r1_ncu_full_sggf.txt)
 
 
 def log(*a):
