@@ -269,3 +269,25 @@ def test_dual_backward_schedule_is_consistent(rb2, j2, r2, c2, spread):
         for recs in periods.values():
             assert len({(ch, cp) for ch, cp, _ in recs}) == 1 and recs[0][2] == 1 and sum(f for _, _, f in recs) == 1
     assert seen_y == set(where)
+
+
+def test_new_entry_points_refuse_cpu_tensors():
+    """No CPU fallback anywhere: the dual backward, the graphed step and the gradient-norm module raise on CPU tensors."""
+    import torch
+
+    import preference_guided_image_captioning_alignment_b200 as pg
+    from preference_guided_image_captioning_alignment_b200 import _lib
+    from preference_guided_image_captioning_alignment_b200 import functional as F
+    x = torch.randn(128, 512).to(torch.bfloat16)
+    with pytest.raises(_lib.PgicaError):
+        F.softmax_grad_gemm_dual(x, x, 1.0, row=(torch.zeros(128), torch.ones(128), None))
+    p = torch.nn.Parameter(torch.zeros(10))
+    p.grad = torch.ones(10)
+    with pytest.raises(_lib.PgicaError):
+        pg.NaNSafeGradientNorm(max_norm=1.0)([p])
+    with pytest.raises(ValueError):
+        pg.NaNSafeGradientNorm(norm_type=1.0)
+    with pytest.raises(RuntimeError):
+        pg.GraphedDPOStep(pg.FusedDPOHead(), torch.zeros(8, 4), None, torch.zeros(2, 3, 4),
+                          torch.zeros(2, 3, dtype=torch.long), None)
+    assert pg.NaNSafeGradientNorm()([torch.nn.Parameter(torch.zeros(3))])[1] is True  # no gradients: (0, True) like the reference
