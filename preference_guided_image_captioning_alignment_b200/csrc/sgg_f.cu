@@ -996,9 +996,9 @@ int plan_and_launch(const void* x, const void* y, int64_t mx, int64_t my, int64_
   p.D = kSlotsPerProducer;
   p.spread = (getenv("PGICA_SGGF_SPREAD") && atoi(getenv("PGICA_SGGF_SPREAD")) != 0) ? 1 : 0;
   p.debug_producers_only = getenv("PGICA_SGGF_DEBUG_PRODUCERS_ONLY") ? 1 : 0;
-  if (const char* e = getenv("PGICA_SGGF_SLOTS")) {  // tuning: exchange double-slots per producer CTA (<= the reserved 4 x 2)
+  if (const char* e = getenv("PGICA_SGGF_SLOTS")) {  // tuning: fewer exchange double-slots per producer CTA (8 was no faster than 4)
     const int v = atoi(e);
-    if (v >= 1 && v <= 2 * kSlotsPerProducer) p.D = v;
+    if (v >= 1 && v <= kSlotsPerProducer) p.D = v;
   }
   const size_t nslots = (size_t)2 * p.nP * p.D * 2;
   const size_t ring_bytes = nslots * kPBytes;
@@ -1117,8 +1117,8 @@ int64_t sggf_schedule(int RB2, int J2, int R2, int C2, int spread, int role, int
 }
 
 size_t sggf_workspace_bytes() {
-  // exchange ring for the largest producer count (80 pairs, twice the default depth for tuning) + flags
-  const size_t nslots = (size_t)2 * 80 * 2 * kSlotsPerProducer * 2;
+  // exchange ring for the largest producer count (72 of 74 resident pairs) + flags
+  const size_t nslots = (size_t)2 * 72 * kSlotsPerProducer * 2;
   return nslots * (size_t)kPBytes + 2 * align_up(nslots * sizeof(uint32_t), 256);
 }
 
