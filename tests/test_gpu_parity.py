@@ -713,3 +713,37 @@ def test_grad_norm_clip_large_mixed(pg, cuda_device):
     keep = [x.clone() for x in bad]
     s4 = F.grad_norm_clip(bad, 0.25)
     assert s4[2].item() == 0.0 and all(torch.equal(a, b) for a, b in zip(bad, keep))
+
+
+def test_softmax_grad_gemm_dual_random_shapes(pg, cuda_device, monkeypatch):
+    """Randomised shapes / terms / role splits (k = 512 ... 2048) of the dual kernel against the single-product
+    launches; tools/dual_stress.py runs the longer version (profiles/r1_dual_stress_60cases.log)."""
+    import random
+
+    from preference_guided_image_captioning_alignment_b200 import functional as F
+    dev = cuda_device
+    rng = random.Random(7)
+    for i in range(14):
+        k = rng.choice([512, 1024, 1536, 2048])
+        S = k // 512
+        mx = rng.choice([rng.randint(1, 300), rng.randint(300, 2000), 128 * rng.randint(1, 12) + 1])
+        my = rng.choice([rng.randint(1, 300), rng.randint(300, 4000), 256 * rng.randint(1, 12) + 129])
+        mode = rng.choice(["row", "col", "both"])
+        if rng.random() < 0.6:
+            monkeypatch.setenv("PGICA_SGGF_PLAN", f"{rng.randint(1, 10 // S + 2)},{rng.randint(1, 10 // S + 2)}")
+        else:
+            monkeypatch.delenv("PGICA_SGGF_PLAN", raising=False)
+        torch.manual_seed(i)
+        x = (torch.randn(mx, k, device=dev) * 0.3).to(torch.bfloat16)
+        y = (torch.randn(my, k, device=dev) * 0.3).to(torch.bfloat16)
+        row = col = None
+        if mode in ("row", "both"):
+            row = (F.gemm_lse(x, y, 1.0)[0], torch.randn(mx, device=dev),
+                   torch.randint(-1, my, (mx,), device=dev, dtype=torch.int32))
+        if mode in ("col", "both"):
+            col = (F.gemm_lse(y, x, 1.0)[0], torch.randn(my, device=dev),
+                   torch.randint(-1, mx, (my,), device=dev, dtype=torch.int32))
+        ox, oy = F.softmax_grad_gemm_dual(x, y, 1.0, row=row, col=col)
+        sx = F.softmax_grad_gemm(x, y, 1.0, row=row, col=col)
+        sy = F.softmax_grad_gemm(y, x, 1.0, row=col, col=row)
+        assert rel(ox, sx) < 1e-3 and rel(oy, sy) < 1e-3, (i, mx, my, k, mode)
