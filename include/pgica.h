@@ -270,6 +270,17 @@ int pgica_logits_grad(const void* logits, int logits_is_bf16, const int32_t* row
                       const float* coef, int64_t nseq, int64_t seqlen, int64_t vocab, void* dlogits, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Stage-1 head at small batch (B <= 128, D in {128, 256, 384, 512}): the whole symmetric NT-Xent of
+ * pkg/models/model.py:970-1000 — similarity, both log-sum-exps, loss (mean when reduce_mean != 0, else sum; both
+ * halved) AND the gradients of that loss w.r.t. a and b — in ONE launch of one CTA (ntxent_small.cu).  The trainer's
+ * default batch is 8 (configs/default.yaml:35), BASELINE config 1 is 64: at these sizes the head is launch latency.
+ * a, b: bf16 [rows][dim], used as given.  da, db: fp32 [rows][dim], 16-byte aligned, gradients for upstream gradient 1.
+ * ---------------------------------------------------------------------------------------------- */
+int pgica_ntxent_small_supported(int64_t rows, int64_t dim);
+int pgica_ntxent_small(const void* a, const void* b, int64_t rows, int64_t dim, float inv_tau, int reduce_mean,
+                       float* loss, float* lse_row, float* lse_col, float* da, float* db, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * SURVEY 8(f) row 2 — finite-check + global L2 gradient norm + clip over ALL gradient tensors at once:
  * NaNSafeGradientNorm.forward (pkg/models/components.py:283-318) and the per-parameter isfinite() scan +
  * clip_grad_norm_ of the trainer (pkg/training/trainer.py:494-515, 619-628).

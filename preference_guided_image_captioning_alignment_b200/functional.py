@@ -384,6 +384,25 @@ def logits_grad(logits, row_label, lse, coef):
     return dlogits
 
 
+def ntxent_small_supported(rows, dim):
+    return bool(_lib.load().pgica_ntxent_small_supported(int(rows), int(dim)))
+
+
+def ntxent_small(a, b, inv_tau, reduce_mean=True):
+    """Whole symmetric NT-Xent (loss + unit-upstream gradients) of bf16 (B, D) operands, B <= 128, in one launch.
+    -> (loss[], lse_row[B], lse_col[B], da[B, D] fp32, db[B, D] fp32)"""
+    _need_cuda(a, b)
+    lib = _lib.load()
+    n, dim = a.shape
+    f32 = dict(dtype=torch.float32, device=a.device)
+    loss = torch.empty((), **f32)
+    lse_row, lse_col = torch.empty(n, **f32), torch.empty(n, **f32)
+    da, db = torch.empty(n, dim, **f32), torch.empty(n, dim, **f32)
+    _lib.check(lib.pgica_ntxent_small(_p(a), _p(b), n, dim, float(inv_tau), 1 if reduce_mean else 0, _p(loss),
+                                      _p(lse_row), _p(lse_col), _p(da), _p(db), _stream()))
+    return loss, lse_row, lse_col, da, db
+
+
 # ----------------------------------------------------------------------------------------- SURVEY 8(f) row 2
 def grad_norm_clip(grads, max_norm, clip=True):
     """Global L2 norm of a list of gradient tensors (fp32 / bf16, contiguous), finite check and in-place clip in three

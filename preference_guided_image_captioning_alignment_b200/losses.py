@@ -63,7 +63,7 @@ class ContrastiveLoss(nn.Module):
         self.logger = logging.getLogger(__name__)
 
     def forward(self, image_embeddings: torch.Tensor, text_embeddings: torch.Tensor) -> torch.Tensor:
-        loss, _, _ = ops.ntxent(image_embeddings, text_embeddings, 1.0 / float(self.temperature), True)
+        loss, _, _ = ops.ntxent_auto(image_embeddings, text_embeddings, 1.0 / float(self.temperature), True)
         return loss.to(image_embeddings.dtype) if image_embeddings.dtype == torch.float64 else loss
 
 

@@ -41,6 +41,41 @@ def _(a, b, inv_tau, reduce_mean):
     return a.new_empty((), dtype=torch.float32), _f32(a.shape[0], a), _f32(b.shape[0], a)
 
 
+@torch.library.custom_op("pgica::ntxent_small", mutates_args=())
+def ntxent_small(a: Tensor, b: Tensor, inv_tau: float, reduce_mean: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """Small-batch form of `ntxent` (B <= 128, D in {128, 256, 384, 512}): loss, both LSE vectors and the gradients
+    of the loss w.r.t. a and b from ONE single-CTA launch (csrc/ntxent_small.cu)."""
+    if a.shape != b.shape or a.dim() != 2:
+        raise ValueError(f"ntxent expects two (B, D) tensors of equal shape, got {tuple(a.shape)} {tuple(b.shape)}")
+    return F.ntxent_small(F.as_bf16(a), F.as_bf16(b), inv_tau, reduce_mean)
+
+
+@ntxent_small.register_fake
+def _(a, b, inv_tau, reduce_mean):
+    return (a.new_empty((), dtype=torch.float32), _f32(a.shape[0], a), _f32(b.shape[0], a),
+            torch.empty_like(a, dtype=torch.float32), torch.empty_like(b, dtype=torch.float32))
+
+
+def _ntxent_small_setup(ctx, inputs, output):
+    ctx.save_for_backward(output[3], output[4])
+    ctx.dtypes = (inputs[0].dtype, inputs[1].dtype)
+
+
+def _ntxent_small_backward(ctx, g_loss, g_lr, g_lc, g_da, g_db):
+    da, db = ctx.saved_tensors  # gradients of the loss itself: scale by the upstream scalar
+    return (da * g_loss).to(ctx.dtypes[0]), (db * g_loss).to(ctx.dtypes[1]), None, None
+
+
+ntxent_small.register_autograd(_ntxent_small_backward, setup_context=_ntxent_small_setup)
+
+
+def ntxent_auto(a: Tensor, b: Tensor, inv_tau: float, reduce_mean: bool):
+    """`ntxent_small` when the batch fits one CTA, else the general kernels.  -> (loss, lse_row, lse_col)"""
+    if a.dim() == 2 and a.shape == b.shape and a.is_cuda and F.ntxent_small_supported(a.shape[0], a.shape[1]):
+        return ntxent_small(a, b, inv_tau, reduce_mean)[:3]
+    return ntxent(a, b, inv_tau, reduce_mean)
+
+
 @torch.library.custom_op("pgica::ntxent_bwd", mutates_args=())
 def ntxent_bwd(a: Tensor, b: Tensor, lse_row: Tensor, lse_col: Tensor, grad_loss: Tensor, inv_tau: float,
                reduce_mean: bool) -> Tuple[Tensor, Tensor]:

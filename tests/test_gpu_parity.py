@@ -747,3 +747,27 @@ def test_softmax_grad_gemm_dual_random_shapes(pg, cuda_device, monkeypatch):
         sx = F.softmax_grad_gemm(x, y, 1.0, row=row, col=col)
         sy = F.softmax_grad_gemm(y, x, 1.0, row=col, col=row)
         assert rel(ox, sx) < 1e-3 and rel(oy, sy) < 1e-3, (i, mx, my, k, mode)
+
+
+@pytest.mark.parametrize("B,D", [(8, 512), (64, 512), (128, 256), (33, 128), (1, 384), (100, 512)])
+@pytest.mark.parametrize("tau,mean", [(0.07, True), (0.5, False)])
+def test_ntxent_small_single_launch(pg, cuda_device, B, D, tau, mean):
+    """The one-launch small-batch NT-Xent (trainer batch 8, cfg1 batch 64) against the float64 oracle: loss, both LSE
+    vectors and the gradients; and through losses.ContrastiveLoss with a non-unit upstream gradient."""
+    from preference_guided_image_captioning_alignment_b200 import functional as F
+    dev = cuda_device
+    g = torch.Generator().manual_seed(B * 7 + D)
+    a = bf16r(torch.nn.functional.normalize(torch.randn(B, D, generator=g), dim=-1))
+    b = bf16r(torch.nn.functional.normalize(a + 0.3 * torch.randn(B, D, generator=g), dim=-1))
+    o = cf.ntxent(a.double().numpy(), b.double().numpy(), tau, normalize=False, clamp_tau=False,
+                  reduction="mean" if mean else "sum")
+    assert F.ntxent_small_supported(B, D)
+    loss, lr, lc, da, db = F.ntxent_small(a.to(dev).to(torch.bfloat16), b.to(dev).to(torch.bfloat16), 1.0 / tau, mean)
+    assert loss_close(loss.item(), o["loss"], 1.0 / tau)
+    assert rel(da, o["dx"]) < GRAD_RTOL and rel(db, o["dy"]) < GRAD_RTOL
+    z = (a.double() @ b.double().T) / tau
+    assert rel(lr, torch.logsumexp(z, 1)) < 1e-5 and rel(lc, torch.logsumexp(z, 0)) < 1e-5
+    if mean:
+        ag, bg = a.to(dev).requires_grad_(True), b.to(dev).requires_grad_(True)
+        (3.0 * pg.ContrastiveLoss(temperature=tau)(ag, bg)).backward()
+        assert rel(ag.grad, 3.0 * o["dx"]) < GRAD_RTOL and rel(bg.grad, 3.0 * o["dy"]) < GRAD_RTOL
