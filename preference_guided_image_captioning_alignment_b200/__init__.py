@@ -6,7 +6,7 @@ Drop-in for the loss-head hot path of A-SHOJAEI/preference-guided-image-captioni
     components.ContrastiveLoss / DPOPreferenceLoss /
         TemperatureScaledSimilarity / compute_sequence_logprobs   <- pkg/models/components.py
     components.FusedDPOHead / lmhead_sequence_logprobs      hidden-state level: logits never materialised
-    graphs.GraphedDPOStep                                   one CUDA-graph launch per head step (forward + backward)
+    graphs.GraphedDPOStep / GraphedContrastiveStep          one or two CUDA-graph launches per head step (forward + backward)
     distributed.global_ntxent / GlobalContrastiveLoss       NT-Xent with negatives from every rank
     install()                                               rebinds the reference's names to the above
 
@@ -16,11 +16,11 @@ CPU or PyTorch fallback: on a machine without a B200 the ops raise.
 from . import _lib  # noqa: F401  (ctypes binding; the library itself is loaded on first use)
 from .components import (DPOPreferenceLoss, FusedDPOHead, NaNSafeGradientNorm, TemperatureScaledSimilarity,  # noqa: F401
                          compute_sequence_logprobs, lmhead_sequence_logprobs)
-from .graphs import GraphedDPOStep  # noqa: F401
+from .graphs import GraphedContrastiveStep, GraphedDPOStep  # noqa: F401
 from .install import install, uninstall  # noqa: F401
 from .losses import ContrastiveLoss, LazyLogits, PreferenceLoss  # noqa: F401
 
 __all__ = ["ContrastiveLoss", "PreferenceLoss", "DPOPreferenceLoss", "FusedDPOHead", "TemperatureScaledSimilarity",
-           "compute_sequence_logprobs", "lmhead_sequence_logprobs", "LazyLogits", "GraphedDPOStep", "NaNSafeGradientNorm",
+           "compute_sequence_logprobs", "lmhead_sequence_logprobs", "LazyLogits", "GraphedDPOStep", "GraphedContrastiveStep", "NaNSafeGradientNorm",
            "install",
            "uninstall"]

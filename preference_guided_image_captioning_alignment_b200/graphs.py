@@ -80,3 +80,40 @@ class GraphedDPOStep:
         """launch() and return the loss as a device tensor (no host synchronisation)."""
         self.launch()
         return self.loss
+
+
+class GraphedContrastiveStep:
+    """CUDA-graph capture of a contrastive-loss step (forward + backward of `loss_module(a, b)`), for the small batches
+    the Stage-1 trainer uses: through the eager module API the step costs ~230 us of host time (custom-op dispatch,
+    casts, autograd) around ~10 us of device time; replayed it is one `cudaGraphLaunch`.
+
+        step = GraphedContrastiveStep(pg.ContrastiveLoss(temperature=0.07), image_embeddings_like, text_embeddings_like)
+        step.copy_inputs(image_embeddings, text_embeddings)
+        loss = step.replay()                 # device tensor; step.da / step.db hold the gradients
+    """
+
+    def __init__(self, loss_module, a: torch.Tensor, b: torch.Tensor, warmup: int = 2):
+        if not a.is_cuda:
+            raise RuntimeError("GraphedContrastiveStep needs CUDA tensors (there is no CPU path)")
+        self.loss_module = loss_module
+        self.a = a.detach().clone().requires_grad_(True)
+        self.b = b.detach().clone().requires_grad_(True)
+        side = torch.cuda.Stream(device=a.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):
+                torch.autograd.grad(self.loss_module(self.a, self.b), (self.a, self.b))
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self.loss_module(self.a, self.b)
+            self.da, self.db = torch.autograd.grad(self.loss, (self.a, self.b))
+
+    def copy_inputs(self, a, b):
+        with torch.no_grad():
+            self.a.copy_(a, non_blocking=True)
+            self.b.copy_(b, non_blocking=True)
+
+    def replay(self) -> torch.Tensor:
+        self.graph.replay()
+        return self.loss

@@ -771,3 +771,21 @@ def test_ntxent_small_single_launch(pg, cuda_device, B, D, tau, mean):
         ag, bg = a.to(dev).requires_grad_(True), b.to(dev).requires_grad_(True)
         (3.0 * pg.ContrastiveLoss(temperature=tau)(ag, bg)).backward()
         assert rel(ag.grad, 3.0 * o["dx"]) < GRAD_RTOL and rel(bg.grad, 3.0 * o["dy"]) < GRAD_RTOL
+
+
+def test_graphed_contrastive_step(pg, cuda_device):
+    """GraphedContrastiveStep replays to the eager result of both NT-Xent flavours, also after new inputs are copied in."""
+    from preference_guided_image_captioning_alignment_b200 import components
+    dev = cuda_device
+    g = torch.Generator().manual_seed(5)
+    for mod, B in ((pg.ContrastiveLoss(temperature=0.07), 8), (components.ContrastiveLoss(temperature=0.5), 64)):
+        xs = [torch.nn.functional.normalize(torch.randn(B, 512, generator=g), dim=-1).to(dev) for _ in range(4)]
+        step = pg.GraphedContrastiveStep(mod, xs[0], xs[1])
+        for a, b in ((xs[0], xs[1]), (xs[2], xs[3])):
+            step.copy_inputs(a, b)
+            loss = step.replay()
+            ag, bg = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+            ref = mod(ag, bg)
+            ref.backward()
+            assert loss.item() == pytest.approx(ref.item(), rel=1e-6)
+            assert torch.equal(step.da, ag.grad) and torch.equal(step.db, bg.grad)

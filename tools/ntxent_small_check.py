@@ -38,10 +38,15 @@ for B, D in ((8, 512), (64, 512), (128, 512)):
         a.grad = b.grad = None
         ops.ntxent(a, b, 2.0, True)[0].backward()
 
+    gstep = pg.GraphedContrastiveStep(pg.ContrastiveLoss(temperature=0.5), a.detach(), b.detach())
+
+    def module_graphed():
+        return gstep.replay()
+
     l1 = small_kernel()
     module_small()
     ga = a.grad.clone()
     module_general()
     rel = ((ga - a.grad).norm() / a.grad.norm()).item()
     print(f"B={B} D={D}: kernel alone {timed(small_kernel):.1f} us; module fwd+bwd small {timed(module_small):.1f} us, "
-          f"general {timed(module_general):.1f} us; grad rel diff small vs general {rel:.1e}; loss {l1[0].item():.5f}", flush=True)
+          f"general {timed(module_general):.1f} us, graphed {timed(module_graphed):.1f} us; grad rel diff small vs general {rel:.1e}; loss {l1[0].item():.5f}", flush=True)
