@@ -195,6 +195,42 @@ int pgica_lmhead_logprob_bwd_scatter(const void* hidden, const void* weight, con
                                      int64_t rows_per_owner, void* tmaps_device, void* workspace,
                                      size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Stage-2 head on COMPACTED rows.  Rows whose mask weight is zero, and the never-scored last position of every
+ * sequence, add nothing to the loss or to any gradient (log_probs * mask, pkg/models/model.py:1081-1083,
+ * pkg/models/components.py:355-358; closed form SURVEY.md Appendix A), and with the reference's tokenisation
+ * (padding="max_length", 128 positions, 10-20 real tokens, pkg/data/preprocessing.py:223-231) they are > 80 % of a real
+ * batch.  The caller builds the list of scored rows, gathers them into a dense bf16 [n][d] matrix (one or more
+ * sequence sets, e.g. preferred ++ rejected, may share the matrix), runs pgica_gemm_lse on it for the forward and
+ * pgica_lmhead_rows_bwd for both gradients, and scatters the per-row results back:
+ *
+ *   pgica_compact_rows      index[0..count) = ascending rows r with row_weight[r] != 0 (NaN counts as scored, so an
+ *                           unmasked out-of-vocabulary label still poisons its sequence); count is a DEVICE int32 —
+ *                           the one value the host has to read to size the launches that follow.
+ *   pgica_gather_rows_bf16  dst[i][:] = bf16(src[index[i]][:]) (src fp32 or bf16; d % 8 == 0), and, when label_in !=
+ *                           NULL, label_out[i] = label_in[index[i]].
+ *   pgica_gather_u32        dst[i] = src[index[i]] for 4-byte elements (the per-row backward coefficients).
+ *   pgica_scatter_u32       dst[0..dst_n) = 0, then dst[index[i]] = src[i] (lse / target logit back to [nseq*seqlen]).
+ *   pgica_scatter_rows      dst[0..dst_rows)[:] = 0, then dst[index[i]][:] = src[i][:] (dhidden back in place, in the
+ *                           caller's dtype): masked rows get the exact zero gradient the reference gives them.
+ *   pgica_lmhead_rows_bwd   dhidden[n][d] and/or dweight[vocab][d] from prepared per-row statistics: lse[i],
+ *                           ncoef[i] = -dLoss/dlogp_i, row_label[i]; dZ = ncoef * (softmax - onehot).  The dual
+ *                           kernel when both are wanted and d % 512 == 0, else one launch per product.  Workspace:
+ *                           pgica_lmhead_rows_workspace_bytes().
+ * ---------------------------------------------------------------------------------------------- */
+int pgica_compact_rows(const float* row_weight, int64_t rows, int32_t* index, int32_t* count, void* stream);
+int pgica_gather_rows_bf16(const void* src, int src_is_bf16, const int32_t* index, int64_t n, int64_t d,
+                           void* dst_bf16, const int32_t* label_in, int32_t* label_out, void* stream);
+int pgica_gather_u32(const void* src, const int32_t* index, int64_t n, void* dst, void* stream);
+int pgica_scatter_u32(const void* src, const int32_t* index, int64_t n, void* dst, int64_t dst_n, void* stream);
+int pgica_scatter_rows(const void* src, int src_is_bf16, const int32_t* index, int64_t n, int64_t d, void* dst,
+                       int dst_is_bf16, int64_t dst_rows, void* stream);
+int pgica_lmhead_rows_workspace_bytes(int64_t rows, int64_t d, int64_t vocab, size_t* bytes_host);
+int pgica_lmhead_rows_bwd(const void* hidden, const void* weight, const int32_t* row_label, const float* lse,
+                          const float* ncoef, int64_t rows, int64_t d, int64_t vocab, void* dhidden,
+                          int dhidden_is_bf16, void* dweight, int dweight_is_bf16, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
 /* DPOPreferenceLoss.forward (pkg/models/components.py:192-249) and the tail of PreferenceLoss.forward
  * (pkg/models/model.py:1046-1048) on n local pairs of an n_global-pair batch (n_global = n on one GPU):
  *   x = beta*((pc-pr) - (rc-rr)),  loss = sum(-logsigmoid(x))/n_global  (label smoothing: cDPO form)

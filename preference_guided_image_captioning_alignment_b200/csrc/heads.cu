@@ -47,6 +47,36 @@ int pgica_lmhead_logprob_fwd(const void* hidden, const void* weight, const int64
   return pgica_seq_reduce(lse, ztgt, row_weight, nseq, seqlen, length_normalize, seq_logp, nll_sum, stream);
 }
 
+int pgica_lmhead_rows_workspace_bytes(int64_t rows, int64_t d, int64_t vocab, size_t* bytes_host) {
+  return pgica_lmhead_logprob_workspace_bytes(rows, 1, d, vocab, bytes_host);
+}
+
+int pgica_lmhead_rows_bwd(const void* hidden, const void* weight, const int32_t* row_label, const float* lse,
+                          const float* ncoef, int64_t rows, int64_t d, int64_t vocab, void* dhidden,
+                          int dhidden_is_bf16, void* dweight, int dweight_is_bf16, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  PGICA_REQUIRE(hidden && weight && row_label && lse && ncoef, "lmhead_rows_bwd: null pointer");
+  PGICA_REQUIRE(dhidden || dweight, "lmhead_rows_bwd: nothing to compute");
+  if (dhidden && dweight && sggf_supported(rows, vocab, d) && workspace && workspace_bytes >= sggf_workspace_bytes() &&
+      (!dweight_is_bf16 || sggf_single_chunk(rows, vocab, d)))
+    // both gradients from one recomputation of the logits (sgg_f.cu)
+    return pgica_softmax_grad_gemm_dual(hidden, weight, rows, vocab, d, 1.0f, lse, ncoef, row_label, nullptr, nullptr,
+                                        nullptr, dhidden, dhidden_is_bf16, dweight, dweight_is_bf16, workspace,
+                                        workspace_bytes, stream);
+  int rc;
+  if (dhidden) {
+    rc = pgica_softmax_grad_gemm(hidden, weight, rows, vocab, d, 1.0f, lse, ncoef, row_label, nullptr, nullptr,
+                                 nullptr, dhidden, dhidden_is_bf16, workspace, workspace_bytes, stream);
+    if (rc != PGICA_OK) return rc;
+  }
+  if (dweight) {
+    rc = pgica_softmax_grad_gemm(weight, hidden, vocab, rows, d, 1.0f, nullptr, nullptr, nullptr, lse, ncoef,
+                                 row_label, dweight, dweight_is_bf16, workspace, workspace_bytes, stream);
+    if (rc != PGICA_OK) return rc;
+  }
+  return PGICA_OK;
+}
+
 int pgica_lmhead_logprob_bwd(const void* hidden, const void* weight, const int32_t* row_label,
                              const float* row_weight, const float* lse, const float* grad_seq, int64_t nseq,
                              int64_t seqlen, int64_t d, int64_t vocab, int length_normalize, void* dhidden,
@@ -65,23 +95,8 @@ int pgica_lmhead_logprob_bwd(const void* hidden, const void* weight, const int32
   const size_t xws_bytes = xws ? workspace_bytes - coef_bytes : 0;
   int rc = pgica_row_coef(grad_seq, row_weight, nseq, seqlen, length_normalize, -1.0f, ncoef, stream);
   if (rc != PGICA_OK) return rc;
-  if (dhidden && dweight && sggf_supported(rows, vocab, d) && xws_bytes >= sggf_workspace_bytes() &&
-      (!dweight_is_bf16 || sggf_single_chunk(rows, vocab, d)))
-    // both gradients from one recomputation of the logits (sgg_f.cu)
-    return pgica_softmax_grad_gemm_dual(hidden, weight, rows, vocab, d, 1.0f, lse, ncoef, row_label, nullptr, nullptr,
-                                        nullptr, dhidden, dhidden_is_bf16, dweight, dweight_is_bf16, xws, xws_bytes,
-                                        stream);
-  if (dhidden) {
-    rc = pgica_softmax_grad_gemm(hidden, weight, rows, vocab, d, 1.0f, lse, ncoef, row_label, nullptr, nullptr,
-                                 nullptr, dhidden, dhidden_is_bf16, xws, xws_bytes, stream);
-    if (rc != PGICA_OK) return rc;
-  }
-  if (dweight) {
-    rc = pgica_softmax_grad_gemm(weight, hidden, vocab, rows, d, 1.0f, nullptr, nullptr, nullptr, lse, ncoef,
-                                 row_label, dweight, dweight_is_bf16, xws, xws_bytes, stream);
-    if (rc != PGICA_OK) return rc;
-  }
-  return PGICA_OK;
+  return pgica_lmhead_rows_bwd(hidden, weight, row_label, lse, ncoef, rows, d, vocab, dhidden, dhidden_is_bf16,
+                               dweight, dweight_is_bf16, xws, xws_bytes, stream);
 }
 
 int pgica_lmhead_logprob_bwd_scatter(const void* hidden, const void* weight, const int32_t* row_label,

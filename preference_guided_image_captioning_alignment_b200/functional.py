@@ -439,3 +439,150 @@ def grad_norm_clip(grads, max_norm, clip=True):
 
 
 _GRADCLIP_CACHE = {}
+
+
+# ----------------------------------------------------------------------------------------- compacted Stage-2 head
+class CompactRows:
+    """What the forward of the compacted head keeps for the backward (device tensors + host counts)."""
+    __slots__ = ("hidden_c", "label_c", "lse_c", "index", "counts", "row_weight", "shapes", "n", "length_normalize",
+                 "lse", "ztgt")
+
+
+def lmhead_compact_fwd(hiddens, weight_bf16, labels, masks, length_normalize=False):
+    """Sequence log-probs of one or more sequence sets (e.g. preferred, rejected) against ONE LM-head weight, computed
+    on the scored rows only: hiddens[s] (B_s, T_s, d) fp32 or bf16, labels[s] (B_s, T_s), masks[s] (B_s, T_s) or None.
+    The scored rows of all sets are gathered (and cast to bf16) into one dense matrix, so the LM-head GEMM runs once
+    over sum_s n_s rows instead of sum_s B_s*T_s.  One host read (the row counts).  -> ([seq_logp_s], CompactRows)"""
+    _need_cuda(weight_bf16, *hiddens, *labels, *[m for m in masks if m is not None])
+    lib = _lib.load()
+    dev = weight_bf16.device
+    V, d = weight_bf16.shape
+    f32 = dict(dtype=torch.float32, device=dev)
+    nset = len(hiddens)
+    counts_dev = torch.empty(nset, dtype=torch.int32, device=dev)
+    index, row_weight, row_label, shapes, srcs = [], [], [], [], []
+    for s in range(nset):
+        h = hiddens[s]
+        if h.dim() != 3 or h.shape[-1] != d:
+            raise ValueError("lmhead_compact_fwd: hidden (nseq, T, d) expected")
+        if h.dtype not in (torch.float32, torch.bfloat16):
+            h = h.float()
+        h = h.contiguous()
+        nseq, T, _ = h.shape
+        rl, rw = prep_rows(labels[s], masks[s], V)
+        idx = torch.empty(nseq * T, dtype=torch.int32, device=dev)
+        _lib.check(lib.pgica_compact_rows(_p(rw), nseq * T, _p(idx), ctypes.c_void_p(counts_dev.data_ptr() + 4 * s),
+                                          _stream()))
+        index.append(idx), row_weight.append(rw), row_label.append(rl), shapes.append((nseq, T)), srcs.append(h)
+    counts = [int(c) for c in counts_dev.tolist()]  # the one device->host read of the compacted path
+    n = sum(counts)
+    ctx = CompactRows()
+    ctx.index, ctx.counts, ctx.row_weight, ctx.shapes, ctx.n = index, counts, row_weight, shapes, n
+    ctx.length_normalize = bool(length_normalize)
+    ctx.hidden_c = torch.empty(max(n, 1), d, dtype=torch.bfloat16, device=dev)
+    ctx.label_c = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    ctx.lse_c = torch.zeros(max(n, 1), **f32)
+    ztgt_c = torch.zeros(max(n, 1), **f32)
+    off = 0
+    for s in range(nset):
+        if counts[s]:
+            _lib.check(lib.pgica_gather_rows_bf16(_p(srcs[s]), 1 if srcs[s].dtype == torch.bfloat16 else 0,
+                                                  _p(index[s]), counts[s], d,
+                                                  ctypes.c_void_p(ctx.hidden_c.data_ptr() + 2 * d * off),
+                                                  _p(row_label[s]), ctypes.c_void_p(ctx.label_c.data_ptr() + 4 * off),
+                                                  _stream()))
+        off += counts[s]
+    if n:
+        need = ctypes.c_size_t(0)
+        _lib.check(lib.pgica_gemm_lse_workspace_bytes(n, V, d, ctypes.byref(need)))
+        ws = _ws(need.value, dev)
+        _lib.check(lib.pgica_gemm_lse(_p(ctx.hidden_c), _p(weight_bf16), n, V, d, 1.0, _p(ctx.label_c), 0,
+                                      _p(ctx.lse_c), _p(ztgt_c), _p(ws), need.value, _stream()))
+    seqs, off = [], 0
+    ctx.lse, ctx.ztgt = [], []
+    for s in range(nset):
+        nseq, T = shapes[s]
+        lse = torch.empty(nseq * T, **f32)
+        ztgt = torch.empty(nseq * T, **f32)
+        for src, dst in ((ctx.lse_c, lse), (ztgt_c, ztgt)):
+            _lib.check(lib.pgica_scatter_u32(ctypes.c_void_p(src.data_ptr() + 4 * off), _p(index[s]), counts[s],
+                                             _p(dst), nseq * T, _stream()))
+        seqs.append(seq_reduce(lse, ztgt, row_weight[s], nseq, T, length_normalize))
+        ctx.lse.append(lse), ctx.ztgt.append(ztgt)
+        off += counts[s]
+    return seqs, ctx
+
+
+def lmhead_compact_bwd(ctx, weight_bf16, grad_seqs, need_dhidden=True, need_dweight=True, dhidden_dtypes=None,
+                       dweight_dtype=torch.float32):
+    """Backward of lmhead_compact_fwd: ONE dual-kernel launch over the compacted rows of all sequence sets.
+    -> ([dhidden_s] in the (B_s, T_s, d) layout, zeros at unscored rows; dweight (V, d))"""
+    lib = _lib.load()
+    dev = weight_bf16.device
+    V, d = weight_bf16.shape
+    n, nset = ctx.n, len(ctx.shapes)
+    dhidden_dtypes = dhidden_dtypes or [torch.float32] * nset
+    if n == 0:
+        dhs = [torch.zeros(ns, T, d, dtype=dt, device=dev) for (ns, T), dt in zip(ctx.shapes, dhidden_dtypes)]
+        return (dhs if need_dhidden else None), (torch.zeros(V, d, dtype=dweight_dtype, device=dev)
+                                                 if need_dweight else None)
+    ncoef_c = torch.empty(n, dtype=torch.float32, device=dev)
+    off = 0
+    for s in range(nset):
+        nseq, T = ctx.shapes[s]
+        coef = row_coef(grad_seqs[s], ctx.row_weight[s], nseq, T, ctx.length_normalize, -1.0)
+        _lib.check(lib.pgica_gather_u32(_p(coef), _p(ctx.index[s]), ctx.counts[s],
+                                        ctypes.c_void_p(ncoef_c.data_ptr() + 4 * off), _stream()))
+        off += ctx.counts[s]
+    # the compacted dhidden is fp32 when any consumer wants fp32 (the trainer's hidden states are fp32)
+    dhc_dtype = torch.bfloat16 if all(dt == torch.bfloat16 for dt in dhidden_dtypes) else torch.float32
+    dhc = torch.empty(n, d, dtype=dhc_dtype, device=dev) if need_dhidden else None
+    dw = torch.empty(V, d, dtype=dweight_dtype, device=dev) if need_dweight else None
+    need = ctypes.c_size_t(0)
+    _lib.check(lib.pgica_lmhead_rows_workspace_bytes(n, d, V, ctypes.byref(need)))
+    ws = _ws(need.value, dev)
+    _lib.check(lib.pgica_lmhead_rows_bwd(_p(ctx.hidden_c), _p(weight_bf16), _p(ctx.label_c), _p(ctx.lse_c), _p(ncoef_c),
+                                         n, d, V, _p(dhc), 1 if dhc_dtype == torch.bfloat16 else 0, _p(dw),
+                                         1 if dweight_dtype == torch.bfloat16 else 0, _p(ws), ws.numel(), _stream()))
+    dhs = None
+    if need_dhidden:
+        dhs, off = [], 0
+        for s in range(nset):
+            nseq, T = ctx.shapes[s]
+            dh = torch.empty(nseq, T, d, dtype=dhidden_dtypes[s], device=dev)
+            _lib.check(lib.pgica_scatter_rows(ctypes.c_void_p(dhc.data_ptr() + dhc.element_size() * d * off),
+                                              1 if dhc_dtype == torch.bfloat16 else 0, _p(ctx.index[s]),
+                                              ctx.counts[s], d, _p(dh), 1 if dh.dtype == torch.bfloat16 else 0,
+                                              nseq * T, _stream()))
+            dhs.append(dh)
+            off += ctx.counts[s]
+    return dhs, dw
+
+
+# ----------------------------------------------------------------------------------------- device guard
+def _device_guard(fn):
+    """Run `fn` with the device of its first CUDA tensor argument current: the stream handed to the C ABI
+    (`_stream()`) and every allocation then belong to the tensors' device, whatever device the caller had selected."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = None
+        for a in args:
+            if isinstance(a, (list, tuple)) and a:
+                a = a[0]
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                dev = a.device
+                break
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
+for _name, _fn in list(globals().items()):
+    if callable(_fn) and getattr(_fn, "__module__", None) == __name__ and not _name.startswith("_") \
+            and _name not in ("mask_kind", "ntxent_small_supported", "CompactRows"):
+        globals()[_name] = _device_guard(_fn)
+del _name, _fn

@@ -9,10 +9,13 @@ What is rebound:
     PreferenceGuidedTrainer.__init__ resolves at pkg/training/trainer.py:204-209.
   * `ContrastiveLoss`, `DPOPreferenceLoss`, `TemperatureScaledSimilarity`, `compute_sequence_logprobs` in
     pkg.models.components.
-  * with fuse_lm_head=True, every CaptionDecoder built afterwards gets its GPT-2 `lm_head` wrapped so that the
-    training forward (pkg/models/model.py:604-610) returns a LazyLogits handle instead of the (B, T, V) tensor, and
-    the HF causal-LM loss that forward computes from `labels` (modeling_gpt2.py:709-716) is taken from the same
-    fused kernel.  Generation (model.py:621-678) keeps dense logits.
+  * with fuse_lm_head=True, every CaptionDecoder built afterwards (and every one passed to `fuse_decoder`) gets the
+    `forward` of its GPT-2 `lm_head` Linear rebound on the instance, so that the training forward
+    (pkg/models/model.py:604-610) returns a LazyLogits handle instead of the (B, T, V) tensor; the HF causal-LM loss
+    that forward computes from `labels` (modeling_gpt2.py:709-716) becomes a deferred value taken from the same fused
+    kernel if anybody reads it.  The module tree and the state_dict keys do not change (checkpoints stay
+    interchangeable, pkg/training/trainer.py:795,845); under LoRA the GPT2LMHeadModel inside the PeftModel is the one
+    patched.  Generation (model.py:621-678) keeps dense logits.
 `python -m preference_guided_image_captioning_alignment_b200.install script.py [args...]` runs a script
 (e.g. the reference's scripts/train.py) with the swap applied.
 """
@@ -20,6 +23,8 @@ import importlib
 import runpy
 import sys
 import threading
+import types
+import weakref
 
 import torch
 import torch.nn as nn
@@ -29,34 +34,36 @@ from . import components, losses, ops
 REFERENCE_PACKAGE = "preference_guided_image_captioning_alignment"
 _originals = {}
 _lazy = threading.local()
+_patched = []  # instance-level patches (weak references), undone by uninstall()
+_MISSING = object()
 
 
-class LazyLMHead(nn.Module):
-    """Wraps the original bias-free nn.Linear (whose weight stays the Parameter tied to wte)."""
-
-    def __init__(self, linear: nn.Linear):
-        super().__init__()
-        if getattr(linear, "bias", None) is not None:
-            raise ValueError("fused LM head expects a bias-free lm_head (GPT-2)")
-        self.linear = linear
-
-    @property
-    def weight(self):
-        return self.linear.weight
-
-    def forward(self, hidden):
-        if getattr(_lazy, "on", False) and hidden.is_cuda and hidden.dim() == 3 and hidden.shape[1] > 1:
-            return losses.LazyLogits(hidden, self.linear.weight)
-        return self.linear(hidden)
+def _lazy_linear_forward(self, hidden):
+    """Replacement `forward` of the GPT-2 `lm_head` Linear (bound on the INSTANCE, so the module tree, the
+    state_dict keys and HF's weight tying are untouched): inside a training / validation forward of CaptionDecoder the
+    (B, T, d) hidden states are handed on as a LazyLogits handle; everywhere else (generation, CPU, 2-D inputs) the
+    Linear runs as usual."""
+    if getattr(_lazy, "on", False) and hidden.dim() == 3 and hidden.shape[1] > 1 and self.bias is None \
+            and (hidden.is_cuda or getattr(_lazy, "any_device", False)):  # any_device: host-logic tests only
+        return losses.LazyLogits(hidden, self.weight)
+    return nn.functional.linear(hidden, self.weight, self.bias)
 
 
 def lazy_causal_lm_loss(logits, labels, vocab_size=None, num_items_in_batch=None, ignore_index=-100, **kwargs):
     """Stand-in for transformers' ForCausalLMLoss (loss_utils.py:45-67): mean over shifted positions whose label
-    is not ignore_index of -log p; LazyLogits go through the fused kernel, tensors through the stock path."""
+    is not ignore_index of -log p.  Tensors go through the stock path; for LazyLogits the value is DEFERRED
+    (losses.DeferredLoss): the Stage-2 trainer never reads `generation_loss`, and computing it means an LM-head
+    pass over every position, pads included.  When somebody does read it, it comes from the fused kernel."""
     if not isinstance(logits, losses.LazyLogits):
         from transformers.loss.loss_utils import ForCausalLMLoss
         return ForCausalLMLoss(logits, labels, vocab_size, num_items_in_batch=num_items_in_batch,
                                ignore_index=ignore_index, **kwargs)
+    return losses.DeferredLoss(lambda: causal_lm_loss_now(logits, labels, num_items_in_batch, ignore_index),
+                               logits.device)
+
+
+def causal_lm_loss_now(logits, labels, num_items_in_batch=None, ignore_index=-100):
+    """The HF causal-LM loss of a LazyLogits handle, evaluated immediately (fused kernel, no logits)."""
     valid = (labels != ignore_index)
     safe = torch.where(valid, labels, torch.zeros_like(labels))
     seq = ops.lmhead_seq_logprob(logits.hidden, logits.weight, safe, valid, False)[0]
@@ -64,13 +71,48 @@ def lazy_causal_lm_loss(logits, labels, vocab_size=None, num_items_in_batch=None
     return -seq.sum() / denom
 
 
+def resolve_causal_lm(lm):
+    """The module that owns `lm_head` and calls `self.loss_function`: `lm` itself, or — when LoRA is configured and
+    CaptionDecoder.lm_model is a PeftModel (pkg/models/model.py:538-558) — the GPT2LMHeadModel inside the wrappers."""
+    seen = set()
+    while id(lm) not in seen:
+        seen.add(id(lm))
+        if hasattr(lm, "get_base_model") and callable(lm.get_base_model):
+            inner = lm.get_base_model()
+        elif hasattr(lm, "base_model") and hasattr(lm.base_model, "model") and lm.base_model is not lm:
+            inner = lm.base_model.model
+        else:
+            break
+        if inner is None or inner is lm:
+            break
+        lm = inner
+    return lm
+
+
 def fuse_decoder(decoder):
-    """Wrap decoder.lm_model.lm_head / loss_function in place (idempotent).  `decoder` is a CaptionDecoder."""
-    lm = decoder.lm_model
+    """Make `decoder.lm_model`'s LM head lazy in place (idempotent).  `decoder` is a CaptionDecoder.  Nothing is added
+    to or renamed in the module tree: checkpoints written before and after install() are interchangeable."""
+    lm = resolve_causal_lm(decoder.lm_model)
     head = lm.get_output_embeddings() if hasattr(lm, "get_output_embeddings") else lm.lm_head
-    if not isinstance(head, LazyLMHead):
-        lm.lm_head = LazyLMHead(head)
-    lm.loss_function = lazy_causal_lm_loss
+    if head is None or not isinstance(head, nn.Linear):
+        raise TypeError(f"fused LM head expects an nn.Linear output embedding, found {type(head).__name__}")
+    if getattr(head, "bias", None) is not None:
+        raise ValueError("fused LM head expects a bias-free lm_head (GPT-2)")
+    if "forward" not in head.__dict__:
+        head.forward = types.MethodType(_lazy_linear_forward, head)
+        _patched.append((weakref.ref(head), "forward"))
+    if getattr(lm, "_loss_function", None) is not lazy_causal_lm_loss:
+        _patched.append((weakref.ref(lm), "_loss_function", getattr(lm, "__dict__", {}).get("_loss_function", _MISSING)))
+        lm.loss_function = lazy_causal_lm_loss
+    return decoder
+
+
+def unfuse_decoder(decoder):
+    lm = resolve_causal_lm(decoder.lm_model)
+    head = lm.get_output_embeddings() if hasattr(lm, "get_output_embeddings") else lm.lm_head
+    head.__dict__.pop("forward", None)
+    if getattr(lm, "_loss_function", None) is lazy_causal_lm_loss:
+        del lm._loss_function
     return decoder
 
 
@@ -137,6 +179,18 @@ def uninstall():
         if name == "forward":
             owner._pgica_wrapped = False
     _originals.clear()
+    for rec in _patched:
+        obj = rec[0]()
+        if obj is None:
+            continue
+        if rec[1] == "forward":
+            obj.__dict__.pop("forward", None)
+        elif rec[1] == "_loss_function" and obj.__dict__.get("_loss_function") is lazy_causal_lm_loss:
+            if rec[2] is _MISSING:
+                del obj.__dict__["_loss_function"]
+            else:
+                obj.__dict__["_loss_function"] = rec[2]
+    _patched.clear()
 
 
 def main(argv=None):

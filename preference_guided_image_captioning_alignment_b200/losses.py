@@ -26,7 +26,6 @@ class LazyLogits:
     def __init__(self, hidden: torch.Tensor, weight: torch.Tensor):
         self.hidden = hidden
         self.weight = weight
-        self._cache = {}
 
     @property
     def shape(self):
@@ -46,11 +45,48 @@ class LazyLogits:
     def dim(self):
         return self.hidden.dim()
 
+    def float(self):
+        return self
+
     def materialize(self) -> torch.Tensor:
         return torch.nn.functional.linear(self.hidden, self.weight)
 
     def seq_logprobs(self, labels, mask, length_normalize):
-        return ops.lmhead_seq_logprob(self.hidden, self.weight, labels, mask, length_normalize)[0]
+        return ops.lmhead_seq_logprob_compact([self.hidden], self.weight, [labels], [mask], length_normalize)[0]
+
+
+class DeferredLoss(torch.Tensor):
+    """A 0-dim loss that is computed the first time anybody looks at it.
+
+    `CaptionDecoder.forward` passes `labels` to GPT-2, so HF computes the causal-LM cross-entropy on every forward
+    (modeling_gpt2.py:709-716) and the reference model returns it as `generation_loss` (pkg/models/model.py:849-851) —
+    but the Stage-2 trainer never reads it (pkg/training/trainer.py:575-603): on the reference that costs a full
+    log-softmax over (B, T, V) per forward; here it would cost an LM-head GEMM over ALL rows, pads included, that the
+    compacted preference loss does not need.  The fused LM head therefore hands HF's `loss_function` result back as
+    this placeholder; any torch function applied to it (`.item()`, `.backward()`, arithmetic, printing, ...) first
+    evaluates the real loss — with the autograd graph it would have had — and continues on that tensor."""
+
+    @staticmethod
+    def __new__(cls, thunk, device):
+        t = torch.Tensor._make_subclass(cls, torch.empty((), device=device))
+        t._thunk = thunk
+        t._value = None
+        t._grad_mode = torch.is_grad_enabled()
+        return t
+
+    def materialize(self) -> torch.Tensor:
+        if self._value is None:
+            with torch.set_grad_enabled(self._grad_mode):
+                self._value = self._thunk()
+            self._thunk = None
+        return self._value
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        from torch.utils._pytree import tree_map
+        real = lambda x: x.materialize() if isinstance(x, DeferredLoss) else x
+        with torch._C.DisableTorchFunctionSubclass():
+            return func(*tree_map(real, args), **tree_map(real, kwargs or {}))
 
 
 class ContrastiveLoss(nn.Module):
@@ -79,8 +115,16 @@ class PreferenceLoss(nn.Module):
     def forward(self, preferred_logits, rejected_logits, preferred_labels: torch.Tensor,
                 rejected_labels: torch.Tensor, preferred_mask: torch.Tensor,
                 rejected_mask: torch.Tensor) -> torch.Tensor:
-        lw = self._compute_log_probs(preferred_logits, preferred_labels, preferred_mask)
-        ll = self._compute_log_probs(rejected_logits, rejected_labels, rejected_mask)
+        if (isinstance(preferred_logits, LazyLogits) and isinstance(rejected_logits, LazyLogits)
+                and preferred_logits.weight is rejected_logits.weight):
+            # both captions in ONE pass over the LM head: scored rows of the two sets gathered into one matrix, one
+            # forward GEMM, one dual backward launch (dW accumulated once), logits never formed
+            lw, ll = ops.lmhead_seq_logprob_compact([preferred_logits.hidden, rejected_logits.hidden],
+                                                    preferred_logits.weight, [preferred_labels, rejected_labels],
+                                                    [preferred_mask, rejected_mask], True)
+        else:
+            lw = self._compute_log_probs(preferred_logits, preferred_labels, preferred_mask)
+            ll = self._compute_log_probs(rejected_logits, rejected_labels, rejected_mask)
         loss, _, _ = ops.dpo_loss(lw, ll, None, None, float(self.beta), 0.0, lw.numel())
         return loss
 

@@ -242,7 +242,7 @@ def lmhead_seq_logprob(hidden: Tensor, weight: Tensor, labels: Tensor, mask: Opt
         raise ValueError("lmhead_seq_logprob: hidden (nseq,T,d) and weight (V,d) expected")
     if tuple(labels.shape) != tuple(hidden.shape[:2]):
         raise ValueError("lmhead_seq_logprob: labels must be (nseq, T)")
-    hb, wb = F.as_bf16(hidden), F.as_bf16(weight)
+    hb, wb = F.as_bf16(hidden), cached_bf16(weight)
     seq, lse, ztgt, rl, rw, _ = F.lmhead_logprob_fwd(hb, wb, labels, mask, length_normalize)
     return seq, lse, ztgt, rl, rw
 
@@ -258,7 +258,7 @@ def _(hidden, weight, labels, mask, length_normalize):
 def lmhead_seq_logprob_bwd(hidden: Tensor, weight: Tensor, row_label: Tensor, row_weight: Tensor, lse: Tensor,
                            grad_seq: Tensor, length_normalize: bool, need_dhidden: bool,
                            need_dweight: bool) -> Tuple[Tensor, Tensor]:
-    hb, wb = F.as_bf16(hidden), F.as_bf16(weight)
+    hb, wb = F.as_bf16(hidden), cached_bf16(weight)
     dh, dw = F.lmhead_logprob_bwd(hb, wb, row_label, row_weight, lse, grad_seq, length_normalize,
                                   need_dhidden=need_dhidden, need_dweight=need_dweight,
                                   dhidden_dtype=_grad_dtype(hidden), dweight_dtype=_grad_dtype(weight))
@@ -392,3 +392,67 @@ def _dpo_backward(ctx, g_loss, g_metrics, g_dpc):
 
 
 dpo_loss.register_autograd(_dpo_backward, setup_context=_dpo_setup)
+
+
+# ============================================================================== LM head on compacted rows
+_BF16_CACHE = {}  # id(weight) -> (weakref, data_ptr, _version, bf16 copy)
+
+
+def cached_bf16(weight: Tensor) -> Tensor:
+    """bf16 operand copy of an fp32 LM-head weight, recast only when the Parameter has been written to (its
+    `_version` moves with every in-place update, i.e. once per optimiser step): the tied wte / lm_head matrix of GPT-2
+    Medium is 206 MB in fp32, and a Stage-2 micro-step would otherwise cast it once per forward and once per backward."""
+    import weakref
+    if weight.dtype == torch.bfloat16:
+        return weight.detach().contiguous()
+    key = id(weight)
+    hit = _BF16_CACHE.get(key)
+    if hit is not None and hit[0]() is weight and hit[1] == weight.data_ptr() and hit[2] == weight._version:
+        return hit[3]
+    copy = F.as_bf16(weight.detach())
+    try:
+        ref = weakref.ref(weight, lambda _r, k=key: _BF16_CACHE.pop(k, None))
+    except TypeError:
+        return copy
+    _BF16_CACHE[key] = (ref, weight.data_ptr(), weight._version, copy)
+    return copy
+
+
+class _LMHeadCompact(torch.autograd.Function):
+    """Sequence log-probs of several sequence sets (preferred, rejected, ...) against one LM-head weight on the scored
+    rows only (functional.lmhead_compact_fwd / _bwd): one forward GEMM and ONE dual backward launch for all sets, so the
+    weight gradient is accumulated once.  A plain autograd.Function: the number of scored rows is read on the host to
+    size the launches, which a shape-static custom op cannot express."""
+
+    @staticmethod
+    def forward(ctx, weight, length_normalize, nset, *rest):
+        hiddens, labels, masks = rest[:nset], rest[nset:2 * nset], rest[2 * nset:3 * nset]
+        wb = cached_bf16(weight)
+        seqs, saved = F.lmhead_compact_fwd(list(hiddens), wb, list(labels), list(masks), length_normalize)
+        ctx.saved, ctx.nset = saved, nset
+        ctx.weight = weight
+        ctx.h_dtypes = [h.dtype for h in hiddens]
+        return tuple(seqs)
+
+    @staticmethod
+    def backward(ctx, *grad_seqs):
+        nset = ctx.nset
+        need_w = ctx.needs_input_grad[0]
+        need_h = any(ctx.needs_input_grad[3:3 + nset])
+        wb = cached_bf16(ctx.weight)
+        gs = [g.contiguous().float() for g in grad_seqs]
+        dts = [dt if dt in (torch.float32, torch.bfloat16) else torch.float32 for dt in ctx.h_dtypes]
+        dhs, dw = F.lmhead_compact_bwd(ctx.saved, wb, gs, need_dhidden=need_h, need_dweight=need_w,
+                                       dhidden_dtypes=dts, dweight_dtype=_grad_dtype(ctx.weight))
+        ctx.saved = None
+        out_h = [None] * nset
+        if need_h:
+            out_h = [dh.to(dt) if ctx.needs_input_grad[3 + s] else None
+                     for s, (dh, dt) in enumerate(zip(dhs, ctx.h_dtypes))]
+        return (dw.to(ctx.weight.dtype) if need_w else None, None, None, *out_h, *([None] * (2 * nset)))
+
+
+def lmhead_seq_logprob_compact(hiddens, weight: Tensor, labels, masks, length_normalize: bool):
+    """[(B_s, T_s, d)] hidden sets, (V, d) weight, [(B_s, T_s)] labels, [(B_s, T_s) or None] masks -> [seq_logp_s]."""
+    nset = len(hiddens)
+    return list(_LMHeadCompact.apply(weight, bool(length_normalize), nset, *hiddens, *labels, *masks))
