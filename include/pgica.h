@@ -49,6 +49,14 @@ int pgica_device_check(void);
 int pgica_sm_count(void);
 /* number of CUDA kernels this library has launched in this process so far */
 int64_t pgica_kernel_launches(void);
+/* Process-wide tuning options (kernel selection / role split).  Defaults are seeded once, at load time, from the
+ * environment variables PGICA_<NAME>; the call path never reads the environment.  Names: "sgg_fused" (1: dual backward
+ * kernel when both gradients are wanted; 0: one launch per product), "sggf_plan_r2" / "sggf_plan_c2" (pin the dual
+ * kernel's role split; 0 = planner), "sggf_coop" (1: cooperative launch, a refused launch is an error; 0: plain
+ * launch), "sggf_spread", "sggf_slots", "sggf_producers_only", "sggf_xprod" (tuning / diagnostics), "sgg_cluster"
+ * (cluster size of the one-product kernel).  set: 0 or PGICA_ERR_INVALID_ARGUMENT; get: INT64_MIN for an unknown name. */
+int pgica_set_option(const char* name, int64_t value);
+int64_t pgica_get_option(const char* name);
 
 /* ------------------------------------------------------------------------------------------------
  * K1/K3 core — tensor-core GEMM with a fused online log-sum-exp + target-gather epilogue.
@@ -78,15 +86,6 @@ int pgica_similarity(const void* a, const void* b, int64_t rows, int64_t cols, i
                      float* lse, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Debug / self-test: one CTA, one 128 x n x k tcgen05 product, D written to `d` (fp32 [128][n]).
- *   b_mn_major = 0: b is [n][k] (K-major);  1: b is [k][n] (MN-major, the layout the backward's second
- *   product reads W / H tiles in).  a_manual = 1 writes the A tile with st.shared through the
- *   sw128 swizzle formula instead of TMA (the way the backward stages its probability tile).
- * ---------------------------------------------------------------------------------------------- */
-int pgica_probe_umma(const void* a, const void* b, int64_t n, int64_t k, int b_mn_major, int a_manual,
-                     uint32_t b_lbo_bytes, uint32_t b_sbo_bytes, float* d, void* stream);
-
-/* ------------------------------------------------------------------------------------------------
  * K2/K4 core — "softmax-gradient GEMM": the backward of both heads, logits recomputed tile-wise.
  *
  *   out[i,:] = sum_j G(i,j) * y[j,:],   z_ij = <x[i,:], y[j,:]>
@@ -99,7 +98,8 @@ int pgica_probe_umma(const void* a, const void* b, int64_t n, int64_t k, int b_m
  * pkg/models/components.py:131-141 (closed forms: SURVEY.md Appendix A).
  * workspace (pgica_softmax_grad_gemm_workspace_bytes, 128-byte aligned): the exchange ring through which the CTAs of
  * a cluster hand each other 128 x 128 bf16 tiles of G (8 tiles per resident cluster, L2-resident, overwritten every
- * 8 tiles).  With workspace == NULL the cluster exchanges tiles over distributed shared memory instead (slower).
+ * 8 tiles).  With workspace == NULL (or k not a multiple of 512) the single-CTA kernel runs, one CTA per
+ * (row block, 256-column slice), each recomputing its own tiles.
  * ---------------------------------------------------------------------------------------------- */
 int pgica_softmax_grad_gemm_workspace_bytes(int64_t mx, int64_t my, int64_t k, size_t* bytes_host);
 int pgica_softmax_grad_gemm(const void* x, const void* y, int64_t mx, int64_t my, int64_t k, float scale,
@@ -126,12 +126,6 @@ int pgica_softmax_grad_gemm_dual_workspace_bytes(int64_t mx, int64_t my, int64_t
  * row pairs per chunk, column pairs per pass, X-holder pairs, Y-holder pairs, producer pairs.  Host arithmetic only. */
 int pgica_softmax_grad_gemm_dual_plan(int64_t mx, int64_t my, int64_t k, int npairs, int single_chunk,
                                       int32_t* plan_host);
-/* Host replay of the dual kernel's tile schedule (the same enumerators the device code runs; test hook, no device):
- * role 0: every quad in production order, 3 ints each (q, row pair, column pair); role 1 / 2: the pair-tiles X- /
- * Y-holder pair `idx` accumulates, 6 ints each (q, sel, row pair, column pair, first-of-period, period).  Returns the
- * number of records (only the first `capacity` are written), -1 on a bad argument. */
-int64_t pgica_debug_dual_schedule(int row_pairs, int col_pairs, int row_pairs_per_chunk, int col_pairs_per_pass,
-                                  int spread, int role, int idx, int32_t* out_host, int64_t capacity);
 int pgica_softmax_grad_gemm_dual(const void* x, const void* y, int64_t mx, int64_t my, int64_t k, float scale,
                                  const float* r_lse, const float* r_coef, const int32_t* r_tgt, const float* c_lse,
                                  const float* c_coef, const int32_t* c_tgt, void* out_x, int out_x_is_bf16,
@@ -278,6 +272,9 @@ int pgica_rownorm_fwd(const void* x, int x_is_bf16, int64_t rows, int64_t dim, f
 int pgica_rownorm_bwd(const void* x, int x_is_bf16, const float* inv_norm, const void* g, int g_is_bf16, int64_t rows,
                       int64_t dim, int64_t g_pitch, int64_t g_second, float* dx, void* stream);
 int pgica_cast_f32_to_bf16(const float* x, int64_t n, void* y_bf16, void* stream);
+/* The same two-term split WITHOUT normalising (inputs used as given, pkg/models/model.py:988): fp32 embeddings that
+ * are not bf16-representable keep ~fp32 accuracy in the similarity.  left3 / right3: bf16 [rows][3*dim]. */
+int pgica_split3_bf16(const float* x, int64_t rows, int64_t dim, void* left3_bf16, void* right3_bf16, void* stream);
 
 /* dst[i] += sum_s srcs[s][i], fp32, n elements (n % 4 == 0, 16-byte aligned pointers), n_src <= 15 sources given as a
  * HOST array of device pointers.  The reduction step of the copy-engine all-reduce of the LM-head weight gradient
@@ -315,6 +312,12 @@ int pgica_logits_grad(const void* logits, int logits_is_bf16, const int32_t* row
 int pgica_ntxent_small_supported(int64_t rows, int64_t dim);
 int pgica_ntxent_small(const void* a, const void* b, int64_t rows, int64_t dim, float inv_tau, int reduce_mean,
                        float* loss, float* lse_row, float* lse_col, float* da, float* db, void* stream);
+/* Same launch for fp32 embeddings given as their bf16 splits (pgica_split3_bf16 / pgica_rownorm_fwd): a_left3 =
+ * [hi|lo|hi], b_right3 = [hi|hi|lo], bf16 [rows][3*dim].  The similarity runs over depth 3*dim (fp32-level accuracy in
+ * the loss, pkg/models/model.py:988 computes it in fp32); the gradient products use the hi parts.  da, db: [rows][dim]. */
+int pgica_ntxent_small_split(const void* a_left3, const void* b_right3, int64_t rows, int64_t dim, float inv_tau,
+                             int reduce_mean, float* loss, float* lse_row, float* lse_col, float* da, float* db,
+                             void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * SURVEY 8(f) row 2 — finite-check + global L2 gradient norm + clip over ALL gradient tensors at once:

@@ -8,6 +8,7 @@ Drop-in for the loss-head hot path of A-SHOJAEI/preference-guided-image-captioni
     components.FusedDPOHead / lmhead_sequence_logprobs      hidden-state level: logits never materialised
     graphs.GraphedDPOStep / GraphedContrastiveStep          one or two CUDA-graph launches per head step (forward + backward)
     distributed.global_ntxent / GlobalContrastiveLoss       NT-Xent with negatives from every rank
+    scoring.compute_similarity / paired_scores              retrieval-style scoring on the similarity kernel
     install()                                               rebinds the reference's names to the above
 
 Everything computes in hand-written CUDA (csrc/, exported through the C ABI in include/pgica.h).  There is no
@@ -18,9 +19,9 @@ from .components import (DPOPreferenceLoss, FusedDPOHead, NaNSafeGradientNorm, T
                          compute_sequence_logprobs, lmhead_sequence_logprobs)
 from .graphs import GraphedContrastiveStep, GraphedDPOStep  # noqa: F401
 from .install import install, uninstall  # noqa: F401
-from .losses import ContrastiveLoss, LazyLogits, PreferenceLoss  # noqa: F401
+from .losses import ContrastiveLoss, DeferredLoss, LazyLogits, PreferenceLoss  # noqa: F401
+from .scoring import compute_similarity, paired_scores, retrieval_ranks  # noqa: F401
 
 __all__ = ["ContrastiveLoss", "PreferenceLoss", "DPOPreferenceLoss", "FusedDPOHead", "TemperatureScaledSimilarity",
            "compute_sequence_logprobs", "lmhead_sequence_logprobs", "LazyLogits", "GraphedDPOStep", "GraphedContrastiveStep", "NaNSafeGradientNorm",
-           "install",
-           "uninstall"]
+           "install", "uninstall", "DeferredLoss", "compute_similarity", "paired_scores", "retrieval_ranks"]

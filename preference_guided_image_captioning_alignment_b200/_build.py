@@ -24,7 +24,7 @@ def _sources():
 
 def _digest():
     h = hashlib.sha256()
-    for f in sorted(os.listdir(CSRC)) + ["../../include/pgica.h"]:
+    for f in sorted(os.listdir(CSRC)) + ["../../include/pgica.h", "../../include/pgica_debug.h"]:
         path = os.path.join(CSRC, f)
         if os.path.isfile(path):
             h.update(f.encode())
@@ -40,12 +40,19 @@ def nvcc_path():
     return nvcc
 
 
+def is_current():
+    """True when libpgica.so exists and was built from the sources as they are now."""
+    try:
+        return os.path.exists(LIB_PATH) and open(_STAMP).read().strip() == _digest()
+    except OSError:
+        return False
+
+
 def build(force=False, verbose=False):
     """Build libpgica.so if sources changed. Returns the library path."""
     digest = _digest()
-    if not force and os.path.exists(LIB_PATH) and os.path.exists(_STAMP):
-        if open(_STAMP).read().strip() == digest:
-            return LIB_PATH
+    if not force and is_current():
+        return LIB_PATH
     nvcc = nvcc_path()
     objdir = os.path.join(_HERE, "build")
     os.makedirs(objdir, exist_ok=True)

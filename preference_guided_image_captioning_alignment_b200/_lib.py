@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # PGICA_LIB_PATH selects another build of the same ABI (tools/ use it for the -DPGICA_TRACE diagnostics build)
 LIB_PATH = os.environ.get("PGICA_LIB_PATH") or os.path.join(_HERE, "libpgica.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "pgica.h")
+DEBUG_HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "pgica_debug.h")  # test / bring-up hooks
 
 _lock = threading.Lock()
 _lib = None
@@ -46,8 +47,14 @@ def _ctype(decl):
     return _SCALARS[base]
 
 
-def parse_header(path=HEADER_PATH):
-    """-> {name: (restype, [argtypes])} for every function prototype in the header."""
+def parse_header(path=None):
+    """-> {name: (restype, [argtypes])} for every function prototype in the header (default: the product ABI plus the
+    debug hooks)."""
+    if path is None:
+        protos = parse_header(HEADER_PATH)
+        if os.path.exists(DEBUG_HEADER_PATH):
+            protos.update(parse_header(DEBUG_HEADER_PATH))
+        return protos
     text = open(path).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     text = re.sub(r"^\s*#.*$", "", text, flags=re.M)
@@ -59,17 +66,41 @@ def parse_header(path=HEADER_PATH):
     return protos
 
 
+def _ensure_built(build_if_missing):
+    """The in-tree library, rebuilt when csrc/ or the headers changed since it was made (source digest, _build.py).
+    One process builds at a time (flock): under torchrun every rank arrives here at once."""
+    from . import _build
+    custom = bool(os.environ.get("PGICA_LIB_PATH"))
+    if custom:
+        return
+    if _build.is_current():
+        return
+    if not build_if_missing and not os.path.exists(LIB_PATH):
+        raise PgicaError(f"{LIB_PATH} is missing; run `python __graft_entry__.py build`")
+    import fcntl
+    with open(os.path.join(_HERE, ".libpgica.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if _build.is_current():
+                return  # another rank built it while this one waited
+            try:
+                _build.build()
+            except Exception as e:
+                if not os.path.exists(LIB_PATH):
+                    raise PgicaError(f"cannot build {LIB_PATH}: {e}") from e
+                import warnings
+                warnings.warn(f"libpgica.so is older than its sources and could not be rebuilt ({e}); using it as is")
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
 def load(build_if_missing=True):
-    """Load the library (building it first if the in-tree .so is absent and nvcc is available)."""
+    """Load the library (building it first if the in-tree .so is absent or stale and nvcc is available)."""
     global _lib
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
-            if not build_if_missing:
-                raise PgicaError(f"{LIB_PATH} is missing; run `python __graft_entry__.py build`")
-            from . import _build
-            _build.build()
+        _ensure_built(build_if_missing)
         lib = ctypes.CDLL(LIB_PATH)
         for name, (restype, argtypes) in parse_header().items():
             fn = getattr(lib, name)  # AttributeError here == header/library mismatch: fail loudly
@@ -79,6 +110,15 @@ def load(build_if_missing=True):
             raise PgicaError("libpgica.so ABI version mismatch")
         _lib = lib
         return lib
+
+
+def set_option(name, value):
+    """Process-wide tuning option of the library (see pgica_set_option in include/pgica.h)."""
+    check(load().pgica_set_option(name.encode(), int(value)))
+
+
+def get_option(name):
+    return int(load().pgica_get_option(name.encode()))
 
 
 def check(rc):

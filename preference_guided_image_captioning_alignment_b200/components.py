@@ -37,24 +37,48 @@ class TemperatureScaledSimilarity(nn.Module):
         else:
             self.register_buffer("temperature", torch.tensor(temperature))
 
+    def _tau_host(self) -> float:
+        """τ as a Python float without a device->host read per call: the value is re-read only when the tensor was
+        written to (its `_version` moves on load_state_dict / an optimiser step of a learnable τ) or replaced."""
+        t = self.temperature
+        key = (id(t), t._version, t.device)
+        cached = self.__dict__.get("_tau_cache")
+        if cached is None or cached[0] != key:
+            cached = (key, float(t.detach()))
+            self.__dict__["_tau_cache"] = cached
+        return cached[1]
+
     def effective_temperature(self) -> float:
-        return float(min(max(float(self.temperature), self.min_temp), self.max_temp))
+        return float(min(max(self._tau_host(), self.min_temp), self.max_temp))
 
     def forward(self, vision_embeds: torch.Tensor, text_embeds: torch.Tensor) -> torch.Tensor:
-        return _DenseSimilarity.apply(vision_embeds, text_embeds, self.temperature, self.min_temp, self.max_temp)
+        return _DenseSimilarity.apply(vision_embeds, text_embeds, self.temperature, self._tau_host(), self.min_temp,
+                                      self.max_temp)
+
+
+def _gemm_nn(a: torch.Tensor, b: torch.Tensor, scale: float) -> torch.Tensor:
+    """scale * a @ b on the library's tcgen05 GEMM (`pgica_similarity` = the gemm_lse main loop with a plain store
+    epilogue): a (m, k) and b (k, n) float; operands go in as bf16, k is zero-padded to a multiple of 8, fp32 out."""
+    from . import functional as F
+    k = a.shape[1]
+    bt = b.t()
+    if k % 8:
+        pad = 8 - k % 8
+        a = torch.nn.functional.pad(a, (0, pad))
+        bt = torch.nn.functional.pad(bt, (0, pad))
+    return F.similarity(F.as_bf16(a.contiguous()), F.as_bf16(bt.contiguous()), scale)
 
 
 class _DenseSimilarity(torch.autograd.Function):
     """S = normalize(v) normalize(t)^T / clamp(tau) as a dense matrix, differentiable like the reference's module
-    (components.py:61-83).  Forward: `pgica_rownorm_fwd` + `pgica_similarity`.  Backward of a DENSE upstream gradient
-    is two plain GEMMs (dS t_hat, dS^T v_hat: library matmuls — there is no softmax to fuse and nothing to recompute)
-    followed by `pgica_rownorm_bwd`; d tau = -sum(dS * S) / tau inside the clamp range.  Training goes through
+    (components.py:61-83).  Forward: `pgica_rownorm_fwd` + `pgica_similarity`.  Backward of a DENSE upstream gradient:
+    dS t_hat and dS^T v_hat on the same tcgen05 GEMM (`_gemm_nn`; there is no softmax to fuse and nothing to
+    recompute), then `pgica_rownorm_bwd`; d tau = -sum(dS * S) / tau inside the clamp range.  Training goes through
     ContrastiveLoss, which never forms S; this path exists for callers that score with the matrix."""
 
     @staticmethod
-    def forward(ctx, v, t, temperature, min_temp, max_temp):
+    def forward(ctx, v, t, temperature, tau, min_temp, max_temp):
         from . import functional as F
-        tau = float(temperature)
         tau_eff = float(min(max(tau, min_temp), max_temp))
         vn, vinv = ops.l2_normalize(v.detach(), 1e-12)
         tn, tinv = ops.l2_normalize(t.detach(), 1e-12)
@@ -71,15 +95,15 @@ class _DenseSimilarity(torch.autograd.Function):
         dS = dS.float().contiguous()
         dv = dt = dtau = None
         if ctx.needs_input_grad[0]:
-            dvn = torch.matmul(dS, tn.float()) / ctx.tau_eff
+            dvn = _gemm_nn(dS, tn, 1.0 / ctx.tau_eff)
             dv = ops.l2_normalize_bwd(v.detach(), vinv, dvn.contiguous()).to(v.dtype)
         if ctx.needs_input_grad[1]:
-            dtn = torch.matmul(dS.t(), vn.float()) / ctx.tau_eff
+            dtn = _gemm_nn(dS.t(), vn, 1.0 / ctx.tau_eff)
             dt = ops.l2_normalize_bwd(t.detach(), tinv, dtn.contiguous()).to(t.dtype)
         if ctx.needs_input_grad[2]:
             dtau = (-(dS * S).sum() / ctx.tau_eff if ctx.tau_inside else torch.zeros((), device=dS.device))
             dtau = dtau.to(ctx.temp_dtype)
-        return dv, dt, dtau, None, None
+        return dv, dt, dtau, None, None, None
 
 
 class ContrastiveLoss(nn.Module):

@@ -3,6 +3,8 @@
 #include <cudaTypedefs.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <atomic>
 #include <mutex>
@@ -86,6 +88,49 @@ int make_tmap_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t co
   return PGICA_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ options
+namespace {
+struct OptionTable {
+  std::atomic<int64_t> v[kOptCount];
+  OptionTable() {
+    static const int64_t defaults[kOptCount] = {1, 0, 0, 1, 0, 0, 0, 0, 0};
+    for (int i = 0; i < kOptCount; ++i) v[i].store(defaults[i]);
+    auto env_int = [](const char* name, Option o, OptionTable* t) {
+      if (const char* e = getenv(name)) t->v[o].store(atoll(e));
+    };
+    env_int("PGICA_SGG_FUSED", kOptSggFused, this);
+    env_int("PGICA_SGGF_COOP", kOptSggfCoop, this);
+    env_int("PGICA_SGGF_SPREAD", kOptSggfSpread, this);
+    env_int("PGICA_SGGF_SLOTS", kOptSggfSlots, this);
+    env_int("PGICA_SGGF_DEBUG_PRODUCERS_ONLY", kOptSggfProducersOnly, this);
+    env_int("PGICA_SGG_CLUSTER", kOptSggCluster, this);
+    env_int("PGICA_SGGF_XPROD", kOptSggfXProd, this);
+    if (const char* e = getenv("PGICA_SGGF_PLAN")) {
+      int r2 = 0, c2 = 0;
+      if (sscanf(e, "%d,%d", &r2, &c2) == 2 && r2 >= 1 && c2 >= 1) {
+        v[kOptSggfPlanR2].store(r2);
+        v[kOptSggfPlanC2].store(c2);
+      }
+    }
+    // a profiler that cannot replay cooperative cluster launches is attached: plain launches, set once here
+    if (getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("CUDA_INJECTION64_PATH")) v[kOptSggfCoop].store(0);
+  }
+};
+OptionTable& options() {
+  static OptionTable t;
+  return t;
+}
+const char* const kOptionNames[kOptCount] = {"sgg_fused",  "sggf_plan_r2", "sggf_plan_c2",        "sggf_coop", "sggf_spread",
+                                             "sggf_slots", "sggf_producers_only", "sgg_cluster", "sggf_xprod"};
+int option_index(const char* name) {
+  if (!name) return -1;
+  for (int i = 0; i < kOptCount; ++i)
+    if (strcmp(name, kOptionNames[i]) == 0) return i;
+  return -1;
+}
+}  // namespace
+int64_t get_option(Option o) { return options().v[o].load(std::memory_order_relaxed); }
+
 static std::atomic<unsigned long long> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 unsigned long long launches_so_far() { return g_launches.load(std::memory_order_relaxed); }
@@ -110,6 +155,21 @@ int pgica_abi_version(void) { return PGICA_ABI_VERSION; }
 const char* pgica_last_error(void) { return pgica::get_error(); }
 int pgica_sm_count(void) { return pgica::device_sm_count(); }
 int64_t pgica_kernel_launches(void) { return (int64_t)pgica::launches_so_far(); }
+
+int pgica_set_option(const char* name, int64_t value) {
+  const int i = pgica::option_index(name);
+  if (i < 0) {
+    pgica::set_error("unknown option '%s'", name ? name : "(null)");
+    return PGICA_ERR_INVALID_ARGUMENT;
+  }
+  pgica::options().v[i].store(value, std::memory_order_relaxed);
+  return PGICA_OK;
+}
+
+int64_t pgica_get_option(const char* name) {
+  const int i = pgica::option_index(name);
+  return i < 0 ? INT64_MIN : pgica::options().v[i].load(std::memory_order_relaxed);
+}
 
 int pgica_device_check(void) {
   int dev = 0, major = 0, minor = 0;

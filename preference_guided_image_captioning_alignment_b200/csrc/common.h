@@ -8,6 +8,7 @@
 #include <stdint.h>
 
 #include "../../include/pgica.h"
+#include "../../include/pgica_debug.h"
 
 namespace pgica {
 
@@ -44,6 +45,22 @@ int device_sm_count();
 
 // process-wide count of kernels this library has launched (bench.py reports it as `gpu_launches`)
 void count_launches(int n);
+
+// Process-wide tuning options (pgica_set_option / pgica_get_option).  Defaults are seeded ONCE, when the library is
+// loaded, from environment variables PGICA_<NAME>; nothing reads the environment on the call path.
+enum Option {
+  kOptSggFused = 0,          // "sgg_fused": 1 = dual backward kernel when both gradients are wanted (default), 0 = one launch per product
+  kOptSggfPlanR2,            // "sggf_plan_r2", "sggf_plan_c2": pin the dual kernel's role split (row pairs per chunk,
+  kOptSggfPlanC2,            //   column pairs per pass); 0 = planner decides
+  kOptSggfCoop,              // "sggf_coop": 1 = cooperative launch, refused launch is an error (default); 0 = plain launch
+  kOptSggfSpread,            // "sggf_spread": alternative diagonal schedule (tuning)
+  kOptSggfSlots,             // "sggf_slots": exchange double-slots per producer CTA (0 = default 4)
+  kOptSggfProducersOnly,     // "sggf_producers_only": diagnostics, holders idle
+  kOptSggCluster,            // "sgg_cluster": cluster size of the one-product kernel (4, 2 or 1; 0 = largest that tiles k)
+  kOptSggfXProd,             // "sggf_xprod": X-holders co-produce (0 = off)
+  kOptCount
+};
+int64_t get_option(Option o);
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -15,6 +15,8 @@
 #include "common.h"
 #include "ptx.cuh"
 
+#include <mutex>
+
 namespace pgica {
 namespace {
 
@@ -33,7 +35,8 @@ constexpr size_t kSmem = 1024 + kOffZ + kZBytes + 4 * kT * 4 + 256;
 constexpr uint32_t kTmemZ = 0, kTmemOut = 128;   // TMEM columns: Z [0,128), two output buffers [128,256) [256,384)
 
 struct NtxSmallParams {
-  int n, k;          // rows per side, depth
+  int n, k;          // rows per side, width of the operands / gradients
+  int kf;            // depth of the similarity product (k, or 3k for split fp32 operands [hi|lo|hi] x [hi|hi|lo])
   float c;           // inv_tau * log2(e)
   float w;           // gradient weight: inv_tau / (2n) (mean) or inv_tau / 2 (sum)
   float loss_mult;   // 0.5 / n (mean) or 0.5 (sum)
@@ -62,7 +65,7 @@ ntxent_small_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = threadIdx.x;  // this thread's row (and, in the column pass, its column)
-  const int nkb = p.k / kBK;
+  const int nkb = p.kf / kBK;
   const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
 
   if (threadIdx.x == 0) {
@@ -273,9 +276,9 @@ extern "C" int pgica_ntxent_small_supported(int64_t rows, int64_t dim) {
   return (rows >= 1 && rows <= 128 && dim >= 128 && dim <= 512 && dim % 128 == 0) ? 1 : 0;
 }
 
-extern "C" int pgica_ntxent_small(const void* a, const void* b, int64_t rows, int64_t dim, float inv_tau,
-                                  int reduce_mean, float* loss, float* lse_row, float* lse_col, float* da, float* db,
-                                  void* stream) {
+static int ntxent_small_launch(const void* a, const void* b, int64_t rows, int64_t dim, int64_t depth, float inv_tau,
+                               int reduce_mean, float* loss, float* lse_row, float* lse_col, float* da, float* db,
+                               void* stream) {
   using namespace pgica;
   int rc = pgica_device_check();
   if (rc != PGICA_OK) return rc;
@@ -288,6 +291,7 @@ extern "C" int pgica_ntxent_small(const void* a, const void* b, int64_t rows, in
   NtxSmallParams p{};
   p.n = (int)rows;
   p.k = (int)dim;
+  p.kf = (int)depth;
   p.c = inv_tau * kLog2e;
   p.w = reduce_mean ? inv_tau / (2.0f * rows) : inv_tau * 0.5f;
   p.loss_mult = reduce_mean ? 0.5f / rows : 0.5f;
@@ -297,13 +301,33 @@ extern "C" int pgica_ntxent_small(const void* a, const void* b, int64_t rows, in
   p.da = da;
   p.db = db;
   CUtensorMap tm_a, tm_b;
-  rc = make_tmap_bf16(&tm_a, a, rows, dim, dim, kT);
+  rc = make_tmap_bf16(&tm_a, a, rows, depth, depth, kT);
   if (rc != PGICA_OK) return rc;
-  rc = make_tmap_bf16(&tm_b, b, rows, dim, dim, kT);
+  rc = make_tmap_bf16(&tm_b, b, rows, depth, depth, kT);
   if (rc != PGICA_OK) return rc;
-  PGICA_CUDA_OK(cudaFuncSetAttribute(ntxent_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+  static std::once_flag once[64];
+  int dev = 0;
+  PGICA_CUDA_OK(cudaGetDevice(&dev));
+  cudaError_t attr_err = cudaSuccess;
+  std::call_once(once[dev & 63], [&] {
+    attr_err = cudaFuncSetAttribute(ntxent_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+  });
+  PGICA_CUDA_OK(attr_err);
   ntxent_small_kernel<<<1, kThreads, kSmem, static_cast<cudaStream_t>(stream)>>>(tm_a, tm_b, p);
   PGICA_CUDA_OK(cudaGetLastError());
   count_launches(1);
   return PGICA_OK;
+}
+
+extern "C" int pgica_ntxent_small(const void* a, const void* b, int64_t rows, int64_t dim, float inv_tau,
+                                  int reduce_mean, float* loss, float* lse_row, float* lse_col, float* da, float* db,
+                                  void* stream) {
+  return ntxent_small_launch(a, b, rows, dim, dim, inv_tau, reduce_mean, loss, lse_row, lse_col, da, db, stream);
+}
+
+extern "C" int pgica_ntxent_small_split(const void* a_left3, const void* b_right3, int64_t rows, int64_t dim,
+                                        float inv_tau, int reduce_mean, float* loss, float* lse_row, float* lse_col,
+                                        float* da, float* db, void* stream) {
+  return ntxent_small_launch(a_left3, b_right3, rows, dim, 3 * dim, inv_tau, reduce_mean, loss, lse_row, lse_col, da, db,
+                             stream);
 }

@@ -357,28 +357,17 @@ sgg_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
 
 }  // namespace
 
-int sgg_cluster_dispatch(int cluster, const void* x, const void* y, int64_t mx, int64_t my, int64_t k, float scale,
-                         const float* r_lse, const float* r_coef, const int32_t* r_tgt, const float* c_lse,
-                         const float* c_coef, const int32_t* c_tgt, void* out, int out_is_bf16, cudaStream_t st);
-
 int sggx_dispatch(int cluster, const void* x, const void* y, int64_t mx, int64_t my, int64_t k, float scale,
                   const float* r_lse, const float* r_coef, const int32_t* r_tgt, const float* c_lse,
                   const float* c_coef, const int32_t* c_tgt, void* out, int out_is_bf16, void* workspace,
                   size_t workspace_bytes, cudaStream_t st);
 size_t sggx_workspace_bytes();
 
-// How the CTAs of a cluster hand G tiles to each other: through the L2-resident exchange ring (sgg_x.cu, default) or
-// through distributed shared memory (sgg_cluster.cu, PGICA_SGG_EXCHANGE=dsmem).
-static bool exchange_via_dsmem() {
-  const char* e = getenv("PGICA_SGG_EXCHANGE");
-  return e != nullptr && e[0] == 'd';
-}
-
-// Cluster size for the shared-recompute kernels: the largest of {4, 2} whose 256-column slices tile k exactly, unless
-// PGICA_SGG_CLUSTER overrides it (1 = single-CTA kernel in this file).
+// Cluster size for the shared-recompute kernel (sgg_x.cu): the largest of {4, 2} whose 256-column slices tile k exactly,
+// unless option sgg_cluster caps it (1 = the single-CTA kernel in this file).
 static int choose_cluster(int64_t k) {
-  int want = 4;
-  if (const char* e = getenv("PGICA_SGG_CLUSTER")) want = atoi(e);
+  int want = (int)get_option(kOptSggCluster);
+  if (want <= 0) want = 4;
   if (want >= 4 && k % 1024 == 0) return 4;
   if (want >= 2 && k % 512 == 0) return 2;
   return 1;
@@ -411,12 +400,9 @@ extern "C" int pgica_softmax_grad_gemm(const void* x, const void* y, int64_t mx,
   PGICA_REQUIRE(!col || c_coef, "softmax_grad_gemm: c_coef missing");
   PGICA_REQUIRE(scale > 0.f, "softmax_grad_gemm: scale must be positive");
   const int cluster = choose_cluster(k);
-  if (cluster > 1 && !exchange_via_dsmem() && workspace != nullptr && workspace_bytes > 0)
+  if (cluster > 1 && workspace != nullptr && workspace_bytes > 0)
     return sggx_dispatch(cluster, x, y, mx, my, k, scale, r_lse, r_coef, r_tgt, c_lse, c_coef, c_tgt, out, out_is_bf16,
                          workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
-  if (cluster > 1)
-    return sgg_cluster_dispatch(cluster, x, y, mx, my, k, scale, r_lse, r_coef, r_tgt, c_lse, c_coef, c_tgt, out,
-                                out_is_bf16, static_cast<cudaStream_t>(stream));
   SggParams p{};
   p.mx = (int)mx;
   p.my = (int)my;

@@ -38,6 +38,8 @@
 #include "common.h"
 #include "ptx.cuh"
 
+#include <mutex>
+
 namespace pgica {
 namespace {
 
@@ -883,11 +885,9 @@ Plan choose_plan(int RB2, int J2, int k, int npairs, bool single_chunk) {
 }
 
 int plan_override(Plan* pl, int npairs, int S) {
-  // PGICA_SGGF_PLAN="R2,C2" pins the role split in pairs (tuning / tests)
-  const char* e = getenv("PGICA_SGGF_PLAN");
-  if (!e) return 0;
-  int R2 = 0, C2 = 0;
-  if (sscanf(e, "%d,%d", &R2, &C2) != 2 || R2 < 1 || C2 < 1) return 0;
+  // options sggf_plan_r2 / sggf_plan_c2 pin the role split in pairs (tuning / tests)
+  const int R2 = (int)get_option(kOptSggfPlanR2), C2 = (int)get_option(kOptSggfPlanC2);
+  if (R2 < 1 || C2 < 1) return 0;
   if (R2 * S + C2 * S >= npairs) return 0;
   pl->R2 = R2;
   pl->C2 = C2;
@@ -901,8 +901,14 @@ constexpr int kSlotsPerProducer = 4;  // double slots (two G tiles each) per pro
 
 template <bool kRow, bool kCol>
 int resident_pairs(int* out) {
-  static int cached = 0;
-  if (cached == 0) {
+  // the shared-memory opt-in is a per-device attribute of the function, the occupancy a per-device number
+  static int cached[64] = {0};
+  static std::mutex mu;
+  int dev = 0;
+  PGICA_CUDA_OK(cudaGetDevice(&dev));
+  PGICA_REQUIRE(dev >= 0 && dev < 64, "softmax_grad_gemm_dual: device ordinal %d out of range", dev);
+  std::lock_guard<std::mutex> lock(mu);
+  if (cached[dev] == 0) {
     auto kern = sggf_kernel<kRow, kCol>;
     PGICA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
     cudaLaunchConfig_t cfg{};
@@ -922,9 +928,9 @@ int resident_pairs(int* out) {
       set_error("softmax_grad_gemm_dual: only %d CTA pairs of this kernel fit on the device", n);
       return PGICA_ERR_CUDA;
     }
-    cached = n;
+    cached[dev] = n;
   }
-  *out = cached;
+  *out = cached[dev];
   return PGICA_OK;
 }
 
@@ -946,20 +952,17 @@ int launch(const CUtensorMap& tm_x128, const CUtensorMap& tm_y128, const CUtenso
   attr[1].id = cudaLaunchAttributeCooperative;  // all pairs co-resident or the launch fails: the roles wait on each other
   attr[1].val.cooperative = 1;
   cfg.attrs = attr;
-  // The cooperative attribute is dropped with PGICA_SGGF_COOP=0, under Nsight Compute (which cannot replay a
-  // cooperative cluster launch) and when the cooperative launch is refused: the grid never exceeds the resident-
-  // cluster count, so on an otherwise idle device all pairs are co-resident anyway.
-  static const bool coop = !(getenv("PGICA_SGGF_COOP") && atoi(getenv("PGICA_SGGF_COOP")) == 0) &&
-                           !getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") && !getenv("CUDA_INJECTION64_PATH");
+  // The roles spin-wait on each other: every pair must be resident, which only a cooperative launch guarantees.  A
+  // refused cooperative launch (SMs held by another context, MPS, a concurrent kernel) is therefore an ERROR, not
+  // something to retry without the attribute.  Option sggf_coop = 0 selects a plain launch explicitly; it is also
+  // the default when a profiler that cannot replay cooperative cluster launches was attached at load time.
+  const bool coop = get_option(kOptSggfCoop) != 0;
   cfg.numAttrs = coop ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm_x128, tm_y128, tm_x64, tm_y64, tm_s, tm_ox, tm_oy, p);
-  if (e != cudaSuccess && coop) {
-    (void)cudaGetLastError();
-    cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kern, tm_x128, tm_y128, tm_x64, tm_y64, tm_s, tm_ox, tm_oy, p);
-  }
   if (e != cudaSuccess) {
-    set_error("softmax_grad_gemm_dual: launch failed: %s", cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    set_error("softmax_grad_gemm_dual: %slaunch of %u CTAs failed: %s", coop ? "cooperative " : "", cfg.gridDim.x,
+              cudaGetErrorString(e));
     return PGICA_ERR_CUDA;
   }
   count_launches(1);
@@ -994,10 +997,10 @@ int plan_and_launch(const void* x, const void* y, int64_t mx, int64_t my, int64_
   p.nW = pl.nW;
   p.nP = pl.nP;
   p.D = kSlotsPerProducer;
-  p.spread = (getenv("PGICA_SGGF_SPREAD") && atoi(getenv("PGICA_SGGF_SPREAD")) != 0) ? 1 : 0;
-  p.debug_producers_only = getenv("PGICA_SGGF_DEBUG_PRODUCERS_ONLY") ? 1 : 0;
-  if (const char* e = getenv("PGICA_SGGF_SLOTS")) {  // tuning: fewer exchange double-slots per producer CTA (8 was no faster than 4)
-    const int v = atoi(e);
+  p.spread = get_option(kOptSggfSpread) != 0 ? 1 : 0;
+  p.debug_producers_only = get_option(kOptSggfProducersOnly) != 0 ? 1 : 0;
+  {  // tuning: fewer exchange double-slots per producer CTA (8 was no faster than 4)
+    const int v = (int)get_option(kOptSggfSlots);
     if (v >= 1 && v <= kSlotsPerProducer) p.D = v;
   }
   const size_t nslots = (size_t)2 * p.nP * p.D * 2;
@@ -1050,9 +1053,8 @@ int plan_and_launch(const void* x, const void* y, int64_t mx, int64_t my, int64_
 }  // namespace
 
 bool sggf_supported(int64_t mx, int64_t my, int64_t k) {
-  // PGICA_SGG_FUSED=0 falls back to one launch per product (sgg_x.cu)
-  if (const char* e = getenv("PGICA_SGG_FUSED"))
-    if (atoi(e) == 0) return false;
+  // option sgg_fused = 0 falls back to one launch per product (sgg_x.cu)
+  if (get_option(kOptSggFused) == 0) return false;
   return k % kNC == 0 && k / kNC <= 4 && mx >= 1 && my >= 1;
 }
 

@@ -22,6 +22,8 @@
 #include "common.h"
 #include "ptx.cuh"
 
+#include <mutex>
+
 namespace pgica {
 namespace {
 
@@ -580,7 +582,13 @@ sggx_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
 
 template <int C, bool kRow, bool kCol>
 int max_clusters(int* out) {
-  static int cached = 0;
+  static int cached_dev[64] = {0};
+  static std::mutex mu;
+  int dev = 0;
+  PGICA_CUDA_OK(cudaGetDevice(&dev));
+  PGICA_REQUIRE(dev >= 0 && dev < 64, "softmax_grad_gemm: device ordinal %d out of range", dev);
+  std::lock_guard<std::mutex> lock(mu);
+  int& cached = cached_dev[dev];
   if (cached == 0) {
     auto kern = sggx_kernel<C, kRow, kCol>;
     PGICA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));

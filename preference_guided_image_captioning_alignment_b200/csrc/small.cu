@@ -199,21 +199,25 @@ __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p, size
 template <typename T>
 __global__ void rownorm_fwd_kernel(const T* __restrict__ x, int rows, int dim, float eps,
                                    __nv_bfloat16* __restrict__ y, float* __restrict__ inv_norm,
-                                   __nv_bfloat16* __restrict__ left3, __nv_bfloat16* __restrict__ right3) {
+                                   __nv_bfloat16* __restrict__ left3, __nv_bfloat16* __restrict__ right3,
+                                   int normalize) {
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= rows) return;
-  float ss = 0.f;
-  for (int k = lane; k < dim; k += 32) {
-    const float v = ldf(x, (size_t)r * dim + k);
-    ss = fmaf(v, v, ss);
+  float inv = 1.f;
+  if (normalize) {
+    float ss = 0.f;
+    for (int k = lane; k < dim; k += 32) {
+      const float v = ldf(x, (size_t)r * dim + k);
+      ss = fmaf(v, v, ss);
+    }
+    ss = warp_sum(ss);
+    inv = 1.f / fmaxf(sqrtf(ss), eps);
   }
-  ss = warp_sum(ss);
-  const float inv = 1.f / fmaxf(sqrtf(ss), eps);
   for (int k = lane; k < dim; k += 32) {
-    const float v = ldf(x, (size_t)r * dim + k) * inv;
+    const float v = normalize ? ldf(x, (size_t)r * dim + k) * inv : ldf(x, (size_t)r * dim + k);
     const __nv_bfloat16 hi = __float2bfloat16(v);
-    y[(size_t)r * dim + k] = hi;
+    if (y) y[(size_t)r * dim + k] = hi;
     if (left3) {
       // two-term bf16 split of the unit vector: <a, b> ~= a_hi.b_hi + a_lo.b_hi + a_hi.b_lo as ONE bf16 GEMM over 3*dim
       const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
@@ -226,7 +230,7 @@ __global__ void rownorm_fwd_kernel(const T* __restrict__ x, int rows, int dim, f
       right3[o + 2 * dim] = lo;
     }
   }
-  if (lane == 0) inv_norm[r] = inv;
+  if (lane == 0 && inv_norm) inv_norm[r] = inv;
 }
 
 // dx = (g - xh * <xh, g>) * inv_norm with xh = x * inv_norm recomputed in fp32.  g is fp32 or bf16, rows `g_pitch`
@@ -486,11 +490,21 @@ int pgica_rownorm_fwd(const void* x, int x_is_bf16, int64_t rows, int64_t dim, f
   if (x_is_bf16)
     rownorm_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(
         static_cast<const __nv_bfloat16*>(x), (int)rows, (int)dim, eps, static_cast<__nv_bfloat16*>(y_bf16), inv_norm,
-        l3, r3);
+        l3, r3, 1);
   else
     rownorm_fwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const float*>(x), (int)rows, (int)dim,
                                                                       eps, static_cast<__nv_bfloat16*>(y_bf16),
-                                                                      inv_norm, l3, r3);
+                                                                      inv_norm, l3, r3, 1);
+  PGICA_CUDA_OK(cudaGetLastError());
+  count_launches(1);
+  return PGICA_OK;
+}
+
+int pgica_split3_bf16(const float* x, int64_t rows, int64_t dim, void* left3_bf16, void* right3_bf16, void* stream) {
+  PGICA_REQUIRE(x && left3_bf16 && right3_bf16 && rows > 0 && dim > 0, "split3: bad argument");
+  rownorm_fwd_kernel<float><<<(unsigned)ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(
+      x, (int)rows, (int)dim, 0.f, nullptr, nullptr, static_cast<__nv_bfloat16*>(left3_bf16),
+      static_cast<__nv_bfloat16*>(right3_bf16), 0);
   PGICA_CUDA_OK(cudaGetLastError());
   count_launches(1);
   return PGICA_OK;

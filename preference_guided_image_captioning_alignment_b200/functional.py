@@ -403,6 +403,32 @@ def ntxent_small(a, b, inv_tau, reduce_mean=True):
     return loss, lse_row, lse_col, da, db
 
 
+def split3(x):
+    """fp32 (rows, dim) -> bf16 (rows, 3*dim) pair ([hi|lo|hi], [hi|hi|lo]) WITHOUT normalising (pgica_split3_bf16)."""
+    _need_cuda(x)
+    lib = _lib.load()
+    x = x.float().contiguous()
+    rows, dim = x.shape
+    l3 = torch.empty(rows, 3 * dim, dtype=torch.bfloat16, device=x.device)
+    r3 = torch.empty(rows, 3 * dim, dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.pgica_split3_bf16(_p(x), rows, dim, _p(l3), _p(r3), _stream()))
+    return l3, r3
+
+
+def ntxent_small_split(a_left3, b_right3, dim, inv_tau, reduce_mean=True):
+    """ntxent_small on split fp32 operands: similarity over depth 3*dim, gradients (B, dim) fp32."""
+    _need_cuda(a_left3, b_right3)
+    lib = _lib.load()
+    n = a_left3.shape[0]
+    f32 = dict(dtype=torch.float32, device=a_left3.device)
+    loss = torch.empty((), **f32)
+    lse_row, lse_col = torch.empty(n, **f32), torch.empty(n, **f32)
+    da, db = torch.empty(n, dim, **f32), torch.empty(n, dim, **f32)
+    _lib.check(lib.pgica_ntxent_small_split(_p(a_left3), _p(b_right3), n, dim, float(inv_tau), 1 if reduce_mean else 0,
+                                            _p(loss), _p(lse_row), _p(lse_col), _p(da), _p(db), _stream()))
+    return loss, lse_row, lse_col, da, db
+
+
 # ----------------------------------------------------------------------------------------- SURVEY 8(f) row 2
 def grad_norm_clip(grads, max_norm, clip=True):
     """Global L2 norm of a list of gradient tensors (fp32 / bf16, contiguous), finite check and in-place clip in three

@@ -9,6 +9,7 @@ What is rebound:
     PreferenceGuidedTrainer.__init__ resolves at pkg/training/trainer.py:204-209.
   * `ContrastiveLoss`, `DPOPreferenceLoss`, `TemperatureScaledSimilarity`, `compute_sequence_logprobs` in
     pkg.models.components.
+  * `PreferenceGuidedCaptioningModel.compute_similarity` (pkg/models/model.py:925-954) -> scoring.model_compute_similarity.
   * with fuse_lm_head=True, every CaptionDecoder built afterwards (and every one passed to `fuse_decoder`) gets the
     `forward` of its GPT-2 `lm_head` Linear rebound on the instance, so that the training forward
     (pkg/models/model.py:604-610) returns a LazyLogits handle instead of the (B, T, V) tensor; the HF causal-LM loss
@@ -29,7 +30,7 @@ import weakref
 import torch
 import torch.nn as nn
 
-from . import components, losses, ops
+from . import components, losses, ops, scoring
 
 REFERENCE_PACKAGE = "preference_guided_image_captioning_alignment"
 _originals = {}
@@ -167,6 +168,12 @@ def install(package: str = REFERENCE_PACKAGE, fuse_lm_head: bool = True):
             done.append((comp_mod.__name__, name))
     except Exception:
         pass
+    if hasattr(model_mod, "PreferenceGuidedCaptioningModel"):
+        cls = model_mod.PreferenceGuidedCaptioningModel
+        if hasattr(cls, "compute_similarity"):
+            _originals.setdefault((cls, "compute_similarity"), cls.compute_similarity)
+            cls.compute_similarity = scoring.model_compute_similarity
+            done.append((model_mod.__name__, "PreferenceGuidedCaptioningModel.compute_similarity"))
     if fuse_lm_head and hasattr(model_mod, "CaptionDecoder"):
         _wrap_caption_decoder(model_mod.CaptionDecoder)
         done.append((model_mod.__name__, "CaptionDecoder.lm_head"))

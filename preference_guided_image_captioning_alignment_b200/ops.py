@@ -29,9 +29,14 @@ def ntxent(a: Tensor, b: Tensor, inv_tau: float, reduce_mean: bool) -> Tuple[Ten
     Returns (loss[], lse_row[B], lse_col[B])."""
     if a.shape != b.shape or a.dim() != 2:
         raise ValueError(f"ntxent expects two (B, D) tensors of equal shape, got {tuple(a.shape)} {tuple(b.shape)}")
-    ab, bb = F.as_bf16(a), F.as_bf16(b)
-    lse_row, diag, lse_col = F.ntxent_fwd(ab, bb, inv_tau, 0)
     n = a.shape[0]
+    if a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16:
+        lse_row, diag, lse_col = F.ntxent_fwd(a.contiguous(), b.contiguous(), inv_tau, 0)
+    else:  # fp32 embeddings: two-term bf16 split, one GEMM of depth 3*D per direction (as ntxent_cosine does)
+        al, ar = F.split3(a)
+        bl, br = F.split3(b)
+        lse_row, diag = F.gemm_lse(al, br, inv_tau, None, 0)
+        lse_col, _ = F.gemm_lse(bl, ar, inv_tau, None, 0, want_tgt=False)
     loss = F.ntxent_loss(lse_row, diag, lse_col, 1.0 / n if reduce_mean else 1.0)
     return loss, lse_row, lse_col
 
@@ -47,7 +52,18 @@ def ntxent_small(a: Tensor, b: Tensor, inv_tau: float, reduce_mean: bool) -> Tup
     of the loss w.r.t. a and b from ONE single-CTA launch (csrc/ntxent_small.cu)."""
     if a.shape != b.shape or a.dim() != 2:
         raise ValueError(f"ntxent expects two (B, D) tensors of equal shape, got {tuple(a.shape)} {tuple(b.shape)}")
-    return F.ntxent_small(F.as_bf16(a), F.as_bf16(b), inv_tau, reduce_mean)
+    return _ntxent_small_impl(a, b, inv_tau, reduce_mean)
+
+
+def _ntxent_small_impl(a, b, inv_tau, reduce_mean):
+    """bf16 inputs are the tensor-core operands as they are; anything wider (the trainer hands over fp32 unit vectors,
+    pkg/models/model.py:826-829) goes in as its two-term bf16 split so the loss keeps the fp32 accuracy the reference
+    computes it with (similarity of depth 3*D; the gradient products use the hi parts)."""
+    if a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16:
+        return F.ntxent_small(a.contiguous(), b.contiguous(), inv_tau, reduce_mean)
+    al3, _ = F.split3(a)
+    _, br3 = F.split3(b)
+    return F.ntxent_small_split(al3, br3, a.shape[1], inv_tau, reduce_mean)
 
 
 @ntxent_small.register_fake
@@ -76,7 +92,7 @@ class _NTXentSmallEager(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, a, b, inv_tau, reduce_mean):
-        loss, lse_row, lse_col, da, db = F.ntxent_small(F.as_bf16(a), F.as_bf16(b), inv_tau, reduce_mean)
+        loss, lse_row, lse_col, da, db = _ntxent_small_impl(a, b, inv_tau, reduce_mean)
         ctx.save_for_backward(da, db)
         ctx.dtypes = (a.dtype, b.dtype)
         ctx.mark_non_differentiable(lse_row, lse_col)
@@ -100,17 +116,24 @@ def ntxent_auto(a: Tensor, b: Tensor, inv_tau: float, reduce_mean: bool):
 @torch.library.custom_op("pgica::ntxent_bwd", mutates_args=())
 def ntxent_bwd(a: Tensor, b: Tensor, lse_row: Tensor, lse_col: Tensor, grad_loss: Tensor, inv_tau: float,
                reduce_mean: bool) -> Tuple[Tensor, Tensor]:
-    ab, bb = F.as_bf16(a), F.as_bf16(b)
-    n = a.shape[0]
+    n, d = a.shape
     mult = 1.0 / (2.0 * n) if reduce_mean else 0.5
-    da, db = F.ntxent_bwd(ab, bb, inv_tau, 0, lse_row, lse_col, grad_loss, mult, da_dtype=_grad_dtype(a),
-                          db_dtype=_grad_dtype(b))
-    return da, db
+    if a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16:
+        return F.ntxent_bwd(a.contiguous(), b.contiguous(), inv_tau, 0, lse_row, lse_col, grad_loss, mult,
+                            da_dtype=torch.bfloat16, db_dtype=torch.bfloat16)
+    # the backward must recompute exactly the logits the forward saw: same split operands, depth 3*D; columns
+    # [0, D) and [2D, 3D) of each product are G.hi and G.lo of the other side
+    al, ar = F.split3(a)
+    bl, br = F.split3(b)
+    g3a, _ = F.ntxent_bwd(al, br, inv_tau, 0, lse_row, lse_col, grad_loss, mult, need_db=False)
+    _, g3b = F.ntxent_bwd(ar, bl, inv_tau, 0, lse_row, lse_col, grad_loss, mult, need_da=False)
+    return g3a[:, :d] + g3a[:, 2 * d:], g3b[:, :d] + g3b[:, 2 * d:]
 
 
 @ntxent_bwd.register_fake
 def _(a, b, lse_row, lse_col, grad_loss, inv_tau, reduce_mean):
-    return torch.empty_like(a, dtype=_grad_dtype(a)), torch.empty_like(b, dtype=_grad_dtype(b))
+    dt = torch.bfloat16 if (a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16) else torch.float32
+    return torch.empty_like(a, dtype=dt), torch.empty_like(b, dtype=dt)
 
 
 def _ntxent_setup(ctx, inputs, output):

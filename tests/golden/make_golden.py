@@ -189,6 +189,53 @@ def make_grad_clip(comp):
     np.savez_compressed(os.path.join(HERE, "grad_clip.npz"), **out)
 
 
+def make_fp32_inputs(comp, TrainerCL, TrainerPL):
+    """Inputs that are NOT bf16-representable: fp32 unit vectors as the model hands them to the trainer's
+    ContrastiveLoss (model.py:826-829 -> 970-1000), fp32 embeddings for the components flavour, and an fp32 hidden /
+    weight pair for the LM head + PreferenceLoss._compute_log_probs.  The reference runs in float64 on the fp32 values."""
+    out = {}
+    for seed, (B, D) in [(5, (32, 512)), (6, (40, 128))]:
+        g = torch.Generator().manual_seed(seed)
+        v = torch.randn(B, D, generator=g, dtype=torch.float32)
+        t = (v + 0.5 * torch.randn(B, D, generator=g, dtype=torch.float32))
+        vn, tn = F.normalize(v, dim=-1), F.normalize(t, dim=-1)           # fp32 values, not bf16-representable
+        key = f"s{seed}"
+        out[key + "_v"], out[key + "_t"] = v.numpy(), t.numpy()
+        out[key + "_vn"], out[key + "_tn"] = vn.numpy(), tn.numpy()
+        for tau in (0.5, 0.07):
+            vv, tt = vn.double().requires_grad_(True), tn.double().requires_grad_(True)
+            loss = TrainerCL(temperature=tau)(vv, tt)
+            loss.backward()
+            k = f"{key}_trainer_tau{tau}"
+            out[k + "_loss"] = np64(loss)
+            out[k + "_dv"], out[k + "_dt"] = np64(vv.grad).astype(np.float32), np64(tt.grad).astype(np.float32)
+            vv, tt = v.double().requires_grad_(True), t.double().requires_grad_(True)
+            loss = comp.ContrastiveLoss(temperature=tau).double()(vv, tt)
+            loss.backward()
+            k = f"{key}_comp_tau{tau}"
+            out[k + "_loss"] = np64(loss)
+            out[k + "_dv"], out[k + "_dt"] = np64(vv.grad).astype(np.float32), np64(tt.grad).astype(np.float32)
+    # LM head on fp32 hidden / weight (what install() sees): trainer-variant mean log-probs + PreferenceLoss
+    g = torch.Generator().manual_seed(8)
+    B, T, d, V = 3, 12, 64, 257
+    f32 = dict(generator=g, dtype=torch.float32)
+    W = torch.randn(V, d, **f32) * 0.05
+    hw, hl = torch.randn(B, T, d, **f32), torch.randn(B, T, d, **f32)
+    yw, yl = torch.randint(0, V, (B, T), generator=g), torch.randint(0, V, (B, T), generator=g)
+    lens = torch.tensor([[12, 7, 4], [9, 12, 5]])
+    mw = (torch.arange(T)[None] < lens[0][:, None]).long()
+    ml = (torch.arange(T)[None] < lens[1][:, None]).long()
+    Wd, hwd, hld = (x.double().requires_grad_(True) for x in (W, hw, hl))
+    pl = TrainerPL(beta=0.1)
+    loss = pl(F.linear(hwd, Wd), F.linear(hld, Wd), yw, yl, mw, ml)
+    loss.backward()
+    out.update(lm_W=W.numpy(), lm_hw=hw.numpy(), lm_hl=hl.numpy(), lm_yw=yw.numpy(), lm_yl=yl.numpy(), lm_mw=mw.numpy(),
+               lm_ml=ml.numpy(), lm_loss=np64(loss), lm_dW=np64(Wd.grad).astype(np.float32),
+               lm_dhw=np64(hwd.grad).astype(np.float32), lm_dhl=np64(hld.grad).astype(np.float32),
+               lm_lpw=np64(pl._compute_log_probs(F.linear(hwd, Wd), yw, mw)))
+    np.savez_compressed(os.path.join(HERE, "fp32_inputs.npz"), **out)
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit("reference not found at " + ref_loader.REFERENCE_ROOT)
@@ -199,6 +246,7 @@ def main():
     make_dpo(comp)
     make_dpo_head(comp)
     make_grad_clip(comp)
+    make_fp32_inputs(comp, TrainerCL, TrainerPL)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

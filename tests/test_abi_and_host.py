@@ -23,10 +23,14 @@ def lib():
 def test_header_symbols_exported(lib):
     from preference_guided_image_captioning_alignment_b200 import _lib
     protos = _lib.parse_header()
-    text = open(_lib.HEADER_PATH).read()
+    text = open(_lib.HEADER_PATH).read() + open(_lib.DEBUG_HEADER_PATH).read()
     declared = set(re.findall(r"\b(pgica_\w+)\s*\(", text))
     assert declared == set(protos), "header parser missed a prototype"
-    assert len(declared) >= 25
+    assert len(declared) >= 50
+    # bring-up / test hooks live in pgica_debug.h, not in the product header
+    product = set(re.findall(r"\b(pgica_\w+)\s*\(", open(_lib.HEADER_PATH).read()))
+    assert not {n for n in product if "debug" in n or "probe" in n}
+    assert {"pgica_set_option", "pgica_get_option", "pgica_compact_rows", "pgica_lmhead_rows_bwd"} <= product
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r"\bT (pgica_\w+)", out))
     assert declared <= exported, f"declared but not exported: {sorted(declared - exported)}"

@@ -789,3 +789,258 @@ def test_graphed_contrastive_step(pg, cuda_device):
             ref.backward()
             assert loss.item() == pytest.approx(ref.item(), rel=1e-6)
             assert torch.equal(step.da, ag.grad) and torch.equal(step.db, bg.grad)
+
+
+# ================================================================================================ compacted rows
+def test_compact_rows_bit_exact(pg, cuda_device):
+    """Index / mask plumbing of the compacted Stage-2 head, bit-exact: the scored-row list equals
+    nonzero(mask[:, 1:]) of the reference's shift (components.py:339-344), gathered rows are the bf16 roundings of the
+    source rows, labels follow their rows, and scatter puts every row back where it came from, zeros elsewhere."""
+    import ctypes
+
+    from preference_guided_image_captioning_alignment_b200 import _lib
+    from preference_guided_image_captioning_alignment_b200 import functional as F
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    for nseq, T, d, kind in ((5, 37, 64, "i64"), (16, 128, 1024, "i64"), (3, 1500, 128, "f32"), (2, 9, 8, "none")):
+        V = 1000
+        labels = torch.randint(0, V + 3, (nseq, T), generator=g).to(cuda_device)        # some labels >= V
+        lens = torch.randint(0, T + 1, (nseq,), generator=g)
+        m01 = (torch.arange(T)[None] < lens[:, None])
+        mask = {"i64": m01.long(), "f32": m01.float() * torch.rand(nseq, T, generator=g), "none": None}[kind]
+        mask = None if mask is None else mask.to(cuda_device)
+        rl, rw = F.prep_rows(labels, mask, V)
+        idx = torch.full((nseq * T,), -7, dtype=torch.int32, device=cuda_device)
+        cnt = torch.zeros(1, dtype=torch.int32, device=cuda_device)
+        _lib.check(lib.pgica_compact_rows(ctypes.c_void_p(rw.data_ptr()), nseq * T, ctypes.c_void_p(idx.data_ptr()),
+                                          ctypes.c_void_p(cnt.data_ptr()), None))
+        # expected: shifted mask, last position of every sequence never scored
+        w = torch.ones(nseq, T, device=cuda_device) if mask is None else mask.float()
+        wshift = torch.cat([w[:, 1:], torch.zeros(nseq, 1, device=cuda_device)], 1).reshape(-1)
+        yshift = torch.cat([labels[:, 1:], torch.zeros(nseq, 1, dtype=torch.long, device=cuda_device)], 1).reshape(-1)
+        scored = (wshift != 0)
+        expect = torch.nonzero(scored).flatten().int()
+        n = int(cnt.item())
+        assert n == expect.numel()
+        assert torch.equal(idx[:n], expect) and bool((idx[n:] == -7).all())
+        oov = scored & (yshift >= V)
+        assert bool(torch.isnan(rw[oov]).all()) and torch.equal(rw[scored & ~oov], wshift[scored & ~oov])
+        if n == 0:
+            continue
+        src = torch.randn(nseq * T, d, generator=g).to(cuda_device)
+        dst = torch.empty(n, d, dtype=torch.bfloat16, device=cuda_device)
+        lab_c = torch.empty(n, dtype=torch.int32, device=cuda_device)
+        _lib.check(lib.pgica_gather_rows_bf16(ctypes.c_void_p(src.data_ptr()), 0, ctypes.c_void_p(idx.data_ptr()), n, d,
+                                              ctypes.c_void_p(dst.data_ptr()), ctypes.c_void_p(rl.data_ptr()),
+                                              ctypes.c_void_p(lab_c.data_ptr()), None))
+        assert torch.equal(dst, src[expect.long()].to(torch.bfloat16)) and torch.equal(lab_c, rl[expect.long()])
+        for out_dtype in (torch.float32, torch.bfloat16):
+            back = torch.full((nseq * T, d), 5.0, dtype=out_dtype, device=cuda_device)
+            _lib.check(lib.pgica_scatter_rows(ctypes.c_void_p(dst.data_ptr()), 1, ctypes.c_void_p(idx.data_ptr()), n, d,
+                                              ctypes.c_void_p(back.data_ptr()), 1 if out_dtype == torch.bfloat16 else 0,
+                                              nseq * T, None))
+            ref = torch.zeros(nseq * T, d, dtype=out_dtype, device=cuda_device)
+            ref[expect.long()] = dst.to(out_dtype)
+            assert torch.equal(back, ref)
+
+
+@pytest.mark.parametrize("length_normalize", [False, True])
+def test_compact_head_equals_full_head(pg, cuda_device, length_normalize):
+    """The compacted, pair-stacked LM head (what PreferenceLoss runs on LazyLogits) against the full-row op on the same
+    inputs: per-row statistics do not depend on which other rows share the GEMM, so sequence log-probs and dhidden agree
+    to fp32 rounding; dweight is summed over rows in another order (1e-3).  Also: all-masked sequence -> NaN (mean) / 0
+    (sum), zero gradient at masked rows, and both against the float64 oracle."""
+    from preference_guided_image_captioning_alignment_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    B, T, d, V = 6, 40, 512, 3001
+    W = (torch.randn(V, d, generator=g) * 0.05).to(cuda_device).requires_grad_(True)          # fp32, not bf16-exact
+    hs = [torch.randn(B, T, d, generator=g).to(cuda_device).requires_grad_(True) for _ in range(2)]
+    ys = [torch.randint(0, V, (B, T), generator=g).to(cuda_device) for _ in range(2)]
+    lens = torch.randint(2, T + 1, (2, B), generator=g)
+    ms = [(torch.arange(T)[None] < lens[i][:, None]).long().to(cuda_device) for i in range(2)]
+    up = [torch.randn(B, generator=g).to(cuda_device) for _ in range(2)]
+
+    def grads(seqs):
+        W.grad = None
+        for h in hs:
+            h.grad = None
+        (seqs[0] * up[0]).sum().add((seqs[1] * up[1]).sum()).backward()
+        return W.grad.clone(), hs[0].grad.clone(), hs[1].grad.clone()
+
+    full = [ops.lmhead_seq_logprob(hs[i], W, ys[i], ms[i], length_normalize)[0] for i in range(2)]
+    gw_f, g0_f, g1_f = grads(full)
+    comp = ops.lmhead_seq_logprob_compact(hs, W, ys, ms, length_normalize)
+    gw_c, g0_c, g1_c = grads(comp)
+    for a, b in zip(comp, full):
+        assert rel(a, b) < 1e-6
+    assert rel(g0_c, g0_f) < 2e-3 and rel(g1_c, g1_f) < 2e-3       # full path hands dhidden back through bf16
+    assert rel(gw_c, gw_f) < 2e-3
+    for i in range(2):
+        masked = (torch.cat([ms[i][:, 1:], torch.zeros(B, 1, dtype=torch.long, device=cuda_device)], 1) == 0)
+        assert bool((hs[i].grad[masked] == 0).all())
+    # float64 oracle on the bf16-rounded operands
+    n = lambda x: bf16r(x.detach()).double().cpu().numpy()
+    o = cf.dpo_head(n(hs[0]), n(hs[1]), n(W), ys[0].cpu().numpy(), ys[1].cpu().numpy(), ms[0].cpu().numpy(),
+                    ms[1].cpu().numpy(), beta=0.1)
+    key = "pc_mean" if length_normalize else "pc"
+    if key in o:
+        assert rel(comp[0], o[key]) < 1e-5
+    # an all-masked sequence: NaN in mean mode, exactly 0 in sum mode, like the reference
+    ms0 = ms[0].clone()
+    ms0[1] = 0
+    out = ops.lmhead_seq_logprob_compact([hs[0]], W, [ys[0]], [ms0], length_normalize)[0]
+    assert (math.isnan(out[1].item()) if length_normalize else out[1].item() == 0.0)
+    assert rel(out[[0, 2, 3, 4, 5]], full[0][[0, 2, 3, 4, 5]]) < 1e-6
+    # everything masked: no GEMM at all, zero gradients
+    out = ops.lmhead_seq_logprob_compact([hs[0]], W, [ys[0]], [torch.zeros_like(ms0)], False)[0]
+    W.grad = None
+    out.sum().backward()
+    assert bool((out == 0).all()) and bool((W.grad == 0).all())
+
+
+# ================================================================================================ fp32 inputs
+@pytest.mark.parametrize("seed", [5, 6])
+@pytest.mark.parametrize("tau", [0.5, 0.07])
+def test_ntxent_fp32_inputs_golden(pg, cuda_device, golden_dir, seed, tau):
+    """Inputs that are NOT bf16-representable (fp32 unit vectors, exactly what the model hands the trainer's loss):
+    the fp32 path (two-term bf16 split, similarity of depth 3*D) keeps the 1e-4 loss bar against the reference run in
+    float64 on the same fp32 values — trainer flavour through the one-launch kernel, components flavour through the
+    general kernels."""
+    from preference_guided_image_captioning_alignment_b200 import components
+    g = np.load(os.path.join(golden_dir, "fp32_inputs.npz"))
+    vn = torch.from_numpy(g[f"s{seed}_vn"]).to(cuda_device).requires_grad_(True)
+    tn = torch.from_numpy(g[f"s{seed}_tn"]).to(cuda_device).requires_grad_(True)
+    loss = pg.ContrastiveLoss(temperature=tau)(vn, tn)
+    k = f"s{seed}_trainer_tau{tau}"
+    assert loss_close(loss.item(), float(g[k + "_loss"]), 1.0 / tau), (loss.item(), float(g[k + "_loss"]))
+    loss.backward()
+    assert rel(vn.grad, g[k + "_dv"]) < GRAD_RTOL and rel(tn.grad, g[k + "_dt"]) < GRAD_RTOL
+    v = torch.from_numpy(g[f"s{seed}_v"]).to(cuda_device).requires_grad_(True)
+    t = torch.from_numpy(g[f"s{seed}_t"]).to(cuda_device).requires_grad_(True)
+    loss = components.ContrastiveLoss(temperature=tau)(v, t)
+    k = f"s{seed}_comp_tau{tau}"
+    assert loss_close(loss.item(), float(g[k + "_loss"]), 10.0), (loss.item(), float(g[k + "_loss"]))
+    loss.backward()
+    assert rel(v.grad, g[k + "_dv"]) < GRAD_RTOL and rel(t.grad, g[k + "_dt"]) < GRAD_RTOL
+
+
+@pytest.mark.parametrize("B", [300, 1024])
+def test_ntxent_fp32_inputs_general_path(pg, cuda_device, B):
+    """B > 128 with fp32 unit vectors: the general kernels on split operands against the float64 oracle (tau = 0.07,
+    where a bf16 rounding of the inputs would cost ~1e-3 of the loss)."""
+    g = torch.Generator().manual_seed(B)
+    a = torch.nn.functional.normalize(torch.randn(B, 512, generator=g), dim=-1)
+    b = torch.nn.functional.normalize(a + 0.3 * torch.randn(B, 512, generator=g), dim=-1)
+    ag, bg = a.to(cuda_device).requires_grad_(True), b.to(cuda_device).requires_grad_(True)
+    loss = pg.ContrastiveLoss(temperature=0.07)(ag, bg)
+    loss.backward()
+    o = cf.ntxent(a.double().numpy(), b.double().numpy(), 0.07, normalize=False, clamp_tau=False)
+    assert loss_close(loss.item(), o["loss"], 1.0 / 0.07), (loss.item(), o["loss"])
+    assert rel(ag.grad, o["dx"]) < GRAD_RTOL and rel(bg.grad, o["dy"]) < GRAD_RTOL
+
+
+def test_preference_loss_fp32_hidden_golden(pg, cuda_device, golden_dir):
+    """LM head on fp32 hidden states and an fp32 weight (what install() sees in the trainer): PreferenceLoss on
+    LazyLogits against the real reference run in float64 on the same fp32 values."""
+    from preference_guided_image_captioning_alignment_b200.losses import LazyLogits
+    g = np.load(os.path.join(golden_dir, "fp32_inputs.npz"))
+    t = lambda k: torch.from_numpy(g[k]).to(cuda_device)
+    W, hw, hl = (t(k).requires_grad_(True) for k in ("lm_W", "lm_hw", "lm_hl"))
+    loss = pg.PreferenceLoss(0.1)(LazyLogits(hw, W), LazyLogits(hl, W), t("lm_yw"), t("lm_yl"), t("lm_mw"), t("lm_ml"))
+    assert abs(loss.item() - float(g["lm_loss"])) <= LOSS_RTOL * abs(float(g["lm_loss"]))
+    loss.backward()
+    assert rel(W.grad, g["lm_dW"]) < GRAD_RTOL
+    assert rel(hw.grad, g["lm_dhw"]) < GRAD_RTOL and rel(hl.grad, g["lm_dhl"]) < GRAD_RTOL
+    lp = pg.PreferenceLoss(0.1)._compute_log_probs(LazyLogits(hw, W), t("lm_yw"), t("lm_mw"))
+    assert rel(lp, g["lm_lpw"]) < 1e-4
+
+
+# ================================================================================================ a1 / scoring
+def test_dense_similarity_backward_own_gemm(pg, cuda_device):
+    """TemperatureScaledSimilarity (components.py:61-83) as a differentiable dense matrix: forward and the backward of
+    a dense upstream gradient (both GEMMs on the library's tcgen05 kernel) against float64 autograd of the reference
+    arithmetic; learnable tau inside and outside the clamp range; B not a multiple of 8."""
+    from oracle import torch_port as tp
+    from preference_guided_image_captioning_alignment_b200 import _lib, components
+    for B, D, tau in ((37, 128, 0.5), (64, 512, 0.07), (130, 256, 1.3)):
+        g = torch.Generator().manual_seed(B)
+        v, t = torch.randn(B, D, generator=g), torch.randn(B, D, generator=g)
+        up = torch.randn(B, B, generator=g)
+        vd, td = v.double().requires_grad_(True), t.double().requires_grad_(True)
+        taud = torch.tensor(tau, dtype=torch.float64, requires_grad=True)
+        vh, th = torch.nn.functional.normalize(vd, dim=-1), torch.nn.functional.normalize(td, dim=-1)
+        Sd = vh @ th.T / torch.clamp(taud, 0.1, 2.0)
+        (Sd * up.double()).sum().backward()
+        mod = components.TemperatureScaledSimilarity(tau, learnable=True).to(cuda_device)
+        vg, tg = v.to(cuda_device).requires_grad_(True), t.to(cuda_device).requires_grad_(True)
+        n0 = _lib.load().pgica_kernel_launches()
+        S = mod(vg, tg)
+        (S * up.to(cuda_device)).sum().backward()
+        assert _lib.load().pgica_kernel_launches() - n0 >= 7   # 2 norms + S, 2 GEMMs + 2 norm backwards: all ours
+        assert rel(S, Sd.detach()) < 5e-3
+        assert rel(vg.grad, vd.grad) < GRAD_RTOL and rel(tg.grad, td.grad) < GRAD_RTOL
+        assert abs(mod.temperature.grad.item() - taud.grad.item()) <= 2e-2 * abs(taud.grad.item()) + 1e-6
+    # the temperature is read once, not per call: no device->host copy on the second forward
+    mod = components.TemperatureScaledSimilarity(0.5).to(cuda_device)
+    mod(vg.detach(), tg.detach())
+    key = mod.__dict__["_tau_cache"][0]
+    mod(vg.detach(), tg.detach())
+    assert mod.__dict__["_tau_cache"][0] == key
+    with torch.no_grad():
+        mod.temperature.fill_(0.25)
+    assert mod.effective_temperature() == 0.25
+
+
+def test_scoring_ops(pg, cuda_device):
+    """compute_similarity (model.py:925-954), per-pair CLIP-style scores (metrics.py:380-439) and
+    retrieval ranks against fp32/fp64 torch."""
+    g = torch.Generator().manual_seed(4)
+    for B, Bt, D in ((50, 50, 512), (130, 77, 256)):
+        img = torch.nn.functional.normalize(torch.randn(B, D, generator=g), dim=-1)
+        txt = torch.nn.functional.normalize(torch.randn(Bt, D, generator=g), dim=-1)
+        ref = img.double() @ txt.double().T / 0.07
+        S = pg.compute_similarity(img.to(cuda_device), txt.to(cuda_device), 0.07)
+        assert S.shape == (B, Bt) and rel(S, ref) < 1e-5
+        Sb = pg.compute_similarity(img.to(cuda_device).bfloat16(), txt.to(cuda_device).bfloat16(), 0.07)
+        assert rel(Sb, img.bfloat16().double() @ txt.bfloat16().double().T / 0.07) < 1e-5
+    raw_i, raw_t = torch.randn(64, 512, generator=g), torch.randn(64, 512, generator=g)
+    sc = pg.paired_scores(raw_i.to(cuda_device), raw_t.to(cuda_device), 100.0)
+    ref = 100.0 * torch.nn.functional.cosine_similarity(raw_i.double(), raw_t.double(), dim=-1)
+    assert rel(sc, ref) < 1e-5
+    a = torch.nn.functional.normalize(torch.randn(40, 128, generator=g), dim=-1)
+    b = torch.nn.functional.normalize(a + 0.8 * torch.randn(40, 128, generator=g), dim=-1)
+    ranks = pg.retrieval_ranks(a.to(cuda_device), b.to(cuda_device))
+    sim = a.double() @ b.double().T
+    assert torch.equal(ranks.cpu(), (sim > sim.diagonal()[:, None]).sum(1))
+
+
+def test_options_api_selects_kernels(pg, cuda_device):
+    """pgica_set_option replaces the per-call getenv of round 1: the plan and the kernel choice are explicit
+    process-wide options, and both backward variants agree."""
+    from preference_guided_image_captioning_alignment_b200 import _lib
+    from preference_guided_image_captioning_alignment_b200 import functional as F
+    g = torch.Generator().manual_seed(2)
+    B, T, d, V = 4, 32, 512, 2000
+    h = torch.randn(B, T, d, generator=g).bfloat16().to(cuda_device)
+    W = (torch.randn(V, d, generator=g) * 0.05).bfloat16().to(cuda_device)
+    y = torch.randint(0, V, (B, T), generator=g).to(cuda_device)
+    seq, lse, _, rl, rw, _ = F.lmhead_logprob_fwd(h, W, y, None, False)
+    gs = torch.randn(B, generator=g).to(cuda_device)
+    assert _lib.get_option("sgg_fused") == 1 and _lib.get_option("sggf_coop") in (0, 1)
+    outs = {}
+    try:
+        for fused in (1, 0):
+            _lib.set_option("sgg_fused", fused)
+            outs[fused] = F.lmhead_logprob_bwd(h, W, rl, rw, lse, gs, False, dhidden_dtype=torch.float32)
+        _lib.set_option("sgg_fused", 1)
+        _lib.set_option("sggf_plan_r2", 1)
+        _lib.set_option("sggf_plan_c2", 3)
+        outs[2] = F.lmhead_logprob_bwd(h, W, rl, rw, lse, gs, False, dhidden_dtype=torch.float32)
+    finally:
+        _lib.set_option("sgg_fused", 1)
+        _lib.set_option("sggf_plan_r2", 0)
+        _lib.set_option("sggf_plan_c2", 0)
+    for k in (0, 2):
+        assert rel(outs[k][0], outs[1][0]) < 1e-3 and rel(outs[k][1], outs[1][1]) < 1e-3
+    with pytest.raises(_lib.PgicaError):
+        _lib.set_option("no_such_option", 1)

@@ -271,3 +271,25 @@ def test_grad_norm_clip_closed_form(golden_dir, tag):
         assert (o["clip_coef"] < 1.0) == (tag != "noclip")
     for i in range(n):
         np.testing.assert_allclose(o["clipped"][i], g[f"{tag}_c{i}"], rtol=2e-6, atol=0, equal_nan=True)
+
+
+def test_fp32_input_fixture_against_oracle(golden_dir):
+    """tests/golden/fp32_inputs.npz (inputs that are not bf16-representable, minted from the real reference in
+    float64): both restatements reproduce it."""
+    g = np.load(os.path.join(golden_dir, "fp32_inputs.npz"))
+    for seed in (5, 6):
+        for tau in (0.5, 0.07):
+            vn, tn = g[f"s{seed}_vn"].astype(np.float64), g[f"s{seed}_tn"].astype(np.float64)
+            o = cf.ntxent(vn, tn, tau, normalize=False, clamp_tau=False)
+            assert abs(o["loss"] - float(g[f"s{seed}_trainer_tau{tau}_loss"])) < 1e-12
+            np.testing.assert_allclose(o["dx"], g[f"s{seed}_trainer_tau{tau}_dv"], rtol=2e-6, atol=1e-9)
+            v, t = g[f"s{seed}_v"].astype(np.float64), g[f"s{seed}_t"].astype(np.float64)
+            o = cf.ntxent(v, t, tau, normalize=True, clamp_tau=True)
+            assert abs(o["loss"] - float(g[f"s{seed}_comp_tau{tau}_loss"])) < 1e-12
+            np.testing.assert_allclose(o["dy"], g[f"s{seed}_comp_tau{tau}_dt"], rtol=2e-6, atol=1e-9)
+    import torch
+    from oracle import torch_port as tp
+    W, hw, hl = (torch.from_numpy(g[k]).double() for k in ("lm_W", "lm_hw", "lm_hl"))
+    yw, yl, mw, ml = (torch.from_numpy(g[k]) for k in ("lm_yw", "lm_yl", "lm_mw", "lm_ml"))
+    loss = tp.preference_loss_trainer(tp.lm_head(hw, W), tp.lm_head(hl, W), yw, yl, mw, ml, 0.1)
+    assert abs(loss.item() - float(g["lm_loss"])) < 1e-12

@@ -5,6 +5,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
+from preference_guided_image_captioning_alignment_b200 import _lib
 from preference_guided_image_captioning_alignment_b200 import functional as F
 
 dev = "cuda"
@@ -36,7 +37,7 @@ def step(ev=None):
 
 
 for mode in ("1", "0"):
-    os.environ["PGICA_SGG_FUSED"] = mode
+    _lib.set_option("sgg_fused", int(mode))
     for _ in range(2):
         step()
     torch.cuda.synchronize()

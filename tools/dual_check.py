@@ -6,7 +6,16 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
+from preference_guided_image_captioning_alignment_b200 import _lib
 from preference_guided_image_captioning_alignment_b200 import functional as F
+
+
+def _set_plan(plan):
+    """"R2,C2" pins the dual kernel's role split (options sggf_plan_r2 / sggf_plan_c2); None hands it back to the planner."""
+    r2, c2 = (int(v) for v in plan.split(",")) if plan else (0, 0)
+    _lib.set_option("sggf_plan_r2", r2)
+    _lib.set_option("sggf_plan_c2", c2)
+
 
 dev = "cuda"
 what = sys.argv[1] if len(sys.argv) > 1 else "all"
@@ -33,9 +42,9 @@ def ref(x, y, row, col):
 
 def case(mx, my, k, mode, plan=None):
     if plan:
-        os.environ["PGICA_SGGF_PLAN"] = plan
+        _set_plan(plan)
     else:
-        os.environ.pop("PGICA_SGGF_PLAN", None)
+        _set_plan(None)
     torch.manual_seed(mx + my)
     x = (torch.randn(mx, k, device=dev) * 0.5).to(torch.bfloat16)
     y = (torch.randn(my, k, device=dev) * 0.2).to(torch.bfloat16)
@@ -63,7 +72,7 @@ if what in ("small", "all"):
     case(2048, 5003, 1024, "row")
 
 if what in ("cfg2", "all"):
-    os.environ.pop("PGICA_SGGF_PLAN", None)
+    _set_plan(None)
     B, T, d, V = 16, 128, 1024, 50257
     g = torch.Generator().manual_seed(1234)
     W = (torch.randn(V, d, generator=g) * 0.02).to(torch.bfloat16).to(dev)
@@ -72,13 +81,13 @@ if what in ("cfg2", "all"):
     m = torch.ones(2 * B, T, dtype=torch.long, device=dev)
     seq, lse, _, rl, rw, _ = F.lmhead_logprob_fwd(H, W, y, m, False)
     gseq = torch.randn(2 * B, device=dev)
-    os.environ["PGICA_SGG_FUSED"] = "0"
+    _lib.set_option("sgg_fused", 0)
     dh0, dw0 = F.lmhead_logprob_bwd(H, W, rl, rw, lse, gseq, False)
-    os.environ["PGICA_SGG_FUSED"] = "1"
+    _lib.set_option("sgg_fused", 1)
     plans = [None] + [p for p in os.environ.get("DUAL_PLANS", "32,22;32,20;32,21").split(";") if p]
     for plan in plans:
         if plan:
-            os.environ["PGICA_SGGF_PLAN"] = plan
+            _set_plan(plan)
         dh1, dw1 = F.lmhead_logprob_bwd(H, W, rl, rw, lse, gseq, False)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -91,7 +100,7 @@ if what in ("cfg2", "all"):
         torch.cuda.synchronize()
         print(f"cfg2 dual plan={plan}: {e0.elapsed_time(e1) / 10:.3f} ms/bwd; vs split: dH rel {rel(dh1.float(), dh0.float()):.2e} "
               f"dW rel {rel(dw1, dw0):.2e}", flush=True)
-    os.environ["PGICA_SGG_FUSED"] = "0"
+    _lib.set_option("sgg_fused", 0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(10):
@@ -101,8 +110,8 @@ if what in ("cfg2", "all"):
     print(f"cfg2 split: {e0.elapsed_time(e1) / 10:.3f} ms/bwd")
 
 if what in ("bf16dw",):
-    os.environ.pop("PGICA_SGGF_PLAN", None)
-    os.environ["PGICA_SGG_FUSED"] = "1"
+    _set_plan(None)
+    _lib.set_option("sgg_fused", 1)
     B, T, d, V = 16, 128, 1024, 50257
     g = torch.Generator().manual_seed(1234)
     W = (torch.randn(V, d, generator=g) * 0.02).to(torch.bfloat16).to(dev)

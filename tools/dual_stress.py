@@ -7,7 +7,16 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
+from preference_guided_image_captioning_alignment_b200 import _lib
 from preference_guided_image_captioning_alignment_b200 import functional as F
+
+
+def _set_plan(plan):
+    """"R2,C2" pins the dual kernel's role split (options sggf_plan_r2 / sggf_plan_c2); None hands it back to the planner."""
+    r2, c2 = (int(v) for v in plan.split(",")) if plan else (0, 0)
+    _lib.set_option("sggf_plan_r2", r2)
+    _lib.set_option("sggf_plan_c2", c2)
+
 
 dev = "cuda"
 cases = int(sys.argv[1]) if len(sys.argv) > 1 else 40
@@ -30,9 +39,9 @@ for i in range(cases):
         r2 = rng.randint(1, max(1, min(12, (70 // S) // 2)))
         c2 = rng.randint(1, max(1, min(12, (70 // S) // 2)))
         plan = f"{r2},{c2}"
-        os.environ["PGICA_SGGF_PLAN"] = plan
+        _set_plan(plan)
     else:
-        os.environ.pop("PGICA_SGGF_PLAN", None)
+        _set_plan(None)
     torch.manual_seed(i)
     x = (torch.randn(mx, k, device=dev) * 0.3).to(torch.bfloat16)
     y = (torch.randn(my, k, device=dev) * 0.3).to(torch.bfloat16)

@@ -5,6 +5,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
+from preference_guided_image_captioning_alignment_b200 import _lib
 from preference_guided_image_captioning_alignment_b200 import functional as F
 
 dev = "cuda"
@@ -15,7 +16,7 @@ for ra, rb in ((64, 64), (4096, 4096), (4096, 32768), (16384, 16384)):
     lr, dg, lc = F.ntxent_fwd(a, b, 2.0)
     res = {}
     for mode in ("1", "0"):
-        os.environ["PGICA_SGG_FUSED"] = mode
+        _lib.set_option("sgg_fused", int(mode))
         for _ in range(3):
             out = F.ntxent_bwd(a, b, 2.0, 0, lr, lc, one, 1.0 / (2 * ra))
         torch.cuda.synchronize()
