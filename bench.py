@@ -32,7 +32,21 @@ UNIT = "pair-tokens/s"
 WORKLOAD = ("cfg2: Stage-2 DPO loss head, GPT-2 Medium LM head d=1024 V=50257, chosen/rejected seq 128, 16 pairs per "
             "GPU, beta=0.1, policy fwd+bwd + frozen-reference fwd, random-init, all-ones masks")
 FLOP_PER_PAIR_TOKEN = 16 * CFG["d"] * CFG["vocab"]  # policy fwd 4dV + ref fwd 4dV + policy bwd 8dV
-NCU_TRAFFIC_DUAL = 824.6e6  # dram read + write of one sggf_kernel launch on cfg2, two-chunk plan (profiles/r1_ncu_full_sggf.txt)
+
+
+def ncu_traffic(kernel_prefix):
+    """DRAM bytes (read + write) per launch of a kernel, from the committed `ncu --set full` summary
+    profiles/ncu_traffic.json (written by tools/ncu_summary.py from the capture of this very workload).  None when no
+    capture of that kernel is on file: the bench never invents the number."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        table = json.load(open(path))
+    except Exception:
+        return None
+    for name, rec in table.items():
+        if name.startswith(kernel_prefix):
+            return rec.get("dram_bytes_per_launch")
+    return None
 
 
 def log(*a):
@@ -126,29 +140,66 @@ def cpu_reference_step_inputs(pairs, seed=1234):
     return W, Wr, hs, yc, yr, m
 
 
-def time_cpu_reference(pairs, steps, warmup):
-    """The reference's CPU path: fp32 torch ops on the host cores (oracle/torch_port.dpo_head_step)."""
+def reference_cpu_step_fn():
+    """One Stage-2 head evaluation on the host cores, written with the reference's OWN modules when its package can be
+    imported (baseline/_ref on the GPU box, /root/reference in the build container: components.py is loaded by file
+    path, it needs torch only) -> kind "reference"; otherwise the restatement in oracle/torch_port.py -> kind "port"."""
     import torch
 
+    from oracle import ref_model
     from oracle import torch_port as tp
+    src = ref_model.reference_src()
+    if src is not None:
+        import importlib.util
+        path = os.path.join(src, "preference_guided_image_captioning_alignment", "models", "components.py")
+        spec = importlib.util.spec_from_file_location("_pgica_ref_components_bench", path)
+        comp = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(comp)
+        dpo = comp.DPOPreferenceLoss(beta=CFG["beta"])
+        csl = comp.compute_sequence_logprobs
+
+        def step(hc, hr, W, yc, yr, m, rhc, rhr, Wr):
+            lin = torch.nn.functional.linear  # GPT2LMHeadModel.lm_head: nn.Linear without bias (modeling_gpt2.py:651,706)
+            pc, pr = csl(lin(hc, W), yc, m), csl(lin(hr, W), yr, m)
+            with torch.no_grad():
+                rc, rr = csl(lin(rhc, Wr), yc, m), csl(lin(rhr, Wr), yr, m)
+            loss, metrics = dpo(pc, pr, rc, rr)
+            loss.backward()
+            return loss.detach()
+        return step, "reference"
+
+    def step(hc, hr, W, yc, yr, m, rhc, rhr, Wr):
+        return tp.dpo_head_step(hc, hr, W, yc, yr, m, m, rhc, rhr, Wr, CFG["beta"])[0]
+    return step, "port"
+
+
+def time_cpu_reference(pairs, steps, warmup):
+    """The reference's CPU path (fp32 torch ops on all host threads): policy fwd+bwd + frozen-reference fwd + DPO loss
+    on `pairs` preference pairs.  -> (pair-tokens/s from the MEDIAN step, median s/step, threads, kind, total s)"""
+    import torch
     torch.set_num_threads(os.cpu_count() or 1)
     W, Wr, hs, yc, yr, m = cpu_reference_step_inputs(pairs)
     W.requires_grad_(True)
     hs[0].requires_grad_(True)
     hs[1].requires_grad_(True)
+    fn, kind = reference_cpu_step_fn()
 
     def step():
         W.grad = hs[0].grad = hs[1].grad = None
-        return tp.dpo_head_step(hs[0], hs[1], W, yc, yr, m, m, hs[2], hs[3], Wr, CFG["beta"])
+        return fn(hs[0], hs[1], W, yc, yr, m, hs[2], hs[3], Wr)
 
     for _ in range(warmup):
         step()
-    t0 = time.perf_counter()
+    times = []
+    t_all = time.perf_counter()
     for _ in range(steps):
+        t0 = time.perf_counter()
         step()
-    dt = time.perf_counter() - t0
-    tokens = pairs * (CFG["seq_len"] - 1) * steps
-    return tokens / dt, dt / steps, torch.get_num_threads()
+        times.append(time.perf_counter() - t0)
+    total = time.perf_counter() - t_all
+    med = statistics.median(times)
+    tokens = pairs * (CFG["seq_len"] - 1)
+    return tokens / med, med, torch.get_num_threads(), kind, total
 
 
 def cpu_model_name():
@@ -162,17 +213,25 @@ def cpu_model_name():
 
 
 def run_reference(args, rank):
+    """`--impl reference`: the reference's CPU implementation of the SAME config (all 16 pairs per step, the requested
+    number of steps), every step measured."""
     if rank != 0:
         return
-    pairs = 4  # bounded sample: 4 of the 16 pairs per step (throughput is linear in pairs); ~1-2 s of CPU work
-    value, sec, threads = time_cpu_reference(pairs, max(args.steps, 1), max(min(args.warmup, 2), 1))
+    pairs = CFG["pairs"]
+    steps, warmup = max(args.steps, 1), max(min(args.warmup, 2), 1)
+    value, sec, threads, kind, total = time_cpu_reference(pairs, steps, warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec * 1e3 * CFG["pairs"] / pairs, "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "parallelism": f"dp{args.gpus}"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{pairs} of 16 pairs per step (linear in pairs), fp32 torch ops, {cpu_model_name()}"},
+        "config": {"workload": WORKLOAD, "pairs_per_gpu": pairs, "seq_len": CFG["seq_len"], "d": CFG["d"],
+                   "vocab": CFG["vocab"], "parallelism": f"dp{args.gpus}",
+                   "note": f"CPU arm: {warmup} warm-up (capped at 2: a step takes ~1 s) + {steps} measured steps, "
+                           f"median step; timed region {total:.1f} s"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": f"all {pairs} pairs per step, {steps} steps (median), fp32 torch ops of the "
+                                   f"{'reference modules' if kind == 'reference' else 'restated reference'}, "
+                                   f"{cpu_model_name()}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -317,7 +376,10 @@ def run_ours(args, rank, world, local_rank):
     # copy stream (every step still pays exactly one host->device copy of its inputs inside the timed region, and one
     # device->host read of its loss).  PGICA_BENCH_E2E_GRAPH=0 times the eager module calls instead.
     head = pg.FusedDPOHead(beta=beta)
-    Wp = W.clone().requires_grad_(True)
+    # fp32 master copy of the tied weight, as in the reference model: the op keeps a bf16 operand copy that is recast
+    # only when the Parameter changes (ops.cached_bf16), and hands back an fp32 dW — the same gradient dtype, and at
+    # N > 1 the same all-reduce (fp32 dW + the packed scalars), as the resident arm above
+    Wp = W.float().requires_grad_(True)
     h2d = sum(t.numel() * t.element_size() for t in (H_host, Hr_host, y_host, m_host))
     use_graph = os.environ.get("PGICA_BENCH_E2E_GRAPH", "1") != "0"
     copy_stream = torch.cuda.Stream(device=dev)
@@ -363,7 +425,10 @@ def run_ours(args, rank, world, local_rank):
             hin.requires_grad_(False)
             grad_w = Wp.grad
         if world > 1:
-            dist.all_reduce(grad_w)  # the module API hands back an ordinary autograd gradient: NCCL all-reduce
+            dist.all_reduce(grad_w)  # the module API hands back an ordinary autograd gradient: NCCL all-reduce (fp32)
+            g = steps_g[slot] if use_graph else None
+            state["packed"] = torch.cat([(g.loss if g else loss).detach().reshape(1), (g.metrics if g else metrics)])
+            dist.all_reduce(state["packed"])
         consumed[slot].record()
         # device -> host read of the step's result; the graphed step copies the loss to pinned memory at the end of its
         # forward graph, so the host reads it while the backward is still running
@@ -431,9 +496,10 @@ def run_ours(args, rank, world, local_rank):
     dom = max(flops, key=lambda n: phase_ms[n])
     kname = {"fwd_policy": "gemm_lse_kernel", "fwd_reference": "gemm_lse_kernel", "bwd_dH": "sggx_kernel<4,row>",
              "bwd_dW": "sggx_kernel<4,col>", "bwd_dH_dW": "sggf_kernel<row> (dual: dH and dW from one recomputation)"}
-    # DRAM bytes per launch of that kernel from `ncu --set full` (profiles/r1_ncu_full_*.txt), cfg2 shape
-    traffic = {"fwd_policy": 121.4e6, "fwd_reference": 120.3e6, "bwd_dH": 116.9e6, "bwd_dW": 282.1e6,
-               "bwd_dH_dW": NCU_TRAFFIC_DUAL}
+    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of this workload
+    short = {"fwd_policy": "gemm_lse_kernel", "fwd_reference": "gemm_lse_kernel", "bwd_dH": "sggx_kernel",
+             "bwd_dW": "sggx_kernel", "bwd_dH_dW": "sggf_kernel"}
+    traffic = {n: ncu_traffic(short[n]) for n in short}
     roofline = {"bound": "tensor", "kernel": kname[dom],
                 "phase": dom, "achieved": kernels[dom]["tflops"], "peak": pk["burst"], "unit": "TFLOP/s",
                 "frac": kernels[dom]["tflops"] / pk["burst"], "peak_source": pk["source"] + " bf16 dense, burst",
@@ -441,10 +507,19 @@ def run_ours(args, rank, world, local_rank):
                 "executed_tflops": kernels[dom]["tflops"] * (1.5 if dom == "bwd_dH_dW" else 2.0 if dom.startswith("bwd") else 1.0),
                 "step_achieved": FLOP_PER_PAIR_TOKEN * pair_tokens_step / (elapsed_ms / args.steps) / 1e9,
                 "step_frac": FLOP_PER_PAIR_TOKEN * pair_tokens_step / (elapsed_ms / args.steps) / 1e9 / pk["burst"]}
-    cpu_val, cpu_sec, cpu_threads = time_cpu_reference(4, 2, 1)
+    cpu_val, cpu_sec, cpu_threads, cpu_kind, cpu_total = time_cpu_reference(CFG["pairs"], 5, 1)
     extras = ntxent_extras(torch, F, dev)
     if dist_ntxent is not None:
         extras["global_negatives"] = dist_ntxent
+    compaction = torch_eager = cfg5 = None
+    if world == 1:
+        compaction = compaction_extra(torch, pg, dev, W.float())
+        torch_eager = torch_eager_extra(torch, dev)
+        cfg5 = cfg5_extra()
+    also = {"cfg3_ntxent_global_negatives": dist_ntxent, "cfg4_dpo_seq512": cfg4,
+            "cfg5_stage2_step": None if cfg5 is None else {k: cfg5.get(k) for k in ("speedup", "first_loss_rel_diff", "unavailable", "error", "skipped") if k in cfg5},
+            "cfg2_valid_row_compaction": None if compaction is None else {k: compaction[k] for k in ("scored_rows", "rows", "speedup")},
+            "ntxent_single_gpu": extras}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -458,10 +533,13 @@ def run_ours(args, rank, world, local_rank):
                                     "scatter inside the backward kernel (TMA stores into the owners' slots over NVLink) + "
                                     "local sum + copy-engine all-gather, fp32" if fused_reduce is not None
                                     else "nccl fp32 all-reduce after the backward"),
+                   "also_measured": also,
                    "l2": "inputs larger than L2: the step streams 2x103 MB of bf16 LM-head weights and writes a "
                          "206 MB fp32 dW (L2 = 126 MB)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "ms_per_step": e2e_ms / args.steps, "last_loss": last_loss,
+                "ms_per_step": e2e_ms / args.steps,
+                "last_loss": last_loss if world == 1 else float(state["packed"][0].item()),
+                "last_loss_read_in_step": last_loss,  # what the step's D2H read returned (this rank's share when N > 1)
                 "api": "GraphedDPOStep.launch + loss_value (CUDA graphs of FusedDPOHead.forward_stacked and its backward)" if use_graph
                        else "FusedDPOHead.forward_stacked + backward, eager"},
         "gpu_launches": int(launches),
@@ -469,10 +547,16 @@ def run_ours(args, rank, world, local_rank):
         "roofline": roofline,
         "kernels": kernels,
         "phase_ms": phase_ms,
-        "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cpu_threads, "kind": "port",
-                         "sample": f"2 steps of 4 pairs (of 16; linear in pairs), fp32 torch ops, {cpu_model_name()}"},
+        "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cpu_threads, "kind": cpu_kind,
+                         "sample": f"5 steps (median, {cpu_sec * 1e3:.0f} ms) of all 16 pairs after 1 warm-up, fp32 "
+                                   f"torch ops of the {'reference modules' if cpu_kind == 'reference' else 'restated reference'}"
+                                   f", {cpu_total:.1f} s of CPU time, {cpu_model_name()}"},
         "ntxent": extras,
+        "global_negatives": dist_ntxent,
         "cfg4": cfg4,
+        "cfg5": cfg5,
+        "valid_row_compaction": compaction,
+        "torch_eager_same_gpu": torch_eager,
         "grad_norm_clip": gradclip,
     }
     emit(line)
@@ -520,6 +604,106 @@ def cfg4_extra(torch, dist, F, dev, rank, world, W, Wr, barrier):
                         + (", NCCL fp32 all-reduce of dW" if world > 1 else ""),
             "ms_per_step": ms, "pair_tokens_per_s": tokens / (ms * 1e-3),
             "algorithmic_tflops_per_gpu": 16.0 * d * V * B * (T - 1) / ms / 1e9}
+
+
+def compaction_extra(torch, pg, dev, W32):
+    """Valid-row compaction on cfg2's shape with the reference's real padding statistics: 16 pairs,
+    seq 128, right-padded captions of U[10, 20] real tokens (pkg/data/preprocessing.py:223-231).  The trainer-facing
+    path — PreferenceLoss on LazyLogits, fp32 hidden states and fp32 tied weight — forward + backward; only scored
+    positions count as pair-tokens.  Next to it the same batch through the full-row op (every row, masked or not)."""
+    from preference_guided_image_captioning_alignment_b200 import ops
+    from preference_guided_image_captioning_alignment_b200.losses import LazyLogits
+    B, T, d, V = CFG["pairs"], CFG["seq_len"], CFG["d"], CFG["vocab"]
+    g = torch.Generator().manual_seed(99)
+    hw = torch.randn(B, T, d, generator=g).to(dev).requires_grad_(True)
+    hl = torch.randn(B, T, d, generator=g).to(dev).requires_grad_(True)
+    W = W32.detach().clone().requires_grad_(True)
+    yw, yl = (torch.randint(0, V, (B, T), generator=g).to(dev) for _ in range(2))
+    lens = torch.randint(10, 21, (2, B), generator=g)
+    mw, ml = ((torch.arange(T)[None] < lens[i][:, None]).long().to(dev) for i in range(2))
+    scored = int(mw[:, 1:].sum() + ml[:, 1:].sum())
+    pl = pg.PreferenceLoss(CFG["beta"])
+
+    def compact_step():
+        W.grad = hw.grad = hl.grad = None
+        loss = pl(LazyLogits(hw, W), LazyLogits(hl, W), yw, yl, mw, ml)
+        loss.backward()
+        return loss
+
+    def full_step():
+        W.grad = hw.grad = hl.grad = None
+        lw = ops.lmhead_seq_logprob(hw, W, yw, mw, True)[0]
+        ll = ops.lmhead_seq_logprob(hl, W, yl, ml, True)[0]
+        loss = ops.dpo_loss(lw, ll, None, None, CFG["beta"], 0.0, B)[0]
+        loss.backward()
+        return loss
+
+    out = {"workload": f"cfg2 shape, right-padded captions U[10,20] of {T}: {scored} scored rows of {2 * B * T}; "
+                       "PreferenceLoss fwd+bwd, fp32 hidden/weight, reference-free (trainer variant)",
+           "scored_rows": scored, "rows": 2 * B * T}
+    for name, fn in (("compacted", compact_step), ("all_rows", full_step)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            loss = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        out[name] = {"ms_per_step": ms, "valid_pair_tokens_per_s": 0.5 * scored / (ms * 1e-3), "loss": loss.item()}
+    out["speedup"] = out["all_rows"]["ms_per_step"] / out["compacted"]["ms_per_step"]
+    return out
+
+
+def torch_eager_extra(torch, dev):
+    """The reference's torch path for cfg2 on the SAME B200 (what a user of the reference gets on this GPU without this
+    library): F.linear + compute_sequence_logprobs x4 + DPOPreferenceLoss + backward, logits materialised; fp32 with
+    TF32 off (the parity setting) and bf16 autocast-free (weights and activations cast to bf16)."""
+    fn, kind = reference_cpu_step_fn()
+    W, Wr, hs, yc, yr, m = cpu_reference_step_inputs(CFG["pairs"])
+    out = {"kind": kind}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    for name, dt in (("fp32_tf32_off", torch.float32), ("bf16", torch.bfloat16)):
+        Wd = W.to(dev, dt).requires_grad_(True)
+        Wrd = Wr.to(dev, dt)
+        h = [x.to(dev, dt) for x in hs]
+        h[0].requires_grad_(True)
+        h[1].requires_grad_(True)
+        ycd, yrd, md = yc.to(dev), yr.to(dev), m.to(dev)
+
+        def step():
+            Wd.grad = h[0].grad = h[1].grad = None
+            return fn(h[0], h[1], Wd, ycd, yrd, md, h[2], h[3], Wrd)
+
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        out[name] = {"ms_per_step": ms, "pair_tokens_per_s": CFG["pairs"] * (CFG["seq_len"] - 1) / (ms * 1e-3),
+                     "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+        del Wd, Wrd, h
+        torch.cuda.empty_cache()
+    return out
+
+
+def cfg5_extra():
+    """BASELINE config 5 (tools/cfg5_step.py): the reference's own Stage-2 micro-step, unpatched vs install()ed."""
+    if os.environ.get("PGICA_BENCH_CFG5", "1") == "0":
+        return {"skipped": "PGICA_BENCH_CFG5=0"}
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import cfg5_step
+        return cfg5_step.run(batch=8, steps=5, warmup=2, log=log)
+    except Exception as e:  # an extra must never take the headline down with it
+        return {"error": repr(e)[:300]}
 
 
 def gradclip_extra(torch, F, dev):

@@ -98,6 +98,9 @@ struct OptionTable {
     auto env_int = [](const char* name, Option o, OptionTable* t) {
       if (const char* e = getenv(name)) t->v[o].store(atoll(e));
     };
+    // a profiler whose kernel replay cannot re-issue cooperative cluster launches is attached: plain launches by
+    // default (PGICA_SGGF_COOP=1 keeps the cooperative launch, e.g. under `ncu --replay-mode application`)
+    if (getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("CUDA_INJECTION64_PATH")) v[kOptSggfCoop].store(0);
     env_int("PGICA_SGG_FUSED", kOptSggFused, this);
     env_int("PGICA_SGGF_COOP", kOptSggfCoop, this);
     env_int("PGICA_SGGF_SPREAD", kOptSggfSpread, this);
@@ -112,8 +115,6 @@ struct OptionTable {
         v[kOptSggfPlanC2].store(c2);
       }
     }
-    // a profiler that cannot replay cooperative cluster launches is attached: plain launches, set once here
-    if (getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("CUDA_INJECTION64_PATH")) v[kOptSggfCoop].store(0);
   }
 };
 OptionTable& options() {
