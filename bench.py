@@ -263,28 +263,26 @@ def run_ours(args, rank, world, local_rank):
     m_host = torch.ones(2 * B, T, dtype=torch.long).pin_memory()
     H, Hr, y, m = H_host.to(dev), Hr_host.to(dev), y_host.to(dev), m_host.to(dev)
     one = torch.ones((), device=dev)
-    fused = os.environ.get("PGICA_SGG_FUSED", "1") != "0"  # dH and dW from one recomputation (sgg_f.cu) vs two launches
+    fused = _lib.get_option("sgg_fused") != 0  # dH and dW from one recomputation (sgg_f.cu) vs two launches
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    reducer = None
-    fused_reduce = None
-    state_r = {}
-    if world > 1 and fused and os.environ.get("PGICA_DW_ALLREDUCE", "nccl") == "fused":
-        # opt-in: scatter of dW inside the backward kernel (TMA stores into the owners' symmetric-memory slots over
-        # NVLink) + local sum + copy-engine all-gather.  Measured slower than NCCL after the kernel at N >= 4
-        # (profiles/r1_scaling_notes.md), so NCCL is the default.
+    # N > 1: how the LM-head weight gradient is summed over the ranks.
+    #   overlap (default)  distributed.OverlappedDWAllReduce: the dual backward kernel publishes per-segment progress,
+    #                      a co-resident peer-memory all-reduce kernel (csrc/peer_ar.cu) sums finished segments over
+    #                      NVLink while the rest of the vocabulary is still being computed; the packed loss / metric
+    #                      scalars ride in the padding rows of the same buffer
+    #   nccl               plain NCCL fp32 all-reduce after the kernel + a second small all-reduce for the scalars
+    ar_mode = os.environ.get("PGICA_DW_ALLREDUCE", "overlap") if world > 1 else "none"
+    overlap = None
+    if world > 1 and ar_mode == "overlap" and fused:
         from preference_guided_image_captioning_alignment_b200 import distributed as D
-        fused_reduce = D.FusedDWReduce(V, d, dev)
-    if world > 1 and not fused and os.environ.get("PGICA_DW_ALLREDUCE", "peer") == "peer":
-        from preference_guided_image_captioning_alignment_b200 import distributed as D
-        reducer = D.PeerAllReduce((V, d), dev)
-        reducer.trace = bool(os.environ.get("PGICA_BENCH_TRACE_AR"))
-        state_r["done"] = torch.cuda.Event()
-        state_r["done"].record()
+        overlap = D.OverlappedDWAllReduce(V, d, dev, segments=int(os.environ.get("PGICA_DW_SEGMENTS", "8")))
+    elif world > 1:
+        ar_mode = "nccl"
 
     # ------------------------------------------------------------------ resident step (functional API + events)
     def resident_step(ev=None):
@@ -299,33 +297,25 @@ def run_ours(args, rank, world, local_rank):
         loss, metrics, dpc = F.dpo_loss_fwd(seq_p[:B], seq_p[B:], seq_r[:B], seq_r[B:], beta, 0.0, n_global)
         gseq = F.dpo_grad_seq(dpc, one)
         mark(3)
-        if fused_reduce is not None:
-            dh, dw = fused_reduce.backward(H, W, rl, rw, lse_p, gseq, False)
-            mark(4)
+        if overlap is not None:
+            packed = torch.cat([loss.reshape(1), metrics])
+            dh, dw, done, packed = overlap.backward(H, W, rl, rw, lse_p, gseq, False, scalars=packed)
+            mark(4)  # end of the backward kernel on the main stream
             mark(5)
-        elif fused:
+            torch.cuda.current_stream().wait_event(done)  # dW (and the scalars) summed over the ranks
+            mark(6)
+            return packed[0], dh, dw
+        if fused:
             dh, dw = F.lmhead_logprob_bwd(H, W, rl, rw, lse_p, gseq, False)
             mark(4)
             mark(5)
         else:
-            if reducer is not None:
-                torch.cuda.current_stream().wait_event(state_r["done"])  # last step's all-reduce has left the buffer
-            _, dw = F.lmhead_logprob_bwd(H, W, rl, rw, lse_p, gseq, False, need_dhidden=False,
-                                         dweight_out=reducer.view if reducer is not None else None)
+            _, dw = F.lmhead_logprob_bwd(H, W, rl, rw, lse_p, gseq, False, need_dhidden=False)
             mark(4)
-            if reducer is not None:
-                dw_ready = torch.cuda.Event()
-                dw_ready.record()
             dh, _ = F.lmhead_logprob_bwd(H, W, rl, rw, lse_p, gseq, False, need_dweight=False)
             mark(5)
         if world > 1:
-            if reducer is not None:
-                # copy-engine all-reduce of dW (distributed.PeerAllReduce), enqueued after the dH kernel so that its
-                # clusters are resident first; the peer copies use no SM and overlap dH
-                state_r["done"] = reducer.all_reduce(after=dw_ready)
-                torch.cuda.current_stream().wait_event(state_r["done"])
-            elif fused_reduce is None:
-                dist.all_reduce(dw)
+            dist.all_reduce(dw)
             packed = torch.cat([loss.reshape(1), metrics])
             dist.all_reduce(packed)
             mark(6)
@@ -347,12 +337,6 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     clocks = sampler.stop() if sampler else None
     launches = lib.pgica_kernel_launches() - launches0
-    if reducer is not None and reducer.trace and rank == 0:
-        tr = reducer.last_trace
-        ref_ev = events[-1][4]  # end of the dW kernel of the last step
-        log("peer all-reduce timeline (ms after the dW kernel finished): " +
-            ", ".join(f"{n} {ref_ev.elapsed_time(e):.3f}" for n, e in tr) +
-            f"; dH kernel done {ref_ev.elapsed_time(events[-1][5]):.3f}")
     elapsed_ms = t_begin.elapsed_time(t_end)
     # order of marks: 0 start,1 after fwd_policy,2 after fwd_ref,3 after dpo,4 after dW (or the fused backward),
     # 5 after dH,(6 after all-reduce)
@@ -528,11 +512,10 @@ def run_ours(args, rank, world, local_rank):
                    "parallelism": f"dp{world}", "pair_tokens_per_step_per_gpu": pair_tokens_step,
                    "backward": "dual kernel: dH and dW from one recomputation of the logits" if fused
                                else "one launch per product",
-                   "dw_allreduce": ("none" if world == 1 else "copy-engine peer all-reduce overlapping dH"
-                                    if reducer is not None else
-                                    "scatter inside the backward kernel (TMA stores into the owners' slots over NVLink) + "
-                                    "local sum + copy-engine all-gather, fp32" if fused_reduce is not None
-                                    else "nccl fp32 all-reduce after the backward"),
+                   "dw_allreduce": ("none" if world == 1 else
+                                    f"progress-gated peer-memory all-reduce kernel beside the backward kernel, fp32, "
+                                    f"{overlap.nseg} vocabulary segments; loss/metric scalars in the same buffer"
+                                    if overlap is not None else "nccl fp32 all-reduce after the backward + nccl scalars"),
                    "also_measured": also,
                    "l2": "inputs larger than L2: the step streams 2x103 MB of bf16 LM-head weights and writes a "
                          "206 MB fp32 dW (L2 = 126 MB)"},

@@ -133,23 +133,49 @@ int pgica_softmax_grad_gemm_dual(const void* x, const void* y, int64_t mx, int64
                                  void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Dual softmax-gradient GEMM fused with the SCATTER half of the data-parallel all-reduce of out_y (the LM-head
- * weight gradient) over the GPUs of an NVLink node: instead of writing out_y locally, every 128-row tile
- * of out_y is stored (TMA, fp32) into THIS rank's slot in the memory of the rank that owns those rows — peer memory
- * mapped into this process (e.g. torch symmetric memory).  Rank r owns rows [r * rows_per_owner, (r+1) *
- * rows_per_owner), rows_per_owner a multiple of 128; out_y_peers_host[r] is the base of the fp32 [rows_per_owner][k]
- * slot that rank r reserves for the caller's tiles (HOST array of n_peers <= 16 device pointers).  After the launch
- * and a barrier across the ranks every owner sums its n_peers slots (pgica_sum_into_f32) and holds the reduced rows;
- * an all-gather completes the all-reduce.  x must fit one chunk of the kernel (<= ~32 row blocks at k = 1024), else
- * PGICA_ERR_INVALID_ARGUMENT.  tmaps_device: 128 * n_peers bytes of device scratch, 128-byte aligned.  Workspace as
- * for pgica_softmax_grad_gemm_dual.
+ * Dual softmax-gradient GEMM that PUBLISHES ITS PROGRESS on out_y, so that the data-parallel all-reduce of the LM-head
+ * weight gradient (what DDP's bucket reducer does for the reference, pkg/training/trainer.py:201,492,616)
+ * can run over NVLink while the tensor cores are still computing the rest of the vocabulary.  out_y rows are cut into
+ * segments of rows_per_segment (a multiple of 256); whenever a drain warp has seen the TMA stores of a final out_y tile
+ * complete it adds 1 to progress[segment] with release semantics at SYSTEM scope.  A full segment has received
+ * (*increments_per_256_rows_host) * rows_per_segment / 256 increments (fewer for the ragged last one: count whole
+ * 256-row pairs of ceil(my / 256)); the counters only ever grow — the caller compares against a per-launch target.
+ * pgica_peer_allreduce_progress below is the consumer.  out_y is fp32 and x must fit one chunk of the kernel.
  * ---------------------------------------------------------------------------------------------- */
-int pgica_softmax_grad_gemm_dual_scatter(const void* x, const void* y, int64_t mx, int64_t my, int64_t k, float scale,
-                                         const float* r_lse, const float* r_coef, const int32_t* r_tgt,
-                                         const float* c_lse, const float* c_coef, const int32_t* c_tgt, void* out_x,
-                                         int out_x_is_bf16, const void* const* out_y_peers_host, int n_peers,
-                                         int64_t rows_per_owner, void* tmaps_device, void* workspace,
-                                         size_t workspace_bytes, void* stream);
+int pgica_softmax_grad_gemm_dual_progress(const void* x, const void* y, int64_t mx, int64_t my, int64_t k, float scale,
+                                          const float* r_lse, const float* r_coef, const int32_t* r_tgt,
+                                          const float* c_lse, const float* c_coef, const int32_t* c_tgt, void* out_x,
+                                          int out_x_is_bf16, void* out_y, int out_y_is_bf16, uint32_t* progress,
+                                          int64_t rows_per_segment, int32_t* increments_per_256_rows_host,
+                                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sum-all-reduce of ONE fp32 buffer that lives at the same offset in the (peer-mapped, e.g. torch symmetric) memory of
+ * every GPU of an NVLink node, segment by segment, each segment as soon as every rank's producer kernel has finished
+ * it — a small kernel that runs BESIDE the producer (256 threads and a few dozen registers per CTA, no shared
+ * memory: it fits on the SMs the persistent dual kernel occupies):
+ *
+ *   for each segment s:  wait until progress[s] >= progress_target_host[s]          (local producer done; NULL: skip)
+ *                        flag barrier with the other ranks over peer memory            (every rank's segment s is final)
+ *                        owner rank r sums ITS 1/world slice of the segment from all `world` buffers (16-byte loads
+ *                        over NVLink, fixed rank order: deterministic, identical on every rank) and stores the result
+ *                        into all `world` buffers
+ *   final flag barrier (every owner's stores have landed everywhere)
+ *
+ * bufs_host[r] / flags_host[r]: rank r's buffer / flag area as mapped into THIS process (HOST arrays of `world`
+ * device pointers; world <= 16).  flags: >= 4 * world * (nseg + 1) bytes per rank, zeroed once before first use.
+ * seg_begin_host[0..nseg]: segment boundaries in ELEMENTS, multiples of 4 * world.  epoch: 1, 2, 3, ... for successive
+ * calls on the same flags.  local_sync: 8 bytes of device scratch of this rank, zeroed once.  max_ctas: grid size
+ * (0 = one CTA per SM; the same value for every call on one local_sync).  With progress != NULL the launch is preceded,
+ * on `stream`, by a cuStreamWaitValue32 on progress[0]: the kernel only becomes resident once the producer's grid is
+ * (its CTAs spin, and must not take SM resources a cooperative producer still needs to become resident).  `stream` must
+ * therefore not be the stream the producer was launched on.  Replaces the NCCL all-reduce after the backward
+ * (distributed.allreduce_dweight).
+ * ---------------------------------------------------------------------------------------------- */
+int pgica_peer_allreduce_progress(const void* const* bufs_host, const void* const* flags_host, int world, int rank,
+                                  const uint32_t* progress, const uint32_t* progress_target_host,
+                                  const int64_t* seg_begin_host, int nseg, uint32_t epoch, uint32_t* local_sync,
+                                  int max_ctas, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Stage-2 head, hidden-state level (logits never materialised).
@@ -179,15 +205,14 @@ int pgica_lmhead_logprob_bwd(const void* hidden, const void* weight, const int32
                              int64_t seqlen, int64_t d, int64_t vocab, int length_normalize, void* dhidden,
                              int dhidden_is_bf16, void* dweight, int dweight_is_bf16, void* workspace,
                              size_t workspace_bytes, void* stream);
-/* pgica_lmhead_logprob_bwd with the weight gradient scattered to its owners inside the kernel (see
- * pgica_softmax_grad_gemm_dual_scatter): dhidden is written locally, dweight tiles are stored into the caller's
- * slots at their owners.  workspace: pgica_lmhead_logprob_workspace_bytes() bytes. */
-int pgica_lmhead_logprob_bwd_scatter(const void* hidden, const void* weight, const int32_t* row_label,
-                                     const float* row_weight, const float* lse, const float* grad_seq, int64_t nseq,
-                                     int64_t seqlen, int64_t d, int64_t vocab, int length_normalize, void* dhidden,
-                                     int dhidden_is_bf16, const void* const* dweight_peers_host, int n_peers,
-                                     int64_t rows_per_owner, void* tmaps_device, void* workspace,
-                                     size_t workspace_bytes, void* stream);
+/* pgica_lmhead_logprob_bwd through pgica_softmax_grad_gemm_dual_progress: dweight (fp32, typically inside a symmetric
+ * buffer) is written locally and its progress published for pgica_peer_allreduce_progress. */
+int pgica_lmhead_logprob_bwd_progress(const void* hidden, const void* weight, const int32_t* row_label,
+                                      const float* row_weight, const float* lse, const float* grad_seq, int64_t nseq,
+                                      int64_t seqlen, int64_t d, int64_t vocab, int length_normalize, void* dhidden,
+                                      int dhidden_is_bf16, void* dweight, uint32_t* progress, int64_t rows_per_segment,
+                                      int32_t* increments_per_256_rows_host, void* workspace, size_t workspace_bytes,
+                                      void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Stage-2 head on COMPACTED rows.  Rows whose mask weight is zero, and the never-scored last position of every

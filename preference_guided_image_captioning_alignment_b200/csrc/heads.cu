@@ -99,28 +99,30 @@ int pgica_lmhead_logprob_bwd(const void* hidden, const void* weight, const int32
                                dweight, dweight_is_bf16, xws, xws_bytes, stream);
 }
 
-int pgica_lmhead_logprob_bwd_scatter(const void* hidden, const void* weight, const int32_t* row_label,
-                                     const float* row_weight, const float* lse, const float* grad_seq, int64_t nseq,
-                                     int64_t seqlen, int64_t d, int64_t vocab, int length_normalize, void* dhidden,
-                                     int dhidden_is_bf16, const void* const* dweight_peers_host, int n_peers,
-                                     int64_t rows_per_owner, void* tmaps_device, void* workspace,
-                                     size_t workspace_bytes, void* stream) {
-  PGICA_REQUIRE(hidden && weight && row_label && row_weight && lse && grad_seq && dhidden && dweight_peers_host,
-                "lmhead_logprob_bwd_scatter: null pointer");
+int pgica_lmhead_logprob_bwd_progress(const void* hidden, const void* weight, const int32_t* row_label,
+                                      const float* row_weight, const float* lse, const float* grad_seq, int64_t nseq,
+                                      int64_t seqlen, int64_t d, int64_t vocab, int length_normalize, void* dhidden,
+                                      int dhidden_is_bf16, void* dweight, uint32_t* progress, int64_t rows_per_segment,
+                                      int32_t* increments_per_256_rows_host, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+  PGICA_REQUIRE(hidden && weight && row_label && row_weight && lse && grad_seq && dhidden && dweight && progress,
+                "lmhead_logprob_bwd_progress: null pointer");
   const int64_t rows = nseq * seqlen;
   const size_t coef_bytes = align_up((size_t)rows * sizeof(float), 256);
   if (!workspace || workspace_bytes < coef_bytes + sggf_workspace_bytes()) {
-    set_error("lmhead_logprob_bwd_scatter: workspace too small (%zu < %zu)", workspace_bytes,
+    set_error("lmhead_logprob_bwd_progress: workspace too small (%zu < %zu)", workspace_bytes,
               coef_bytes + sggf_workspace_bytes());
     return PGICA_ERR_WORKSPACE_TOO_SMALL;
   }
+  PGICA_REQUIRE(sggf_supported(rows, vocab, d), "lmhead_logprob_bwd_progress: needs the dual kernel (d %% 512 == 0)");
   float* ncoef = static_cast<float*>(workspace);
   int rc = pgica_row_coef(grad_seq, row_weight, nseq, seqlen, length_normalize, -1.0f, ncoef, stream);
   if (rc != PGICA_OK) return rc;
-  return pgica_softmax_grad_gemm_dual_scatter(hidden, weight, rows, vocab, d, 1.0f, lse, ncoef, row_label, nullptr, nullptr,
-                                              nullptr, dhidden, dhidden_is_bf16, dweight_peers_host, n_peers,
-                                              rows_per_owner, tmaps_device, static_cast<uint8_t*>(workspace) + coef_bytes,
-                                              workspace_bytes - coef_bytes, stream);
+  return pgica_softmax_grad_gemm_dual_progress(hidden, weight, rows, vocab, d, 1.0f, lse, ncoef, row_label, nullptr,
+                                               nullptr, nullptr, dhidden, dhidden_is_bf16, dweight, 0, progress,
+                                               rows_per_segment, increments_per_256_rows_host,
+                                               static_cast<uint8_t*>(workspace) + coef_bytes,
+                                               workspace_bytes - coef_bytes, stream);
 }
 
 int pgica_ntxent_workspace_bytes(int64_t rows_a, int64_t rows_b, int64_t dim, size_t* bytes_host) {

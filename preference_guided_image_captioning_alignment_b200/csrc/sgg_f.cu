@@ -58,7 +58,10 @@ constexpr uint32_t kDrainBytes = 32768;                // holder: 4 drain warps 
 constexpr int kStagesPerTile = kBT / 64;              // 2
 constexpr int kThreads = 256;
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr size_t kSmem = 1024 + 7 * 32768 + 3 * kBT * 4 + 512;
+// No slack for aligning the dynamic window by hand: the array is declared __align__(1024) (checked on the device),
+// which keeps 1.5 KB of the SM's 228 KB free — enough for the 1 KB the hardware reserves per resident CTA, so that a
+// small shared-memory-free kernel (the progress-gated peer all-reduce, peer_ar.cu) can run BESIDE this one.
+constexpr size_t kSmem = 7 * 32768 + 3 * kBT * 4 + 512;
 static_assert(kPRing * kPStageBytes + kPBytes == 7 * 32768, "producer shared-memory plan");
 static_assert(2 * kPBytes + kCRing * kCStageBytes + kDrainBytes == 7 * 32768, "holder shared-memory plan");
 
@@ -112,8 +115,11 @@ struct SggfParams {
   const int* c_tgt;
   void* out_x;
   void* out_y;
-  const CUtensorMap* oy_maps;  // scatter mode: one fp32 map per owner rank's slot for THIS rank's tiles (device array), else null
-  int own_blocks;              // ... column tiles (128 rows of OutY) per owner
+  uint32_t* progress;     // optional: progress[s] += 1 (release, system scope) whenever a drain warp's stores of a FINAL
+  int cp_per_seg;         //   OutY tile of segment s = (column pair / cp_per_seg) are complete; a column pair (256 rows
+                          //   of OutY) contributes 8 * S increments.  Lets a co-resident kernel or the host start
+                          //   moving finished rows of OutY (the data-parallel all-reduce of dW) while the grid is
+                          //   still computing the rest.
   uint32_t* ready;        // [2*nP*D*2] use count + 1 of the tile that is complete in the slot
   uint32_t* done;         // [2*nP*D*2] consumers that have pulled a tile out of the slot, ever
 };
@@ -301,8 +307,12 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
             const __grid_constant__ CUtensorMap tm_x64, const __grid_constant__ CUtensorMap tm_y64,
             const __grid_constant__ CUtensorMap tm_s, const __grid_constant__ CUtensorMap tm_ox,
             const __grid_constant__ CUtensorMap tm_oy, const SggfParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = align_smem_1024(smem_raw);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) {
+    if (threadIdx.x == 0) printf("pgica: sggf_kernel dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
   float* s_cl = reinterpret_cast<float*>(smem + 7 * 32768);
   float* s_cc = s_cl + kBT;
   int* s_ct = reinterpret_cast<int*>(s_cc + kBT);
@@ -771,17 +781,20 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const int out_col0 = split * kNC;
     const uint64_t pol_stream = l2_policy_evict_first();
+    const int n_chunks = (p.RB2 + p.R2 - 1) / p.R2;
+    int pending_seg = -1;  // segment of the OutY tile whose TMA stores this warp has issued but not yet seen complete
+    auto signal_progress = [&](int seg) {
+      // TMA (async-proxy) stores complete -> generic-proxy release at SYSTEM scope: the reader may be another GPU
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p.progress + seg), "r"(1u) : "memory");
+    };
     LAP_DECL;
     for_each_holder_tile(
         p, is_y, hidx, [&](int, int, int, int, bool, int) {},
         [&](int period, int chunk, int pass) {
           const int blk = 2 * (is_y ? pass * p.C2 + hidx : chunk * p.R2 + hidx) + (int)rho;
           const bool bf16 = (is_y ? p.outy_bf16 : p.outx_bf16) != 0;
-          // scatter mode: an OutY tile is STORED into this rank's slot in the memory of the rank that owns its rows (peer
-          // memory over NVLink; plain stores — remote add-reductions run an order of magnitude slower); the owner sums
-          // the slots afterwards.  One chunk only (the planner is pinned), so nothing is ever accumulated remotely.
-          const bool scatter = is_y && p.oy_maps != nullptr;
-          const bool accumulate = !scatter && is_y && chunk > 0;
+          const bool accumulate = is_y && chunk > 0;
           LAP(0);
           mbar_wait(outfull_bar, (uint32_t)period & 1u);
           LAP(1);
@@ -790,16 +803,19 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
           // accumulated over chunks): full 128-byte lines instead of 32 scattered 16-byte stores per instruction, and
           // the rows past the end of the matrix are clipped by the tensor map.  One box = 32 rows x 128 bytes:
           // 32 fp32 columns, or 64 bf16 columns.
-          const int owner = scatter ? blk / p.own_blocks : 0;
-          const CUtensorMap* tm_o = scatter ? p.oy_maps + owner : is_y ? &tm_oy : &tm_ox;
+          const CUtensorMap* tm_o = is_y ? &tm_oy : &tm_ox;
           uint8_t* stg = drain_stage + quarter * 8192;
-          const int row0 = (blk - owner * p.own_blocks) * kBM + quarter * 32;  // row inside the owner's slot
+          const int row0 = blk * kBM + quarter * 32;
           const int cols_per_box = bf16 ? 64 : 32;
           // The stores of the previous period had a whole period to complete; waiting for them HERE (not at the end of
           // their own drain) keeps a drain as short as its shared-memory traffic even when the destination is a peer
           // GPU, and still orders a tile's plain store before the add-reduction a later chunk makes into it.
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            if (pending_seg >= 0) signal_progress(pending_seg);  // the previous period's tile is complete in memory
+          }
           __syncwarp();
+          pending_seg = (is_y && p.progress != nullptr && chunk == n_chunks - 1) ? (pass * p.C2 + hidx) / p.cp_per_seg : -1;
 #pragma unroll 1
           for (int bx = 0; bx < kNC / cols_per_box; ++bx) {
             uint32_t rr[32];
@@ -838,7 +854,10 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
           mbar_arrive_cluster(outfree_bar, 0);  // tell the leader: this CTA's accumulator may be overwritten
           LAP(2);
         });
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the last period's stores are complete
+    if (lane == 0) {
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the last period's stores are complete
+      if (pending_seg >= 0) signal_progress(pending_seg);
+    }
     __syncwarp();
     if (threadIdx.x == 128) LAP_FLUSH(10, 3);
   }
@@ -969,28 +988,39 @@ int launch(const CUtensorMap& tm_x128, const CUtensorMap& tm_y128, const CUtenso
   return PGICA_OK;
 }
 
-struct ScatterSpec {
-  const void* const* peers_host = nullptr;  // base of every rank's fp32 [>= my][k] OutY buffer
-  int n_peers = 0;
-  int64_t rows_per_owner = 0;               // multiple of 128
-  void* tmaps_device = nullptr;             // >= 128 * n_peers bytes, 128-byte aligned
+struct ProgressSpec {
+  uint32_t* counters = nullptr;  // device, one uint32 per segment of OutY rows (system-scope visible)
+  int64_t rows_per_segment = 0;  // multiple of 256 (a column pair)
 };
 
 template <bool kRow, bool kCol>
 int plan_and_launch(const void* x, const void* y, int64_t mx, int64_t my, int64_t k, SggfParams p, void* workspace,
-                    size_t workspace_bytes, const ScatterSpec& sc, cudaStream_t st) {
+                    size_t workspace_bytes, const ProgressSpec& pg, cudaStream_t st) {
   int npairs = 0;
   int rc = resident_pairs<kRow, kCol>(&npairs);
   if (rc != PGICA_OK) return rc;
   const int S = p.S;
-  // a bf16 OutY cannot be accumulated over chunks: all of X must then fit one chunk of X-holders
-  Plan pl = choose_plan(p.RB2, p.J2, (int)k, npairs, p.outy_bf16 != 0 || sc.n_peers > 0);
+  // a bf16 OutY cannot be accumulated over chunks: all of X must then fit one chunk of X-holders.  One chunk is also
+  // preferred whenever it fits and the model puts it within 6 % of the best split: W is then streamed once and OutY
+  // written once (325 MB instead of 825 MB of DRAM traffic on cfg2), and with a progress counter the rows of OutY
+  // become final from the first pass on instead of only during the last chunk.
+  Plan pl = choose_plan(p.RB2, p.J2, (int)k, npairs, p.outy_bf16 != 0);
+  if (pl.R2 < p.RB2) {
+    const Plan one = choose_plan(p.RB2, p.J2, (int)k, npairs, true);
+    if (one.R2 >= p.RB2 && one.nP >= 1 && (one.cost <= 1.06 * pl.cost || pg.counters != nullptr)) pl = one;
+  }
   plan_override(&pl, npairs, S);
   PGICA_REQUIRE(pl.R2 >= 1 && pl.nP >= 1, "softmax_grad_gemm_dual: no role split of %d CTA pairs fits %d row blocks%s",
                 npairs, 2 * p.RB2, p.outy_bf16 ? " in one chunk (bf16 OutY)" : "");
-  PGICA_REQUIRE(!((p.outy_bf16 || sc.n_peers > 0) && p.RB2 > pl.R2),
-                "softmax_grad_gemm_dual: a bf16 or scattered OutY cannot be accumulated over chunks (x has %d row blocks)",
-                2 * p.RB2);
+  PGICA_REQUIRE(!(p.outy_bf16 && p.RB2 > pl.R2),
+                "softmax_grad_gemm_dual: a bf16 OutY cannot be accumulated over chunks (x has %d row blocks)", 2 * p.RB2);
+  if (pg.counters != nullptr) {
+    PGICA_REQUIRE(pg.rows_per_segment > 0 && pg.rows_per_segment % (2 * kBT) == 0,
+                  "softmax_grad_gemm_dual: rows_per_segment must be a positive multiple of 256 (got %lld)",
+                  (long long)pg.rows_per_segment);
+    p.progress = pg.counters;
+    p.cp_per_seg = (int)(pg.rows_per_segment / (2 * kBT));
+  }
   p.R2 = pl.R2;
   p.C2 = pl.C2;
   p.nH = pl.nH;
@@ -1029,24 +1059,8 @@ int plan_and_launch(const void* x, const void* y, int64_t mx, int64_t my, int64_
   CUtensorMap tm_ox, tm_oy;
   rc = p.outx_bf16 ? make_tmap_bf16(&tm_ox, p.out_x, mx, k, k, 32) : make_tmap_f32(&tm_ox, p.out_x, mx, k, k, 32);
   if (rc != PGICA_OK) return rc;
-  if (sc.n_peers > 0) {
-    // one tensor map per owner's buffer, copied to the device ahead of the launch (the copy stages its pageable
-    // source synchronously, so the host array may die when this function returns)
-    CUtensorMap maps[16];
-    for (int r = 0; r < sc.n_peers; ++r) {
-      int64_t rows_r = my - r * sc.rows_per_owner;  // valid rows of owner r (the map clips the rest)
-      rows_r = rows_r < 1 ? 1 : rows_r > sc.rows_per_owner ? sc.rows_per_owner : rows_r;
-      rc = make_tmap_f32(&maps[r], sc.peers_host[r], rows_r, k, k, 32);
-      if (rc != PGICA_OK) return rc;
-    }
-    PGICA_CUDA_OK(cudaMemcpyAsync(sc.tmaps_device, maps, sizeof(CUtensorMap) * sc.n_peers, cudaMemcpyHostToDevice, st));
-    p.oy_maps = static_cast<const CUtensorMap*>(sc.tmaps_device);
-    p.own_blocks = (int)(sc.rows_per_owner / kBM);
-    tm_oy = maps[0];
-  } else {
-    rc = p.outy_bf16 ? make_tmap_bf16(&tm_oy, p.out_y, my, k, k, 32) : make_tmap_f32(&tm_oy, p.out_y, my, k, k, 32);
-    if (rc != PGICA_OK) return rc;
-  }
+  rc = p.outy_bf16 ? make_tmap_bf16(&tm_oy, p.out_y, my, k, k, 32) : make_tmap_f32(&tm_oy, p.out_y, my, k, k, 32);
+  if (rc != PGICA_OK) return rc;
   return launch<kRow, kCol>(tm_x128, tm_y128, tm_x64, tm_y64, tm_s, tm_ox, tm_oy, p, st);
 }
 
@@ -1127,23 +1141,13 @@ size_t sggf_workspace_bytes() {
 int sggf_dispatch(const void* x, const void* y, int64_t mx, int64_t my, int64_t k, float scale, const float* r_lse,
                   const float* r_coef, const int32_t* r_tgt, const float* c_lse, const float* c_coef,
                   const int32_t* c_tgt, void* out_x, int out_x_is_bf16, void* out_y, int out_y_is_bf16,
-                  void* workspace, size_t workspace_bytes, cudaStream_t st, const void* const* peers_host = nullptr,
-                  int n_peers = 0, int64_t rows_per_owner = 0, void* tmaps_device = nullptr) {
+                  void* workspace, size_t workspace_bytes, cudaStream_t st, uint32_t* progress = nullptr,
+                  int64_t rows_per_segment = 0) {
   PGICA_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0,
                 "softmax_grad_gemm_dual: workspace missing or not 256-byte aligned");
-  ScatterSpec sc;
-  if (n_peers > 0) {
-    PGICA_REQUIRE(peers_host && n_peers <= 16 && tmaps_device && (reinterpret_cast<uintptr_t>(tmaps_device) & 127u) == 0,
-                  "softmax_grad_gemm_dual_scatter: bad peer list / tensor-map scratch");
-    PGICA_REQUIRE(rows_per_owner > 0 && rows_per_owner % kBM == 0 && rows_per_owner * n_peers >= my,
-                  "softmax_grad_gemm_dual_scatter: rows_per_owner %lld x %d ranks must be a multiple of 128 covering %lld rows",
-                  (long long)rows_per_owner, n_peers, (long long)my);
-    PGICA_REQUIRE(!out_y_is_bf16, "softmax_grad_gemm_dual_scatter: the scattered OutY is fp32");
-    sc.peers_host = peers_host;
-    sc.n_peers = n_peers;
-    sc.rows_per_owner = rows_per_owner;
-    sc.tmaps_device = tmaps_device;
-  }
+  ProgressSpec sc;
+  sc.counters = progress;
+  sc.rows_per_segment = rows_per_segment;
   const int RB = (int)ceil_div(mx, kBM), J = (int)ceil_div(my, kBT);
   PGICA_REQUIRE((int64_t)RB * J < (1ll << 30), "softmax_grad_gemm_dual: problem too large");
   SggfParams p{};
@@ -1233,24 +1237,25 @@ extern "C" int pgica_softmax_grad_gemm_dual(const void* x, const void* y, int64_
                        out_y_is_bf16, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int pgica_softmax_grad_gemm_dual_scatter(const void* x, const void* y, int64_t mx, int64_t my, int64_t k,
-                                                    float scale, const float* r_lse, const float* r_coef,
-                                                    const int32_t* r_tgt, const float* c_lse, const float* c_coef,
-                                                    const int32_t* c_tgt, void* out_x, int out_x_is_bf16,
-                                                    const void* const* out_y_peers_host, int n_peers,
-                                                    int64_t rows_per_owner, void* tmaps_device, void* workspace,
-                                                    size_t workspace_bytes, void* stream) {
+extern "C" int pgica_softmax_grad_gemm_dual_progress(const void* x, const void* y, int64_t mx, int64_t my, int64_t k,
+                                                     float scale, const float* r_lse, const float* r_coef,
+                                                     const int32_t* r_tgt, const float* c_lse, const float* c_coef,
+                                                     const int32_t* c_tgt, void* out_x, int out_x_is_bf16, void* out_y,
+                                                     int out_y_is_bf16, uint32_t* progress, int64_t rows_per_segment,
+                                                     int32_t* increments_per_256_rows_host, void* workspace,
+                                                     size_t workspace_bytes, void* stream) {
   using namespace pgica;
   int rc = pgica_device_check();
   if (rc != PGICA_OK) return rc;
-  PGICA_REQUIRE(x && y && out_x && out_y_peers_host && n_peers >= 1, "softmax_grad_gemm_dual_scatter: null operand");
+  PGICA_REQUIRE(x && y && out_x && out_y && progress, "softmax_grad_gemm_dual_progress: null operand");
   PGICA_REQUIRE(mx > 0 && my > 0 && k > 0 && k % kNC == 0 && k / kNC <= 4,
-                "softmax_grad_gemm_dual_scatter: bad shape (mx %lld my %lld k %lld)", (long long)mx, (long long)my,
+                "softmax_grad_gemm_dual_progress: bad shape (mx %lld my %lld k %lld)", (long long)mx, (long long)my,
                 (long long)k);
   const bool row = r_lse != nullptr, col = c_lse != nullptr;
-  PGICA_REQUIRE(row || col, "softmax_grad_gemm_dual_scatter: need row statistics, column statistics or both");
-  PGICA_REQUIRE((!row || r_coef) && (!col || c_coef) && scale > 0.f, "softmax_grad_gemm_dual_scatter: bad statistics");
-  return sggf_dispatch(x, y, mx, my, k, scale, r_lse, r_coef, r_tgt, c_lse, c_coef, c_tgt, out_x, out_x_is_bf16,
-                       const_cast<void*>(out_y_peers_host[0]), 0, workspace, workspace_bytes,
-                       static_cast<cudaStream_t>(stream), out_y_peers_host, n_peers, rows_per_owner, tmaps_device);
+  PGICA_REQUIRE(row || col, "softmax_grad_gemm_dual_progress: need row statistics, column statistics or both");
+  PGICA_REQUIRE((!row || r_coef) && (!col || c_coef) && scale > 0.f, "softmax_grad_gemm_dual_progress: bad statistics");
+  if (increments_per_256_rows_host) *increments_per_256_rows_host = 8 * (int32_t)(k / kNC);  // 2 CTAs x S splits x 4 drain warps
+  return sggf_dispatch(x, y, mx, my, k, scale, r_lse, r_coef, r_tgt, c_lse, c_coef, c_tgt, out_x, out_x_is_bf16, out_y,
+                       out_y_is_bf16, workspace, workspace_bytes, static_cast<cudaStream_t>(stream), progress,
+                       rows_per_segment);
 }

@@ -141,152 +141,91 @@ def allreduce_dweight(dweight: torch.Tensor, group=None, async_op: bool = False)
     return dist.all_reduce(dweight, group=group, async_op=async_op)
 
 
-class PeerAllReduce:
-    """Sum-all-reduce of ONE fixed fp32 buffer across the GPUs of an NVLink node, moved by the COPY ENGINES.
+class OverlappedDWAllReduce:
+    """Data-parallel sum of the LM-head weight gradient that runs WHILE the backward kernel is still producing it.
 
-    Why not NCCL here: the gradient kernels of the Stage-2 head are persistent 4-CTA-cluster kernels that keep 128-132
-    of the 148 SMs resident; every SM an NCCL kernel takes displaces a whole cluster, so an "overlapped" NCCL
-    all-reduce of the 206 MB LM-head weight gradient made the dH kernel wait for it (measured at N=2: 1.27 ms
-    overlapped vs 0.82 + 0.34 ms back to back).  Peer copies through symmetric memory use no SM at all:
+    The dual backward kernel (csrc/sgg_f.cu) finalises dW in vocabulary order and bumps a per-segment progress counter
+    (system-scope release) whenever the stores of a finished tile have completed.  Next to it, on a second stream, runs
+    `pgica_peer_allreduce_progress` (csrc/peer_ar.cu): one small CTA per SM that fits beside the persistent kernel.  Per
+    segment it waits for the local counter, meets the other ranks at a flag barrier in peer memory, and every rank sums
+    its 1/W slice of the segment straight out of all W symmetric buffers over NVLink and stores the result into all of
+    them (reduce-scatter + all-gather of a two-shot all-reduce, one pass, deterministic).  Only the last segment's
+    share of the transfer is exposed after the backward kernel ends; the NCCL all-reduce it replaces cost 0.61 ms of a
+    2.2 ms step on 8 GPUs (profiles/r1_scaling_notes.md).
 
-        barrier -> pull my 1/W chunk of every peer's buffer (W-1 peer copies into scratch)
-                -> pgica_sum_into_f32 (a few CTAs: fits beside the resident clusters)
-                -> push the reduced chunk into every peer's buffer -> barrier
+        red = OverlappedDWAllReduce(vocab, d, device)
+        dh, dw, done = red.backward(hidden, weight, row_label, row_weight, lse, grad_seq)   # per step
+        torch.cuda.current_stream().wait_event(done)      # dw = the summed (V, d) gradient, identical on every rank
 
-    Traffic per GPU and direction: 2 (W-1)/W of the buffer, the same as a ring all-reduce; measured peer-copy rate on
-    this pool ~700 GB/s.  The buffer lives in symmetric memory (torch.distributed._symmetric_memory); the kernels
-    write the gradient straight into it (`functional.lmhead_logprob_bwd(..., dweight_out=reducer.view)`)."""
+    dW lives in torch symmetric memory; the buffer must not be rewritten (next backward) before `done` has fired on
+    every rank — `backward` itself orders that."""
 
-    def __init__(self, shape, device, group=None, sum_ctas: int = 32):
-        import torch.distributed._symmetric_memory as symm
-        self.group = group if group is not None else dist.group.WORLD
-        self.world, self.rank = _world(group)
-        self.shape = tuple(shape)
-        numel = 1
-        for s in self.shape:
-            numel *= int(s)
-        unit = 4 * self.world  # chunks are float4-aligned
-        self.numel = numel
-        self.padded = (numel + unit - 1) // unit * unit
-        self.chunk = self.padded // self.world
-        self.buf = symm.empty(self.padded, dtype=torch.float32, device=device)
-        self.hdl = symm.rendezvous(self.buf, self.group)
-        self.peers = [self.hdl.get_buffer(p, (self.padded,), torch.float32) for p in range(self.world)]
-        self.scratch = torch.empty((max(self.world - 1, 1), self.chunk), dtype=torch.float32, device=device)
-        self.stream = torch.cuda.Stream(device=device)
-        self.sum_ctas = sum_ctas
-        self.trace = False       # set True to keep timing events of the last all_reduce in .last_trace
-        self.last_trace = None
-        self.buf.zero_()
-
-    @property
-    def view(self):
-        """The local buffer with the caller's shape (what the gradient kernel writes into)."""
-        return self.buf[: self.numel].view(self.shape)
-
-    def all_reduce(self, after: Optional[torch.cuda.Event] = None) -> torch.cuda.Event:
-        """Enqueue the all-reduce on the reducer's own stream, ordered after `after` (default: everything enqueued
-        on the current stream so far).  Returns the event that marks the reduced buffer complete on this rank; the
-        buffer must not be rewritten before every rank's event has fired (wait on it before the next producer)."""
-        if after is None:
-            after = torch.cuda.Event()
-            after.record()
-        s = self.stream
-        s.wait_event(after)
-        lo, hi = self.rank * self.chunk, (self.rank + 1) * self.chunk
-        others = [p for p in range(self.world) if p != self.rank]
-        trace = [] if self.trace else None
-
-        def mark(name):
-            if trace is not None:
-                e = torch.cuda.Event(enable_timing=True)
-                e.record()
-                trace.append((name, e))
-
-        with torch.cuda.stream(s):
-            mark("start")
-            self.hdl.barrier(channel=0)  # every rank's buffer is complete
-            mark("barrier0")
-            for i, p in enumerate(others):
-                self.scratch[i].copy_(self.peers[p][lo:hi])
-            mark("pull")
-            if others:
-                F.sum_into(self.buf[lo:hi], [self.scratch[i] for i in range(len(others))], self.sum_ctas)
-            mark("sum")
-            for p in others:
-                self.peers[p][lo:hi].copy_(self.buf[lo:hi])
-            mark("push")
-            self.hdl.barrier(channel=1)  # every rank's pushes have landed
-            mark("barrier1")
-            done = torch.cuda.Event()
-            done.record()
-        if trace is not None:
-            self.last_trace = trace
-        return done
-
-
-class FusedDWReduce:
-    """Data-parallel sum of the LM-head weight gradient with the SCATTER done by the backward kernel itself.
-
-    The dual backward kernel (csrc/sgg_f.cu) keeps 128-row tiles of dW resident in TMEM; in scatter mode it drains
-    every finished tile with a TMA store straight into this rank's slot in the memory of the rank that OWNS those rows
-    — peer memory over NVLink / NVSwitch, mapped through torch symmetric memory — while the tensor cores are already
-    on the next tiles.  When the kernels of all ranks have ended, rank r holds W partial copies of its rows
-    [r * own, (r+1) * own), sums them (pgica_sum_into_f32, HBM-bound, 1/W of dW), and the all-gather that completes
-    the all-reduce is W-1 peer copies of 1/W of the buffer on the copy engines:
-
-        barrier -> backward kernel (dH local, dW tiles -> owners' slots) -> barrier -> sum my slots
-                -> push my rows to every peer -> barrier
-
-    Per GPU the kernel sends (W-1)/W of dW spread over its whole run time (~0.2 TB/s at W=8, a fraction of NVLink)
-    and only the sum and the all-gather are exposed.  (Remote TMA add-reductions instead of per-source slots were
-    measured an order of magnitude slower: 2.5 ms instead of 1.0 ms for the kernel at W=8.)  Needs a problem whose
-    rows fit one chunk of the kernel (<= 32 row blocks at d = 1024); larger ones accumulate dW locally and all-reduce.
-
-    `backward(...)` returns (dhidden, dweight_view); dweight_view is this rank's copy of the reduced (V, d) fp32
-    gradient inside the symmetric buffer, valid on the current stream when the call returns."""
-
-    def __init__(self, vocab: int, d: int, device, group=None):
+    def __init__(self, vocab: int, d: int, device, group=None, segments: int = 8, max_ctas: int = 0):
         import torch.distributed._symmetric_memory as symm
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = _world(group)
         self.vocab, self.d = int(vocab), int(d)
-        blocks = (self.vocab + 127) // 128
-        self.own_rows = 128 * ((blocks + self.world - 1) // self.world)
-        self.rows = self.own_rows * self.world
-        n_own = self.own_rows * self.d
-        # one symmetric allocation: [reduced gradient: rows x d][slots: world x own_rows x d]
-        self.buf = symm.empty(self.rows * self.d + self.world * n_own, dtype=torch.float32, device=device)
+        pairs = (self.vocab + 255) // 256                       # 256-row column pairs of the kernel
+        self.rows = pairs * 256
+        segments = max(1, min(int(segments), pairs, 32))
+        self.pairs_per_seg = (pairs + segments - 1) // segments
+        self.nseg = (pairs + self.pairs_per_seg - 1) // self.pairs_per_seg
+        self.rows_per_seg = self.pairs_per_seg * 256
+        n = self.rows * self.d
+        nflag = (self.nseg + 1) * self.world
+        # one symmetric allocation: [dW: rows x d fp32][flags: (nseg + 1) x world uint32, padded]
+        self.flag_off = n
+        self.buf = symm.empty(n + ((nflag + 63) // 64) * 64, dtype=torch.float32, device=device)
+        self.buf.zero_()
         self.hdl = symm.rendezvous(self.buf, self.group)
         total = self.buf.numel()
         flat = [self.hdl.get_buffer(p, (total,), torch.float32) for p in range(self.world)]
-        self.out_peers = [f[: self.rows * self.d].view(self.rows, self.d) for f in flat]
-        self.local = self.out_peers[self.rank]
-        self.slots = flat[self.rank][self.rows * self.d:].view(self.world, self.own_rows, self.d)
-        # where rank p keeps the slot for MY tiles
-        base = self.rows * self.d + self.rank * n_own
-        self.peer_ptrs = [f[base: base + n_own].data_ptr() for f in flat]
-        raw = torch.empty(128 * self.world + 128, dtype=torch.uint8, device=device)
-        off = (-raw.data_ptr()) % 128
-        self.tmaps = raw[off: off + 128 * self.world]
-        self.buf.zero_()
+        self.buf_ptrs = [f.data_ptr() for f in flat]
+        self.flag_ptrs = [f.data_ptr() + 4 * self.flag_off for f in flat]
+        self._flat = flat
+        self.local = flat[self.rank][:n].view(self.rows, self.d)
+        self.progress = torch.zeros(self.nseg, dtype=torch.int32, device=device)
+        self.local_sync = torch.zeros(2, dtype=torch.int32, device=device)
+        unit = 4 * self.world
+        assert (self.rows_per_seg * self.d) % unit == 0
+        self.seg_begin = [min(s * self.rows_per_seg, self.rows) * self.d for s in range(self.nseg + 1)]
+        self.seg_pairs = [(min((s + 1) * self.rows_per_seg, self.rows) - s * self.rows_per_seg) // 256
+                          for s in range(self.nseg)]
+        self.stream = torch.cuda.Stream(device=device)
+        self.max_ctas = int(max_ctas)
+        self.epoch = 0
+        self.done = torch.cuda.Event()
+        self.done.record()
+        torch.cuda.synchronize(device)
+        self.hdl.barrier(channel=0)  # every rank's flags are zero before anybody's first epoch
 
     @property
     def view(self):
+        """The reduced gradient, (V, d) fp32 (rows past the vocabulary belong to the padding of the last tile pair)."""
         return self.local[: self.vocab]
 
     def backward(self, hidden, weight, row_label, row_weight, lse, grad_seq, length_normalize=False,
-                 dhidden_dtype=torch.bfloat16):
-        lo, hi = self.rank * self.own_rows, (self.rank + 1) * self.own_rows
-        self.hdl.barrier(channel=0)  # every owner has summed last step's slots: they may be overwritten
-        dh = F.lmhead_logprob_bwd_scatter(hidden, weight, row_label, row_weight, lse, grad_seq, self.peer_ptrs,
-                                          self.own_rows, self.tmaps, length_normalize, dhidden_dtype)
-        self.hdl.barrier(channel=1)  # every rank's tiles have landed in my slots
-        mine = self.local[lo:hi]
-        mine.zero_()
-        F.sum_into(mine, [self.slots[s] for s in range(self.world)])
-        for p in range(self.world):
-            if p != self.rank:
-                self.out_peers[p][lo:hi].copy_(mine)
-        self.hdl.barrier(channel=2)  # everybody's rows have arrived here
-        return dh, self.view
+                 dhidden_dtype=torch.bfloat16, scalars: Optional[torch.Tensor] = None):
+        """-> (dhidden, dweight view, event[, summed scalars]): dweight is complete on the event (recorded on the
+        reducer's stream).  `scalars` (a few fp32 values: the local loss / metric sums) ride along in the padding rows
+        of the last tile pair — rows past the vocabulary that the kernel never writes — and come back summed over the
+        ranks, so the step needs no second collective."""
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self.done)  # the previous all-reduce has left the buffer (on every rank: its final barrier)
+        self.epoch += 1
+        pad = None
+        if scalars is not None:
+            if self.rows == self.vocab or scalars.numel() > self.d:
+                raise ValueError("no padding row to carry the scalars (vocabulary is a multiple of 256)")
+            pad = self.local[self.rows - 1, : scalars.numel()]
+            pad.copy_(scalars.detach().float().reshape(-1))
+        dh, inc = F.lmhead_logprob_bwd_progress(hidden, weight, row_label, row_weight, lse, grad_seq, self.view,
+                                                self.progress, self.rows_per_seg, length_normalize, dhidden_dtype)
+        targets = [self.epoch * inc * np_ for np_ in self.seg_pairs]
+        F.peer_allreduce_progress(self.buf_ptrs, self.flag_ptrs, self.rank, self.progress, targets, self.seg_begin,
+                                  self.epoch, self.local_sync, self.max_ctas, stream=self.stream)
+        self.done = torch.cuda.Event()
+        self.done.record(self.stream)
+        if scalars is not None:
+            return dh, self.view, self.done, pad
+        return dh, self.view, self.done

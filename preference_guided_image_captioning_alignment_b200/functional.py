@@ -309,27 +309,44 @@ def rownorm_bwd(x, inv_norm, g, second=-1):
 
 
 # ----------------------------------------------------------------------------------------- logits path
-def lmhead_logprob_bwd_scatter(hidden, weight, row_label, row_weight, lse, grad_seq, peer_ptrs, rows_per_owner,
-                               tmaps, length_normalize=False, dhidden_dtype=torch.bfloat16):
-    """Backward of the LM head with the weight gradient reduce-scattered inside the kernel: dhidden is returned,
-    dweight tiles are added into the fp32 buffers at `peer_ptrs` (one device pointer per rank, rank r owning rows
-    [r * rows_per_owner, ...)).  `tmaps`: uint8 device scratch of >= 128 * len(peer_ptrs) bytes."""
-    _need_cuda(hidden, weight, grad_seq, tmaps)
+def lmhead_logprob_bwd_progress(hidden, weight, row_label, row_weight, lse, grad_seq, dweight_out, progress,
+                                rows_per_segment, length_normalize=False, dhidden_dtype=torch.bfloat16):
+    """Backward of the LM head that publishes its progress on dweight (pgica_lmhead_logprob_bwd_progress): dweight_out is
+    a caller-owned fp32 (V, d) tensor (inside a symmetric buffer), `progress` a uint32/int32 device tensor with one
+    counter per `rows_per_segment` rows.  -> (dhidden, increments one 256-row pair of dweight contributes)"""
+    _need_cuda(hidden, weight, grad_seq, dweight_out, progress)
     lib = _lib.load()
     nseq, T, d = hidden.shape
     V = weight.shape[0]
     dev = hidden.device
+    if tuple(dweight_out.shape) != (V, d) or dweight_out.dtype != torch.float32 or not dweight_out.is_contiguous():
+        raise ValueError("dweight_out must be a contiguous fp32 (V, d) tensor")
     need = ctypes.c_size_t(0)
     _lib.check(lib.pgica_lmhead_logprob_workspace_bytes(nseq, T, d, V, ctypes.byref(need)))
     ws = _ws(need.value, dev)
     dh = torch.empty(nseq, T, d, dtype=dhidden_dtype, device=dev)
-    arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(q) for q in peer_ptrs])
-    _lib.check(lib.pgica_lmhead_logprob_bwd_scatter(_p(hidden), _p(weight), _p(row_label), _p(row_weight), _p(lse),
-                                                    _p(grad_seq.float().contiguous()), nseq, T, d, V,
-                                                    1 if length_normalize else 0, _p(dh),
-                                                    1 if dhidden_dtype == torch.bfloat16 else 0, arr, len(peer_ptrs),
-                                                    int(rows_per_owner), _p(tmaps), _p(ws), ws.numel(), _stream()))
-    return dh
+    inc = ctypes.c_int32(0)
+    _lib.check(lib.pgica_lmhead_logprob_bwd_progress(_p(hidden), _p(weight), _p(row_label), _p(row_weight), _p(lse),
+                                                     _p(grad_seq.float().contiguous()), nseq, T, d, V,
+                                                     1 if length_normalize else 0, _p(dh),
+                                                     1 if dhidden_dtype == torch.bfloat16 else 0, _p(dweight_out),
+                                                     _p(progress), int(rows_per_segment), ctypes.byref(inc), _p(ws),
+                                                     ws.numel(), _stream()))
+    return dh, inc.value
+
+
+def peer_allreduce_progress(buf_ptrs, flag_ptrs, rank, progress, targets, seg_begin, epoch, local_sync, max_ctas=0,
+                            stream=None):
+    """Launch the progress-gated peer all-reduce (pgica_peer_allreduce_progress) on `stream` (default: current)."""
+    lib = _lib.load()
+    world, nseg = len(buf_ptrs), len(seg_begin) - 1
+    bufs = (ctypes.c_void_p * world)(*[int(q) for q in buf_ptrs])
+    flags = (ctypes.c_void_p * world)(*[int(q) for q in flag_ptrs])
+    tg = (ctypes.c_uint32 * nseg)(*[int(t) & 0xFFFFFFFF for t in targets]) if progress is not None else None
+    sb = (ctypes.c_int64 * (nseg + 1))(*[int(v) for v in seg_begin])
+    st = ctypes.c_void_p(stream.cuda_stream) if stream is not None else _stream()
+    _lib.check(lib.pgica_peer_allreduce_progress(bufs, flags, world, int(rank), _p(progress), tg, sb, nseg,
+                                                 int(epoch) & 0xFFFFFFFF, _p(local_sync), int(max_ctas), st))
 
 
 def prep_rows(labels, mask, vocab):

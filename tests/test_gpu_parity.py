@@ -1044,3 +1044,43 @@ def test_options_api_selects_kernels(pg, cuda_device):
         assert rel(outs[k][0], outs[1][0]) < 1e-3 and rel(outs[k][1], outs[1][1]) < 1e-3
     with pytest.raises(_lib.PgicaError):
         _lib.set_option("no_such_option", 1)
+
+
+# ================================================================================================ progress / peer all-reduce
+def test_dual_backward_progress_and_peer_allreduce_single_rank(pg, cuda_device):
+    """The pieces of the overlapped dW all-reduce on ONE GPU: the dual kernel with progress counters gives the same
+    gradients as the plain launch and every segment counter ends exactly at its target; the peer all-reduce kernel,
+    running beside it on a second stream (world = 1: it sums one buffer, but waits on the counters and walks every
+    segment / flag barrier), leaves dW intact and terminates; three epochs on the same counters and flags."""
+    from preference_guided_image_captioning_alignment_b200 import functional as F
+    g = torch.Generator().manual_seed(12)
+    for (B, T, d, V, rows_per_seg) in ((4, 64, 1024, 5003, 1024), (16, 128, 1024, 50257, 6400), (3, 50, 512, 1000, 256)):
+        h = torch.randn(B, T, d, generator=g).bfloat16().to(cuda_device)
+        W = (torch.randn(V, d, generator=g) * 0.03).bfloat16().to(cuda_device)
+        y = torch.randint(0, V, (B, T), generator=g).to(cuda_device)
+        _, lse, _, rl, rw, _ = F.lmhead_logprob_fwd(h, W, y, None, False)
+        gs = torch.randn(B, generator=g).to(cuda_device)
+        dh_ref, dw_ref = F.lmhead_logprob_bwd(h, W, rl, rw, lse, gs, False)
+        pairs = (V + 255) // 256
+        rows = pairs * 256
+        nseg = (rows + rows_per_seg - 1) // rows_per_seg
+        buf = torch.zeros(rows * d + 64 * (nseg + 1), dtype=torch.float32, device=cuda_device)
+        dw = buf[: V * d].view(V, d)
+        progress = torch.zeros(nseg, dtype=torch.int32, device=cuda_device)
+        local_sync = torch.zeros(2, dtype=torch.int32, device=cuda_device)
+        seg_begin = [min(s * rows_per_seg, rows) * d for s in range(nseg + 1)]
+        seg_pairs = [(min((s + 1) * rows_per_seg, rows) - s * rows_per_seg) // 256 for s in range(nseg)]
+        side = torch.cuda.Stream(device=cuda_device)
+        for epoch in (1, 2, 3):
+            dw.zero_()
+            torch.cuda.synchronize()
+            dh, inc = F.lmhead_logprob_bwd_progress(h, W, rl, rw, lse, gs, dw, progress, rows_per_seg, False)
+            assert inc == 8 * (d // 512)
+            targets = [epoch * inc * n for n in seg_pairs]
+            F.peer_allreduce_progress([buf.data_ptr()], [buf.data_ptr() + 4 * rows * d], 0, progress, targets, seg_begin,
+                                      epoch, local_sync, 0, stream=side)
+            side.synchronize()
+            torch.cuda.synchronize()
+            assert progress.tolist() == targets, (progress.tolist(), targets)
+            assert rel(dw, dw_ref) < 1e-3 and rel(dh.float(), dh_ref.float()) < 1e-3
+            assert local_sync[0].item() == epoch * nseg

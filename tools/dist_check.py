@@ -96,25 +96,10 @@ def main():
     ok &= res["ok"]
     if rank == 0:
         print(json.dumps(res), flush=True)
-    # ---------------------------------------------------------------- copy-engine all-reduce == NCCL all-reduce
+    # ---------------------------------------------------------------- overlapped peer all-reduce of dW == NCCL all-reduce
     from preference_guided_image_captioning_alignment_b200 import distributed as D2
-    red = D2.PeerAllReduce((1003, 257), dev)
-    g = torch.Generator(device="cpu").manual_seed(100 + rank)
-    local = torch.randn(1003, 257, generator=g).to(dev)
-    for trial in range(3):
-        red.view.copy_(local * (trial + 1))
-        want = (local * (trial + 1)).clone()
-        dist.all_reduce(want)
-        ev = red.all_reduce()
-        torch.cuda.current_stream().wait_event(ev)
-        err = (red.view - want).abs().max().item()
-        res = {"check": "peer_allreduce", "world": world, "trial": trial, "maxabs": err, "ok": bool(err < 1e-5)}
-        ok &= res["ok"]
-        if rank == 0:
-            print(json.dumps(res), flush=True)
-    # ---------------------------------------------------------------- in-kernel reduce-scatter of dW == NCCL all-reduce
     from preference_guided_image_captioning_alignment_b200 import functional as Fn
-    for (B2, T2, d2, V2) in ((4, 48, 512, 3001), (6, 64, 1024, 5003)):
+    for (B2, T2, d2, V2, nseg) in ((4, 48, 512, 3001, 3), (6, 64, 1024, 5003, 8), (16, 128, 1024, 50257, 8)):
         gen2 = torch.Generator().manual_seed(200 + rank)
         gw = torch.Generator().manual_seed(7)
         W2 = (torch.randn(V2, d2, generator=gw) * 0.05).to(torch.bfloat16).to(dev)
@@ -126,17 +111,28 @@ def main():
         dh_ref, dw_ref = Fn.lmhead_logprob_bwd(H2, W2, rl2, rw2, lse2, gs, False)
         dw_ref = dw_ref.clone()
         dist.all_reduce(dw_ref)
-        fr = D2.FusedDWReduce(V2, d2, dev)
-        for trial in range(2):
-            dh2, dw2 = fr.backward(H2, W2, rl2, rw2, lse2, gs, False)
+        red = D2.OverlappedDWAllReduce(V2, d2, dev, segments=nseg)
+        for trial in range(3):
+            scal = torch.arange(6, device=dev, dtype=torch.float32) + rank + trial
+            dh2, dw2, done, scal_sum = red.backward(H2, W2, rl2, rw2, lse2, gs, False, scalars=scal)
+            torch.cuda.current_stream().wait_event(done)
             torch.cuda.synchronize()
             e_w = rel(dw2.cpu().numpy(), dw_ref.cpu().numpy())
             e_h = rel(dh2.float().cpu().numpy(), dh_ref.float().cpu().numpy())
-            res = {"check": "fused_dw_reduce", "world": world, "shape": [B2, T2, d2, V2], "trial": trial, "dw_rel": e_w,
-                   "dh_rel": e_h, "ok": bool(e_w < 1e-5 and e_h < 1e-5)}
+            want_scal = sum(torch.arange(6, dtype=torch.float32) + q + trial for q in range(world))
+            e_s = float((scal_sum.cpu() - want_scal).abs().max())
+            # every rank must hold bit-identical sums (fixed rank order inside the kernel)
+            chk = dw2.double().sum().reshape(1)
+            allchk = [torch.empty_like(chk) for _ in range(world)]
+            dist.all_gather(allchk, chk)
+            same = all(bool(c.item() == allchk[0].item()) for c in allchk)
+            res = {"check": "overlapped_dw_allreduce", "world": world, "shape": [B2, T2, d2, V2], "segments": red.nseg,
+                   "trial": trial, "dw_rel": e_w, "dh_rel": e_h, "scalars_maxabs": e_s, "identical_on_all_ranks": same,
+                   "ok": bool(e_w < 1e-5 and e_h < 1e-5 and e_s < 1e-4 and same)}
             ok &= res["ok"]
             if rank == 0:
                 print(json.dumps(res), flush=True)
+        del red
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
