@@ -53,7 +53,8 @@ int64_t pgica_kernel_launches(void);
  * environment variables PGICA_<NAME>; the call path never reads the environment.  Names: "sgg_fused" (1: dual backward
  * kernel when both gradients are wanted; 0: one launch per product), "sggf_plan_r2" / "sggf_plan_c2" (pin the dual
  * kernel's role split; 0 = planner), "sggf_coop" (1: cooperative launch, a refused launch is an error; 0: plain
- * launch), "sggf_spread", "sggf_slots", "sggf_producers_only", "sggf_xprod" (tuning / diagnostics), "sgg_cluster"
+ * launch), "sggf_single_chunk" (1: keep all of x in one chunk whenever it fits — y streamed once, out_y written once),
+ * "sggf_spread", "sggf_slots", "sggf_producers_only" (tuning / diagnostics), "sgg_cluster"
  * (cluster size of the one-product kernel).  set: 0 or PGICA_ERR_INVALID_ARGUMENT; get: INT64_MIN for an unknown name. */
 int pgica_set_option(const char* name, int64_t value);
 int64_t pgica_get_option(const char* name);

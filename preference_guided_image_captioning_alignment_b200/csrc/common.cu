@@ -107,7 +107,7 @@ struct OptionTable {
     env_int("PGICA_SGGF_SLOTS", kOptSggfSlots, this);
     env_int("PGICA_SGGF_DEBUG_PRODUCERS_ONLY", kOptSggfProducersOnly, this);
     env_int("PGICA_SGG_CLUSTER", kOptSggCluster, this);
-    env_int("PGICA_SGGF_XPROD", kOptSggfXProd, this);
+    env_int("PGICA_SGGF_SINGLE_CHUNK", kOptSggfSingleChunk, this);
     if (const char* e = getenv("PGICA_SGGF_PLAN")) {
       int r2 = 0, c2 = 0;
       if (sscanf(e, "%d,%d", &r2, &c2) == 2 && r2 >= 1 && c2 >= 1) {
@@ -122,7 +122,7 @@ OptionTable& options() {
   return t;
 }
 const char* const kOptionNames[kOptCount] = {"sgg_fused",  "sggf_plan_r2", "sggf_plan_c2",        "sggf_coop", "sggf_spread",
-                                             "sggf_slots", "sggf_producers_only", "sgg_cluster", "sggf_xprod"};
+                                             "sggf_slots", "sggf_producers_only", "sgg_cluster", "sggf_single_chunk"};
 int option_index(const char* name) {
   if (!name) return -1;
   for (int i = 0; i < kOptCount; ++i)

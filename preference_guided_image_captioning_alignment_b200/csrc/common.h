@@ -57,7 +57,7 @@ enum Option {
   kOptSggfSlots,             // "sggf_slots": exchange double-slots per producer CTA (0 = default 4)
   kOptSggfProducersOnly,     // "sggf_producers_only": diagnostics, holders idle
   kOptSggCluster,            // "sgg_cluster": cluster size of the one-product kernel (4, 2 or 1; 0 = largest that tiles k)
-  kOptSggfXProd,             // "sggf_xprod": X-holders co-produce (0 = off)
+  kOptSggfSingleChunk,       // "sggf_single_chunk": 1 = keep all of X in one chunk whenever it fits (W streamed once)
   kOptCount
 };
 int64_t get_option(Option o);

@@ -1001,13 +1001,14 @@ int plan_and_launch(const void* x, const void* y, int64_t mx, int64_t my, int64_
   if (rc != PGICA_OK) return rc;
   const int S = p.S;
   // a bf16 OutY cannot be accumulated over chunks: all of X must then fit one chunk of X-holders.  One chunk is also
-  // preferred whenever it fits and the model puts it within 6 % of the best split: W is then streamed once and OutY
-  // written once (325 MB instead of 825 MB of DRAM traffic on cfg2), and with a progress counter the rows of OutY
-  // become final from the first pass on instead of only during the last chunk.
+  // taken, when it fits, with a progress counter (the rows of OutY then become final from the first pass on instead
+  // of only during the last chunk: the overlapped all-reduce gets the whole launch to hide in) and with option
+  // sggf_single_chunk = 1 (W streamed once, OutY written once: 325 MB instead of 825 MB of DRAM traffic on cfg2, for
+  // ~2 % more time — measured 1.071 vs 1.051 ms, profiles/r2_dual_ab1.log).
   Plan pl = choose_plan(p.RB2, p.J2, (int)k, npairs, p.outy_bf16 != 0);
-  if (pl.R2 < p.RB2) {
+  if (pl.R2 < p.RB2 && (pg.counters != nullptr || get_option(kOptSggfSingleChunk) != 0)) {
     const Plan one = choose_plan(p.RB2, p.J2, (int)k, npairs, true);
-    if (one.R2 >= p.RB2 && one.nP >= 1 && (one.cost <= 1.06 * pl.cost || pg.counters != nullptr)) pl = one;
+    if (one.R2 >= p.RB2 && one.nP >= 1) pl = one;
   }
   plan_override(&pl, npairs, S);
   PGICA_REQUIRE(pl.R2 >= 1 && pl.nP >= 1, "softmax_grad_gemm_dual: no role split of %d CTA pairs fits %d row blocks%s",

@@ -41,6 +41,26 @@ def loss_close(got, ref, logit_scale=1.0):
     return abs(got - ref) <= LOSS_RTOL * abs(ref) + 2e-6 * max(1.0, logit_scale)
 
 
+def set_plan(plan):
+    """"R2,C2" pins the dual kernel's role split through the option API; None hands it back to the planner."""
+    from preference_guided_image_captioning_alignment_b200 import _lib
+    r2, c2 = (int(v) for v in plan.split(",")) if plan else (0, 0)
+    _lib.set_option("sggf_plan_r2", r2)
+    _lib.set_option("sggf_plan_c2", c2)
+
+
+@pytest.fixture(autouse=True)
+def _reset_library_options():
+    yield
+    try:
+        from preference_guided_image_captioning_alignment_b200 import _lib
+        set_plan(None)
+        _lib.set_option("sgg_fused", 1)
+        _lib.set_option("sgg_cluster", 0)
+    except Exception:
+        pass
+
+
 @pytest.fixture(scope="module")
 def pg(cuda_device):
     import preference_guided_image_captioning_alignment_b200 as pkg
@@ -494,8 +514,10 @@ def test_softmax_grad_gemm_shapes(pg, cuda_device, mx, my, k, mode):
     assert rel(ob.float(), exact) < GRAD_RTOL
 
 
-def test_softmax_grad_gemm_dsmem_variant_matches(pg, cuda_device, monkeypatch):
-    """The DSMEM-exchange cluster kernel (PGICA_SGG_EXCHANGE=dsmem) and the default L2-exchange kernel agree."""
+def test_softmax_grad_gemm_single_cta_variant_matches(pg, cuda_device):
+    """The single-CTA kernel (option sgg_cluster = 1; also the path for k not a multiple of 512) and the default
+    cluster kernel with its L2 exchange ring agree."""
+    from preference_guided_image_captioning_alignment_b200 import _lib
     from preference_guided_image_captioning_alignment_b200 import functional as F
     dev = cuda_device
     torch.manual_seed(9)
@@ -504,9 +526,9 @@ def test_softmax_grad_gemm_dsmem_variant_matches(pg, cuda_device, monkeypatch):
     lse, _ = F.gemm_lse(x, y, 1.0)
     row = (lse, torch.randn(640, device=dev), torch.randint(0, 1500, (640,), device=dev, dtype=torch.int32))
     a = F.softmax_grad_gemm(x, y, 1.0, row=row)
-    monkeypatch.setenv("PGICA_SGG_EXCHANGE", "dsmem")
+    _lib.set_option("sgg_cluster", 1)
     b = F.softmax_grad_gemm(x, y, 1.0, row=row)
-    monkeypatch.delenv("PGICA_SGG_EXCHANGE")
+    _lib.set_option("sgg_cluster", 0)
     assert rel(a, b) < 1e-5
 
 
@@ -570,8 +592,7 @@ def test_softmax_grad_gemm_dual(pg, cuda_device, monkeypatch, mx, my, k, mode, p
     two single-product launches; deterministic."""
     from preference_guided_image_captioning_alignment_b200 import functional as F
     x, y, row, col = _dual_inputs(cuda_device, mx, my, k, mode)
-    if plan:
-        monkeypatch.setenv("PGICA_SGGF_PLAN", plan)
+    set_plan(plan)
     ox, oy = F.softmax_grad_gemm_dual(x, y, 1.0, row=row, col=col)
     ox2, oy2 = F.softmax_grad_gemm_dual(x, y, 1.0, row=row, col=col)
     assert torch.equal(ox, ox2) and torch.equal(oy, oy2)
@@ -605,10 +626,12 @@ def test_lmhead_backward_dual_matches_split(pg, cuda_device, monkeypatch):
     m[:, T - 9:] = 0
     seq, lse, _, rl, rw, _ = F.lmhead_logprob_fwd(H, W, y, m, False)
     gseq = torch.randn(B, device=dev)
-    monkeypatch.setenv("PGICA_SGG_FUSED", "1")
+    from preference_guided_image_captioning_alignment_b200 import _lib
+    _lib.set_option("sgg_fused", 1)
     dh1, dw1 = F.lmhead_logprob_bwd(H, W, rl, rw, lse, gseq, False)
-    monkeypatch.setenv("PGICA_SGG_FUSED", "0")
+    _lib.set_option("sgg_fused", 0)
     dh0, dw0 = F.lmhead_logprob_bwd(H, W, rl, rw, lse, gseq, False)
+    _lib.set_option("sgg_fused", 1)
     assert rel(dh1.float(), dh0.float()) < 2e-3 and rel(dw1, dw0) < 2e-3
     assert torch.count_nonzero(dh1[:, T - 10:]).item() == 0  # rows that score nothing get exactly zero
 
@@ -729,10 +752,7 @@ def test_softmax_grad_gemm_dual_random_shapes(pg, cuda_device, monkeypatch):
         mx = rng.choice([rng.randint(1, 300), rng.randint(300, 2000), 128 * rng.randint(1, 12) + 1])
         my = rng.choice([rng.randint(1, 300), rng.randint(300, 4000), 256 * rng.randint(1, 12) + 129])
         mode = rng.choice(["row", "col", "both"])
-        if rng.random() < 0.6:
-            monkeypatch.setenv("PGICA_SGGF_PLAN", f"{rng.randint(1, 10 // S + 2)},{rng.randint(1, 10 // S + 2)}")
-        else:
-            monkeypatch.delenv("PGICA_SGGF_PLAN", raising=False)
+        set_plan(f"{rng.randint(1, 10 // S + 2)},{rng.randint(1, 10 // S + 2)}" if rng.random() < 0.6 else None)
         torch.manual_seed(i)
         x = (torch.randn(mx, k, device=dev) * 0.3).to(torch.bfloat16)
         y = (torch.randn(my, k, device=dev) * 0.3).to(torch.bfloat16)
@@ -1084,3 +1104,96 @@ def test_dual_backward_progress_and_peer_allreduce_single_rank(pg, cuda_device):
             assert progress.tolist() == targets, (progress.tolist(), targets)
             assert rel(dw, dw_ref) < 1e-3 and rel(dh.float(), dh_ref.float()) < 1e-3
             assert local_sync[0].item() == epoch * nseg
+
+
+# ================================================================================================ full-size parity
+def _torch_lmhead_reference(h, W, y, m, gseq, chunk_rows=8192):
+    """fp32 torch (TF32 off) reference of the Stage-2 head at full size with the logits MATERIALISED row-chunk by
+    row-chunk on the GPU: seq_logp[b] = sum_t m[b,t+1] log softmax(W h[b,t])[y[b,t+1]], and the gradients of
+    sum_b gseq[b] seq_logp[b] w.r.t. h and W from the closed form dZ = coef (onehot - softmax)."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    nseq, T, d = h.shape
+    V = W.shape[0]
+    Wf = W.float()
+    hf = h.float().reshape(nseq * T, d)
+    tgt = torch.cat([y[:, 1:], torch.zeros(nseq, 1, dtype=y.dtype, device=y.device)], 1).reshape(-1)
+    wt = torch.cat([m[:, 1:].float(), torch.zeros(nseq, 1, device=h.device)], 1).reshape(-1)
+    coef = wt * gseq.float().repeat_interleave(T)
+    logp = torch.empty(nseq * T, device=h.device)
+    dh = torch.zeros(nseq * T, d, device=h.device)
+    dW = torch.zeros(V, d, device=h.device)
+    for r0 in range(0, nseq * T, chunk_rows):
+        sl = slice(r0, min(r0 + chunk_rows, nseq * T))
+        z = hf[sl] @ Wf.T
+        lp = torch.log_softmax(z, dim=-1)
+        logp[sl] = lp.gather(1, tgt[sl, None]).squeeze(1)
+        dz = -torch.exp(lp) * coef[sl, None]
+        dz.scatter_add_(1, tgt[sl, None], coef[sl, None])
+        dh[sl] = dz @ Wf
+        dW += dz.T @ hf[sl]
+    seq = (logp * wt).reshape(nseq, T).sum(1)
+    return seq, dh.reshape(nseq, T, d), dW
+
+
+@pytest.mark.parametrize("plan", [None, "8,11", "16,9"])
+def test_cfg2_full_size_gradients_vs_torch(pg, cuda_device, plan):
+    """The EXACT launch bench.py times (cfg2: 16 pairs, seq 128, d = 1024, V = 50257: 4096 x 50257 logits; planner's own
+    split, the two-chunk split of round 1 and a pinned one-chunk split) against fp32 torch with the logits
+    materialised: every sequence log-prob, all of dH and all of dW."""
+    from preference_guided_image_captioning_alignment_b200 import functional as F
+    dev = cuda_device
+    W, h, y, m = _cfg2_inputs(dev, 16)
+    gseq = torch.randn(32, generator=torch.Generator().manual_seed(3)).to(dev)
+    seq_ref, dh_ref, dW_ref = _torch_lmhead_reference(h, W, y, m, gseq)
+    set_plan(plan)
+    seq, lse, _, rl, rw, _ = F.lmhead_logprob_fwd(h, W, y, m, False)
+    dh, dw = F.lmhead_logprob_bwd(h, W, rl, rw, lse, gseq, False, dhidden_dtype=torch.float32)
+    set_plan(None)
+    assert rel(seq, seq_ref) < 1e-5
+    assert rel(dh, dh_ref) < GRAD_RTOL and rel(dw, dW_ref) < GRAD_RTOL
+    assert torch.count_nonzero(dh[:, -1]).item() == 0
+
+
+def test_cfg4_rank_slice_gradients_vs_torch(pg, cuda_device):
+    """One rank's share of BASELINE config 4 at FULL size (32 pairs, seq 512: 32768 rows x 50257 logits, 8 chunks of the
+    dual kernel with dW accumulated in place) against fp32 torch with materialised logits."""
+    from preference_guided_image_captioning_alignment_b200 import functional as F
+    dev = cuda_device
+    W, h, y, m = _cfg2_inputs(dev, 32, T=512, seed=4321)
+    gseq = torch.randn(64, generator=torch.Generator().manual_seed(4)).to(dev)
+    seq_ref, dh_ref, dW_ref = _torch_lmhead_reference(h, W, y, m, gseq, chunk_rows=4096)
+    seq, lse, _, rl, rw, _ = F.lmhead_logprob_fwd(h, W, y, m, False)
+    dh, dw = F.lmhead_logprob_bwd(h, W, rl, rw, lse, gseq, False, dhidden_dtype=torch.float32)
+    assert rel(seq, seq_ref) < 1e-5
+    assert rel(dh, dh_ref) < GRAD_RTOL and rel(dw, dW_ref) < GRAD_RTOL
+
+
+def test_cfg3_rank_slice_vs_torch(pg, cuda_device):
+    """One rank's share of BASELINE config 3 at FULL size: 4096 local rows against 32768 gathered rows (D = 512,
+    tau = 0.5, positives on diagonal offset 3 * 4096): row LSE, diagonal, column-LSE partial, dA and the dB partial
+    against fp32 torch with the 4096 x 32768 slice materialised; loss terms within 1e-4."""
+    from preference_guided_image_captioning_alignment_b200 import functional as F
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = cuda_device
+    nb, Bg, D, tau, off = 4096, 32768, 512, 0.5, 3 * 4096
+    g = torch.Generator().manual_seed(33)
+    b_all = torch.nn.functional.normalize(torch.randn(Bg, D, generator=g), dim=-1).bfloat16().to(dev)
+    a = torch.nn.functional.normalize(b_all[off:off + nb].float().cpu() + 0.5 * torch.randn(nb, D, generator=g),
+                                      dim=-1).bfloat16().to(dev)
+    S = (a.float() @ b_all.float().T) / tau
+    lse_row_ref = torch.logsumexp(S, 1)
+    lse_col_ref = torch.logsumexp(S, 0)
+    idx = torch.arange(nb, device=dev)
+    diag_ref = S[idx, idx + off]
+    lse_row, diag, lse_col = F.ntxent_fwd(a, b_all, 1.0 / tau, off)
+    assert rel(lse_row, lse_row_ref) < 1e-5 and rel(lse_col, lse_col_ref) < 1e-5 and rel(diag, diag_ref) < 1e-5
+    loss_terms = (lse_row - diag).sum().item()
+    assert abs(loss_terms - (lse_row_ref - diag_ref).sum().item()) <= LOSS_RTOL * abs(loss_terms)
+    # backward with the rank-local column LSE standing in for the merged one (same closed form, one rank)
+    one = torch.ones((), device=dev)
+    mult = 1.0 / (2.0 * Bg)
+    da, db = F.ntxent_bwd(a, b_all, 1.0 / tau, off, lse_row, lse_col, one, mult)
+    dS = torch.exp(S - lse_row_ref[:, None]) + torch.exp(S - lse_col_ref[None, :])
+    dS[idx, idx + off] -= 2.0
+    dS *= mult / tau
+    assert rel(da, dS @ b_all.float()) < GRAD_RTOL and rel(db, dS.T @ a.float()) < GRAD_RTOL
