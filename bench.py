@@ -280,7 +280,8 @@ def run_ours(args, rank, world, local_rank):
     overlap = None
     if world > 1 and ar_mode == "overlap" and fused:
         from preference_guided_image_captioning_alignment_b200 import distributed as D
-        overlap = D.OverlappedDWAllReduce(V, d, dev, segments=int(os.environ.get("PGICA_DW_SEGMENTS", "8")))
+        overlap = D.OverlappedDWAllReduce(V, d, dev, segments=int(os.environ.get("PGICA_DW_SEGMENTS", "8")),
+                                          max_ctas=int(os.environ.get("PGICA_DW_AR_CTAS", "0")))
     elif world > 1:
         ar_mode = "nccl"
 
@@ -352,6 +353,13 @@ def run_ours(args, rank, world, local_rank):
         elapsed_ms = t.item()
     pair_tokens_step = B * (T - 1)
     value = pair_tokens_step * world * args.steps / (elapsed_ms * 1e-3)
+    if os.environ.get("PGICA_BENCH_LEAN"):  # tuning runs: the resident step only (NOT the contract line)
+        if rank == 0:
+            emit({"lean": True, "metric": METRIC, "value": value, "n_gpus": world, "ms_per_step": elapsed_ms / args.steps,
+                  "phase_ms": phase_ms, "dw_allreduce": ar_mode,
+                  "segments": overlap.nseg if overlap is not None else None,
+                  "ar_ctas": overlap.max_ctas if overlap is not None else None})
+        return
 
     # ------------------------------------------------------------------ end-to-end step (public module API)
     # FusedDPOHead.forward_stacked and its backward, recorded once per input-buffer set into CUDA graphs

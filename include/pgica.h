@@ -54,6 +54,7 @@ int64_t pgica_kernel_launches(void);
  * kernel when both gradients are wanted; 0: one launch per product), "sggf_plan_r2" / "sggf_plan_c2" (pin the dual
  * kernel's role split; 0 = planner), "sggf_coop" (1: cooperative launch, a refused launch is an error; 0: plain
  * launch), "sggf_single_chunk" (1: keep all of x in one chunk whenever it fits — y streamed once, out_y written once),
+ * "sggf_col_groups" (1: the planner may use column groups, 0: never, n > 1: exactly n),
  * "sggf_spread", "sggf_slots", "sggf_producers_only" (tuning / diagnostics), "sgg_cluster"
  * (cluster size of the one-product kernel).  set: 0 or PGICA_ERR_INVALID_ARGUMENT; get: INT64_MIN for an unknown name. */
 int pgica_set_option(const char* name, int64_t value);
@@ -121,12 +122,15 @@ int pgica_softmax_grad_gemm(const void* x, const void* y, int64_t mx, int64_t my
  * recompute G tiles or keep a 128 x 512 slice of out_x / out_y resident in TMEM; tiles travel through an
  * L2-resident exchange ring inside `workspace` (pgica_softmax_grad_gemm_dual_workspace_bytes, 256-byte aligned).
  * out_y must be fp32 when x has more row blocks than fit one chunk (it is then accumulated in place).
+ * When x has FEW row blocks (the compacted Stage-2 batches: 2-4) and out_x is fp32, several X-holder pairs share the
+ * sweep over y ("column groups"; out_x is zeroed and the partial sums add-reduced), so the launch scales with the
+ * rows of x instead of costing a fixed ~0.5 ms for the GPT-2 vocabulary.
  * ---------------------------------------------------------------------------------------------- */
 int pgica_softmax_grad_gemm_dual_workspace_bytes(int64_t mx, int64_t my, int64_t k, size_t* bytes_host);
-/* The role split the kernel's planner picks when `npairs` CTA pairs are resident (74 on a B200): plan_host[0..4] =
- * row pairs per chunk, column pairs per pass, X-holder pairs, Y-holder pairs, producer pairs.  Host arithmetic only. */
-int pgica_softmax_grad_gemm_dual_plan(int64_t mx, int64_t my, int64_t k, int npairs, int single_chunk,
-                                      int32_t* plan_host);
+/* The role split the kernel's planner picks when `npairs` CTA pairs are resident (74 on a B200): plan_host[0..5] =
+ * row pairs per chunk, column pairs per pass, X-holder pairs, Y-holder pairs, producer pairs, column groups of the
+ * X-holders.  flags bit 0: x must stay in one chunk; bit 1: column groups allowed (fp32 out_x).  Host arithmetic only. */
+int pgica_softmax_grad_gemm_dual_plan(int64_t mx, int64_t my, int64_t k, int npairs, int flags, int32_t* plan_host);
 int pgica_softmax_grad_gemm_dual(const void* x, const void* y, int64_t mx, int64_t my, int64_t k, float scale,
                                  const float* r_lse, const float* r_coef, const int32_t* r_tgt, const float* c_lse,
                                  const float* c_coef, const int32_t* c_tgt, void* out_x, int out_x_is_bf16,

@@ -24,7 +24,8 @@ int pgica_probe_umma(const void* a, const void* b, int64_t n, int64_t k, int b_m
 /* Host replay of the dual kernel's tile schedule (the same enumerators the device code runs; test hook, no device):
  * role 0: every quad in production order, 3 ints each (q, row pair, column pair); role 1 / 2: the pair-tiles X- /
  * Y-holder pair `idx` accumulates, 6 ints each (q, sel, row pair, column pair, first-of-period, period).  Returns the
- * number of records (only the first `capacity` are written), -1 on a bad argument. */
+ * number of records (only the first `capacity` are written), -1 on a bad argument.  Bits 8.. of `spread` carry the
+ * column-group count of the X-holders (0 / 1 = none); with groups, X-holder idx = (row pair) * groups + group. */
 int64_t pgica_debug_dual_schedule(int row_pairs, int col_pairs, int row_pairs_per_chunk, int col_pairs_per_pass,
                                   int spread, int role, int idx, int32_t* out_host, int64_t capacity);
 

@@ -93,7 +93,7 @@ namespace {
 struct OptionTable {
   std::atomic<int64_t> v[kOptCount];
   OptionTable() {
-    static const int64_t defaults[kOptCount] = {1, 0, 0, 1, 0, 0, 0, 0, 0};
+    static const int64_t defaults[kOptCount] = {1, 0, 0, 1, 0, 0, 0, 0, 0, 1};
     for (int i = 0; i < kOptCount; ++i) v[i].store(defaults[i]);
     auto env_int = [](const char* name, Option o, OptionTable* t) {
       if (const char* e = getenv(name)) t->v[o].store(atoll(e));
@@ -108,6 +108,7 @@ struct OptionTable {
     env_int("PGICA_SGGF_DEBUG_PRODUCERS_ONLY", kOptSggfProducersOnly, this);
     env_int("PGICA_SGG_CLUSTER", kOptSggCluster, this);
     env_int("PGICA_SGGF_SINGLE_CHUNK", kOptSggfSingleChunk, this);
+    env_int("PGICA_SGGF_COL_GROUPS", kOptSggfColGroups, this);
     if (const char* e = getenv("PGICA_SGGF_PLAN")) {
       int r2 = 0, c2 = 0;
       if (sscanf(e, "%d,%d", &r2, &c2) == 2 && r2 >= 1 && c2 >= 1) {
@@ -122,7 +123,8 @@ OptionTable& options() {
   return t;
 }
 const char* const kOptionNames[kOptCount] = {"sgg_fused",  "sggf_plan_r2", "sggf_plan_c2",        "sggf_coop", "sggf_spread",
-                                             "sggf_slots", "sggf_producers_only", "sgg_cluster", "sggf_single_chunk"};
+                                             "sggf_slots", "sggf_producers_only", "sgg_cluster", "sggf_single_chunk",
+                                             "sggf_col_groups"};
 int option_index(const char* name) {
   if (!name) return -1;
   for (int i = 0; i < kOptCount; ++i)

@@ -58,6 +58,8 @@ enum Option {
   kOptSggfProducersOnly,     // "sggf_producers_only": diagnostics, holders idle
   kOptSggCluster,            // "sgg_cluster": cluster size of the one-product kernel (4, 2 or 1; 0 = largest that tiles k)
   kOptSggfSingleChunk,       // "sggf_single_chunk": 1 = keep all of X in one chunk whenever it fits (W streamed once)
+  kOptSggfColGroups,         // "sggf_col_groups": 1 = the planner may split an X-holder's column sweep over several pairs (default),
+                             //   0 = never, n > 1 = exactly n groups when they fit
   kOptCount
 };
 int64_t get_option(Option o);

@@ -102,6 +102,8 @@ struct SggfParams {
   int mx, my, k;
   int RB2, J2;            // row-block pairs of X, column-tile pairs of Y
   int R2, C2, S;          // row pairs per chunk, column pairs per pass, 512-column splits of k
+  int CG;                 // column groups: X-holder (row pair, group g) accumulates only the column pairs cp with cp % CG == g
+                          //   (few row blocks: several pairs share the sweep over Y; partial OutX sums are add-reduced)
   int nH, nW, nP, D;      // PAIRS per role; exchange double-slots per producer CTA
   int spread;             // 1: spread an X-holder's quads evenly over a pass (StepOffsets)
   int debug_producers_only;  // diagnostics: holders exit at once, producers publish nothing (results are garbage)
@@ -260,6 +262,8 @@ __host__ __device__ __forceinline__ void for_each_quad(const SggfParams& p, F&& 
 template <class F, class G>
 __host__ __device__ __forceinline__ void for_each_holder_tile(const SggfParams& p, bool is_y, int idx, F&& f, G&& g) {
   int qbase = 0, period = 0;
+  const int CG = p.CG > 1 ? p.CG : 1;
+  const int xrow = is_y ? 0 : idx / CG, xgrp = is_y ? 0 : idx % CG;  // X-holder slot = (row pair in chunk, column group)
   for (int r0 = 0, chunk = 0; r0 < p.RB2; r0 += p.R2, ++chunk) {
     const int Rc = p.R2 < p.RB2 - r0 ? p.R2 : p.RB2 - r0;
     bool first = true;
@@ -278,15 +282,15 @@ __host__ __device__ __forceinline__ void for_each_holder_tile(const SggfParams& 
           g(period, chunk, pass);
           ++period;
         }
-      } else if (idx < Rc) {
+      } else if (xrow < Rc) {
         for (int t = 0; t < Rc; ++t) {
           StepOffsets so(Rc, Cc, p.spread);
           for (int c = 0; c < Cc; ++c) {  // column pairs that meet this row pair in step t, increasing
-            if (so.row(t) == idx) {
+            if (so.row(t) == xrow && (c0 + c) % CG == xgrp) {
               const int q = qbase + t * Cc + c;
-              f(q, 0, r0 + idx, c0 + c, first, period);
+              f(q, 0, r0 + xrow, c0 + c, first, period);
               first = false;
-              f(q, 1, r0 + idx, c0 + c, false, period);
+              f(q, 1, r0 + xrow, c0 + c, false, period);
             }
             so.next();
           }
@@ -294,7 +298,7 @@ __host__ __device__ __forceinline__ void for_each_holder_tile(const SggfParams& 
       }
       qbase += Rc * Cc;
     }
-    if (!is_y && idx < Rc) {
+    if (!is_y && xrow < Rc) {
       g(period, chunk, 0);
       ++period;
     }
@@ -595,7 +599,8 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
 
   // ======================================================================================================= holders
   const bool is_y = pair >= p.nH;
-  const int hidx = (is_y ? pair - p.nH : pair) / p.S;   // row pair in chunk (X-holder) / column pair in pass (Y-holder)
+  const int hidx = (is_y ? pair - p.nH : pair) / p.S;   // X-holder: (row pair in chunk) * CG + column group; Y-holder: column pair in pass
+  const int xrow = hidx / (p.CG > 1 ? p.CG : 1);        // X-holder's row pair in the chunk
   const int split = (is_y ? pair - p.nH : pair) % p.S;  // which 512 output columns
   uint8_t* gbuf = smem;                       // two G tiles
   uint8_t* ring = smem + 2 * kPBytes;         // kCRing operand stages
@@ -792,9 +797,9 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
     for_each_holder_tile(
         p, is_y, hidx, [&](int, int, int, int, bool, int) {},
         [&](int period, int chunk, int pass) {
-          const int blk = 2 * (is_y ? pass * p.C2 + hidx : chunk * p.R2 + hidx) + (int)rho;
+          const int blk = 2 * (is_y ? pass * p.C2 + hidx : chunk * p.R2 + xrow) + (int)rho;
           const bool bf16 = (is_y ? p.outy_bf16 : p.outx_bf16) != 0;
-          const bool accumulate = is_y && chunk > 0;
+          const bool accumulate = is_y ? chunk > 0 : p.CG > 1;  // OutY over chunks / OutX over column groups (zeroed by the host)
           LAP(0);
           mbar_wait(outfull_bar, (uint32_t)period & 1u);
           LAP(1);
@@ -871,6 +876,7 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
 struct Plan {
   int R2, C2, nH, nW, nP;  // pairs
   double cost;
+  int CG;                  // column groups of the X-holders (1 unless x has few row blocks)
 };
 
 // Time model in units of one 256 x 256 x 16 pair instruction at the rate the holders sustain (~150 cycles): a holder
@@ -878,26 +884,35 @@ struct Plan {
 // arrived in time; measured on cfg2 it needs 1.5x that (profiles/r1_trace_sggf_v2_pairs.log: a quarter of its time
 // goes to waiting for TMA loads), and a drain of the 128 x 512 accumulator costs about 90.  The slowest role sets
 // the pace of a chunk.
-Plan choose_plan(int RB2, int J2, int k, int npairs, bool single_chunk) {
+//
+// Column groups (allow_groups): an X-holder pair sweeps ALL column pairs of its row pair, 32 instructions each —
+// 6300 for the GPT-2 vocabulary however few rows x has (the compacted Stage-2 batches of the trainer have 2-4 row
+// blocks).  When all of x fits one chunk with pairs to spare, CG X-holder pairs share a row pair's sweep (column pair
+// cp goes to group cp % CG) and add-reduce their partial OutX at the end.
+Plan choose_plan(int RB2, int J2, int k, int npairs, bool single_chunk, bool allow_groups = false) {
   const int S = k / kNC;
   const double per_quad = 1.5 * k / 16.0, drain = 90.0;
-  Plan best{0, 0, 0, 0, 0, 1e300};
+  Plan best{0, 0, 0, 0, 0, 1e300, 1};
   for (int R2 = single_chunk ? RB2 : 1; R2 <= RB2 && R2 * S <= npairs - S - 1; ++R2) {
-    const int nH = R2 * S;
-    for (int C2 = 1; C2 * S <= npairs - nH - 1 && C2 <= J2; ++C2) {
-      const int nW = C2 * S, nP = npairs - nH - nW;
-      const int passes = (J2 + C2 - 1) / C2;
-      double total = 0;
-      for (int r0 = 0; r0 < RB2; r0 += R2) {
-        const int Rc = RB2 - r0 < R2 ? RB2 - r0 : R2;
-        const double tH = 32.0 * J2 + drain;
-        const double tW = passes * (32.0 * Rc + drain);
-        const double tP = (double)(((long)J2 * Rc + nP - 1) / nP) * per_quad;
-        double t = tH > tW ? tH : tW;
-        if (tP > t) t = tP;
-        total += t + per_quad + 64;  // pipeline fill / drain of a chunk
+    const int max_groups = (allow_groups && R2 >= RB2) ? 16 : 1;
+    for (int CG = 1; CG <= max_groups && CG <= J2; ++CG) {
+      const int nH = R2 * S * CG;
+      if (nH > npairs - S - 1) break;
+      for (int C2 = 1; C2 * S <= npairs - nH - 1 && C2 <= J2; ++C2) {
+        const int nW = C2 * S, nP = npairs - nH - nW;
+        const int passes = (J2 + C2 - 1) / C2;
+        double total = 0;
+        for (int r0 = 0; r0 < RB2; r0 += R2) {
+          const int Rc = RB2 - r0 < R2 ? RB2 - r0 : R2;
+          const double tH = 32.0 * ((J2 + CG - 1) / CG) + drain;
+          const double tW = passes * (32.0 * Rc + drain);
+          const double tP = (double)(((long)J2 * Rc + nP - 1) / nP) * per_quad;
+          double t = tH > tW ? tH : tW;
+          if (tP > t) t = tP;
+          total += t + per_quad + 64;  // pipeline fill / drain of a chunk
+        }
+        if (total < best.cost) best = Plan{R2, C2, nH, nW, nP, total, CG};
       }
-      if (total < best.cost) best = Plan{R2, C2, nH, nW, nP, total};
     }
   }
   return best;
@@ -910,6 +925,7 @@ int plan_override(Plan* pl, int npairs, int S) {
   if (R2 * S + C2 * S >= npairs) return 0;
   pl->R2 = R2;
   pl->C2 = C2;
+  pl->CG = 1;
   pl->nH = R2 * S;
   pl->nW = C2 * S;
   pl->nP = npairs - pl->nH - pl->nW;
@@ -1005,9 +1021,11 @@ int plan_and_launch(const void* x, const void* y, int64_t mx, int64_t my, int64_
   // of only during the last chunk: the overlapped all-reduce gets the whole launch to hide in) and with option
   // sggf_single_chunk = 1 (W streamed once, OutY written once: 325 MB instead of 825 MB of DRAM traffic on cfg2, for
   // ~2 % more time — measured 1.071 vs 1.051 ms, profiles/r2_dual_ab1.log).
-  Plan pl = choose_plan(p.RB2, p.J2, (int)k, npairs, p.outy_bf16 != 0);
+  // column groups need an OutX that can be add-reduced: fp32
+  const bool groups_ok = !p.outx_bf16 && get_option(kOptSggfColGroups) != 0;
+  Plan pl = choose_plan(p.RB2, p.J2, (int)k, npairs, p.outy_bf16 != 0, groups_ok);
   if (pl.R2 < p.RB2 && (pg.counters != nullptr || get_option(kOptSggfSingleChunk) != 0)) {
-    const Plan one = choose_plan(p.RB2, p.J2, (int)k, npairs, true);
+    const Plan one = choose_plan(p.RB2, p.J2, (int)k, npairs, true, groups_ok);
     if (one.R2 >= p.RB2 && one.nP >= 1) pl = one;
   }
   plan_override(&pl, npairs, S);
@@ -1024,6 +1042,15 @@ int plan_and_launch(const void* x, const void* y, int64_t mx, int64_t my, int64_
   }
   p.R2 = pl.R2;
   p.C2 = pl.C2;
+  p.CG = pl.CG;
+  if (const int64_t forced = get_option(kOptSggfColGroups); forced > 1 && !p.outx_bf16 && pl.R2 >= p.RB2 &&
+                                                            pl.R2 * S * (int)forced + pl.nW < npairs && forced <= p.J2) {
+    p.CG = (int)forced;  // option sggf_col_groups > 1 pins the group count (tests)
+    pl.nH = pl.R2 * S * p.CG;
+    pl.nP = npairs - pl.nH - pl.nW;
+  }
+  if (p.CG > 1)  // partial OutX sums of the groups are add-reduced into zeros
+    PGICA_CUDA_OK(cudaMemsetAsync(p.out_x, 0, (size_t)mx * k * sizeof(float), st));
   p.nH = pl.nH;
   p.nW = pl.nW;
   p.nP = pl.nP;
@@ -1083,9 +1110,10 @@ bool sggf_single_chunk(int64_t mx, int64_t my, int64_t k) {
 }
 
 // Role split the planner picks for `npairs` resident CTA pairs (host arithmetic only; no device needed).
-void sggf_plan(int64_t mx, int64_t my, int64_t k, int npairs, int single_chunk, int out[5]) {
+void sggf_plan(int64_t mx, int64_t my, int64_t k, int npairs, int single_chunk, int out[6]) {
   const int RB2 = (int)((ceil_div(mx, kBM) + 1) / 2), J2 = (int)((ceil_div(my, kBT) + 1) / 2);
-  const Plan pl = choose_plan(RB2, J2, (int)k, npairs, single_chunk != 0);
+  const Plan pl = choose_plan(RB2, J2, (int)k, npairs, (single_chunk & 1) != 0, (single_chunk & 2) != 0);
+  out[5] = pl.CG;
   out[0] = pl.R2;
   out[1] = pl.C2;
   out[2] = pl.nH;
@@ -1098,6 +1126,8 @@ void sggf_plan(int64_t mx, int64_t my, int64_t k, int npairs, int single_chunk, 
 // (q, sel, row pair, column pair, first, period) per pair-tile.  Returns the number of records (written up to `cap`).
 int64_t sggf_schedule(int RB2, int J2, int R2, int C2, int spread, int role, int idx, int32_t* out, int64_t cap) {
   SggfParams p{};
+  p.CG = spread >> 8;  // bits 8.. of `spread` carry the column-group count for the host replay (0 / 1 = none)
+  spread &= 1;
   p.RB2 = RB2;
   p.J2 = J2;
   p.R2 = R2;
@@ -1185,24 +1215,25 @@ extern "C" int pgica_debug_set_sggf_trace(void* buf) {
 #endif
 
 namespace pgica {
-void sggf_plan(int64_t mx, int64_t my, int64_t k, int npairs, int single_chunk, int out[5]);
+void sggf_plan(int64_t mx, int64_t my, int64_t k, int npairs, int single_chunk, int out[6]);
 int64_t sggf_schedule(int RB2, int J2, int R2, int C2, int spread, int role, int idx, int32_t* out, int64_t cap);
 }
 extern "C" int64_t pgica_debug_dual_schedule(int row_pairs, int col_pairs, int row_pairs_per_chunk, int col_pairs_per_pass,
                                              int spread, int role, int idx, int32_t* out_host, int64_t capacity) {
   if (row_pairs < 1 || col_pairs < 1 || row_pairs_per_chunk < 1 || col_pairs_per_pass < 1 || role < 0 || role > 2 ||
-      idx < 0 || !out_host || capacity < 0)
+      idx < 0 || !out_host || capacity < 0 || (spread >> 8) > 64)
     return -1;
   return pgica::sggf_schedule(row_pairs, col_pairs, row_pairs_per_chunk, col_pairs_per_pass, spread, role, idx, out_host,
                               capacity);
 }
-extern "C" int pgica_softmax_grad_gemm_dual_plan(int64_t mx, int64_t my, int64_t k, int npairs, int single_chunk,
+extern "C" int pgica_softmax_grad_gemm_dual_plan(int64_t mx, int64_t my, int64_t k, int npairs, int flags,
                                                  int32_t* plan_host) {
+  const int single_chunk = flags;
   PGICA_REQUIRE(plan_host && mx > 0 && my > 0 && k > 0 && k % 512 == 0 && k / 512 <= 4 && npairs >= 3,
                 "softmax_grad_gemm_dual_plan: bad argument");
-  int out[5];
+  int out[6];
   pgica::sggf_plan(mx, my, k, npairs, single_chunk, out);
-  for (int i = 0; i < 5; ++i) plan_host[i] = out[i];
+  for (int i = 0; i < 6; ++i) plan_host[i] = out[i];
   return PGICA_OK;
 }
 

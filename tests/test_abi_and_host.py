@@ -200,7 +200,7 @@ def test_dual_backward_planner_host_side():
 
     from preference_guided_image_captioning_alignment_b200 import _lib
     lib = _lib.load()
-    out = (ctypes.c_int32 * 5)()
+    out = (ctypes.c_int32 * 6)()
     for mx, my, k in ((4096, 50257, 1024), (32768, 50257, 1024), (64, 64, 512), (4096, 4096, 512), (32768, 32768, 512),
                       (4096, 32768, 1536), (300, 1000, 2048)):
         S = k // 512
@@ -208,7 +208,8 @@ def test_dual_backward_planner_host_side():
         for npairs in (74, 66, 8):
             for single in (0, 1):
                 assert lib.pgica_softmax_grad_gemm_dual_plan(mx, my, k, npairs, single, out) == 0
-                r2, c2, nh, nw, npr = list(out)
+                r2, c2, nh, nw, npr, cg = list(out)
+                assert cg == 1
                 if npairs < 2 * S + 1 or (single and rb2 * S > npairs - S - 1):
                     assert r2 == 0  # no split / not in one chunk: the caller falls back to one launch per product
                     continue
@@ -217,12 +218,19 @@ def test_dual_backward_planner_host_side():
                 if single:
                     assert r2 == rb2
     assert lib.pgica_softmax_grad_gemm_dual_plan(4096, 50257, 1000, 74, 0, out) != 0  # k must be a multiple of 512
+    # few row blocks + column groups allowed (flags bit 1): several X-holder pairs share the sweep over the vocabulary
+    for mx in (218, 470, 900):
+        assert lib.pgica_softmax_grad_gemm_dual_plan(mx, 50257, 1024, 74, 2, out) == 0
+        r2, c2, nh, nw, npr, cg = list(out)
+        rb2 = ((mx + 127) // 128 + 1) // 2
+        assert r2 == rb2 and cg > 1 and nh == r2 * 2 * cg and nh + nw + npr == 74 and npr >= 1
 
 
 @pytest.mark.parametrize("rb2,j2,r2,c2", [(16, 197, 16, 9), (16, 197, 8, 11), (3, 5, 2, 4), (7, 6, 3, 2), (1, 1, 1, 1),
                                            (5, 40, 5, 3), (22, 22, 22, 22), (4, 9, 3, 9)])
 @pytest.mark.parametrize("spread", [0, 1])
-def test_dual_backward_schedule_is_consistent(rb2, j2, r2, c2, spread):
+@pytest.mark.parametrize("groups", [1, 3])
+def test_dual_backward_schedule_is_consistent(rb2, j2, r2, c2, spread, groups):
     """The three roles of the dual backward kernel walk ONE schedule (replayed on the host by the enumerators the
     device code runs): every (row pair, column pair) quad is produced exactly once; every X-holder consumes exactly the
     quads of its row pair and every Y-holder exactly those of its column pair, both in increasing production order
@@ -234,12 +242,16 @@ def test_dual_backward_schedule_is_consistent(rb2, j2, r2, c2, spread):
     from preference_guided_image_captioning_alignment_b200 import _lib
     lib = _lib.load()
 
+    if groups > 1 and (r2 < rb2 or groups > j2):
+        pytest.skip("column groups need all of x in one chunk and at least one column pair per group")
+    sp = spread | (groups << 8)
+
     def replay(role, idx, width):
         dummy = np.zeros(1, np.int32)
-        n = lib.pgica_debug_dual_schedule(rb2, j2, r2, c2, spread, role, idx, ctypes.c_void_p(dummy.ctypes.data), 0)
+        n = lib.pgica_debug_dual_schedule(rb2, j2, r2, c2, sp, role, idx, ctypes.c_void_p(dummy.ctypes.data), 0)
         assert n >= 0
         buf = np.zeros((max(n, 1), width), dtype=np.int32)
-        assert lib.pgica_debug_dual_schedule(rb2, j2, r2, c2, spread, role, idx, ctypes.c_void_p(buf.ctypes.data), n) == n
+        assert lib.pgica_debug_dual_schedule(rb2, j2, r2, c2, sp, role, idx, ctypes.c_void_p(buf.ctypes.data), n) == n
         return buf[:n]
 
     quads = replay(0, 0, 3)
@@ -247,14 +259,18 @@ def test_dual_backward_schedule_is_consistent(rb2, j2, r2, c2, spread):
     assert np.array_equal(quads[:, 0], np.arange(rb2 * j2))                       # q numbers every quad once, in order
     assert len({(r, c) for _, r, c in quads}) == rb2 * j2                          # every (row pair, column pair) once
     where = {(int(r), int(c)): int(q) for q, r, c in quads}
-    # X-holders: slot `idx` of a chunk serves row pairs idx, idx + r2, ... ; one accumulation period per chunk
+    # X-holders: slot `idx` of a chunk serves row pairs idx, idx + r2, ... ; one accumulation period per chunk.  With
+    # column groups slot = (row pair) * groups + g serves only the column pairs cp with cp % groups == g.
     seen_x = set()
-    for idx in range(min(r2, rb2)):
-        tiles = replay(1, idx, 6)
+    for slot in range(min(r2, rb2) * groups):
+        idx, grp = slot // groups, slot % groups
+        tiles = replay(1, slot, 6)
+        assert len(tiles) > 0
         assert np.all(np.diff(tiles[:, 0]) >= 0)                                   # production order
         assert np.array_equal(tiles[0::2, 1], np.zeros(len(tiles) // 2)) and np.array_equal(tiles[1::2, 1], np.ones(len(tiles) // 2))
         for q, sel, rp, cp, first, period in tiles[0::2]:
-            assert where[(rp, cp)] == q and rp % r2 == idx and period == rp // r2
+            assert where[(rp, cp)] == q and rp % r2 == idx and period == rp // r2 and cp % groups == grp
+            assert (int(rp), int(cp)) not in seen_x                                # exactly one group accumulates a quad
             seen_x.add((int(rp), int(cp)))
         starts = tiles[tiles[:, 4] == 1]
         assert len(starts) == len({int(t[5]) for t in tiles}) and np.all(starts[:, 1] == 0)

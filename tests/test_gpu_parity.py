@@ -1197,3 +1197,27 @@ def test_cfg3_rank_slice_vs_torch(pg, cuda_device):
     dS[idx, idx + off] -= 2.0
     dS *= mult / tau
     assert rel(da, dS @ b_all.float()) < GRAD_RTOL and rel(db, dS.T @ a.float()) < GRAD_RTOL
+
+
+@pytest.mark.parametrize("mx,my,k", [(100, 5003, 1024), (470, 50257, 1024), (300, 3000, 512), (513, 9000, 1536)])
+def test_dual_backward_column_groups(pg, cuda_device, mx, my, k):
+    """Few row blocks (the compacted Stage-2 batches): several X-holder pairs share a row pair's sweep over the vocabulary
+    ("column groups", partial OutX add-reduced into zeros).  Planner's choice, pinned group counts and the un-grouped
+    launch give the same gradients; OutX rows past mx stay untouched; fp32 torch agrees."""
+    from preference_guided_image_captioning_alignment_b200 import _lib
+    from preference_guided_image_captioning_alignment_b200 import functional as F
+    x, y, row, col = _dual_inputs(cuda_device, mx, my, k, "row")
+    outs = {}
+    try:
+        for groups in (0, 1, 2, 5):
+            _lib.set_option("sggf_col_groups", groups)
+            outs[groups] = F.softmax_grad_gemm_dual(x, y, 1.0, row=row, col=col)
+    finally:
+        _lib.set_option("sggf_col_groups", 1)
+    for groups in (1, 2, 5):
+        assert rel(outs[groups][0], outs[0][0]) < 1e-5 and rel(outs[groups][1], outs[0][1]) < 1e-5, groups
+    exact_x, _ = _sgg_reference(x, y, 1.0, row, col)
+    assert rel(outs[1][0], exact_x) < GRAD_RTOL
+    # bf16 OutX cannot be add-reduced: the launch falls back to one group and still works
+    bx, _ = F.softmax_grad_gemm_dual(x, y, 1.0, row=row, col=col, out_x_dtype=torch.bfloat16)
+    assert rel(bx.float(), exact_x) < GRAD_RTOL
