@@ -281,7 +281,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1 and ar_mode == "overlap" and fused:
         from preference_guided_image_captioning_alignment_b200 import distributed as D
         overlap = D.OverlappedDWAllReduce(V, d, dev, segments=int(os.environ.get("PGICA_DW_SEGMENTS", "8")),
-                                          max_ctas=int(os.environ.get("PGICA_DW_AR_CTAS", "0")))
+                                          max_ctas=int(os.environ.get("PGICA_DW_AR_CTAS", "-1")))
     elif world > 1:
         ar_mode = "nccl"
 
@@ -510,7 +510,9 @@ def run_ours(args, rank, world, local_rank):
         cfg5 = cfg5_extra()
     also = {"cfg3_ntxent_global_negatives": dist_ntxent, "cfg4_dpo_seq512": cfg4,
             "cfg5_stage2_step": None if cfg5 is None else {k: cfg5.get(k) for k in ("speedup", "first_loss_rel_diff", "unavailable", "error", "skipped") if k in cfg5},
-            "cfg2_valid_row_compaction": None if compaction is None else {k: compaction[k] for k in ("scored_rows", "rows", "speedup")},
+            "cfg2_valid_row_compaction": None if compaction is None else
+            {"rows": compaction["rows"], "speedup_at_10_20_tokens": compaction["speedup"],
+             "ms_vs_scored_rows": [[r["scored_rows"], round(r["c_abi_ms_per_step"], 4)] for r in compaction["sweep"]]},
             "ntxent_single_gpu": extras}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -599,9 +601,11 @@ def cfg4_extra(torch, dist, F, dev, rank, world, W, Wr, barrier):
 
 def compaction_extra(torch, pg, dev, W32):
     """Valid-row compaction on cfg2's shape with the reference's real padding statistics: 16 pairs,
-    seq 128, right-padded captions of U[10, 20] real tokens (pkg/data/preprocessing.py:223-231).  The trainer-facing
-    path — PreferenceLoss on LazyLogits, fp32 hidden states and fp32 tied weight — forward + backward; only scored
-    positions count as pair-tokens.  Next to it the same batch through the full-row op (every row, masked or not)."""
+    seq 128, right-padded captions (pkg/data/preprocessing.py:223-231 pads to 128; real captions are 10-20 tokens).
+    The trainer-facing path — PreferenceLoss on LazyLogits, fp32 hidden states and fp32 tied weight — forward + backward;
+    only scored positions count as pair-tokens.  Three paddings show how the time follows the scored rows; next to the
+    shortest one the same batch through the full-row op (every row, masked or not)."""
+    from preference_guided_image_captioning_alignment_b200 import functional as F
     from preference_guided_image_captioning_alignment_b200 import ops
     from preference_guided_image_captioning_alignment_b200.losses import LazyLogits
     B, T, d, V = CFG["pairs"], CFG["seq_len"], CFG["d"], CFG["vocab"]
@@ -609,42 +613,58 @@ def compaction_extra(torch, pg, dev, W32):
     hw = torch.randn(B, T, d, generator=g).to(dev).requires_grad_(True)
     hl = torch.randn(B, T, d, generator=g).to(dev).requires_grad_(True)
     W = W32.detach().clone().requires_grad_(True)
+    Wb = ops.cached_bf16(W)
     yw, yl = (torch.randint(0, V, (B, T), generator=g).to(dev) for _ in range(2))
-    lens = torch.randint(10, 21, (2, B), generator=g)
-    mw, ml = ((torch.arange(T)[None] < lens[i][:, None]).long().to(dev) for i in range(2))
-    scored = int(mw[:, 1:].sum() + ml[:, 1:].sum())
     pl = pg.PreferenceLoss(CFG["beta"])
+    out = {"workload": f"cfg2 shape ({B} pairs, seq {T}, d {d}, V {V}), right-padded captions; PreferenceLoss fwd+bwd on "
+                       "LazyLogits, fp32 hidden/weight, reference-free (trainer variant)", "rows": 2 * B * T, "sweep": []}
 
-    def compact_step():
-        W.grad = hw.grad = hl.grad = None
-        loss = pl(LazyLogits(hw, W), LazyLogits(hl, W), yw, yl, mw, ml)
-        loss.backward()
-        return loss
-
-    def full_step():
-        W.grad = hw.grad = hl.grad = None
-        lw = ops.lmhead_seq_logprob(hw, W, yw, mw, True)[0]
-        ll = ops.lmhead_seq_logprob(hl, W, yl, ml, True)[0]
-        loss = ops.dpo_loss(lw, ll, None, None, CFG["beta"], 0.0, B)[0]
-        loss.backward()
-        return loss
-
-    out = {"workload": f"cfg2 shape, right-padded captions U[10,20] of {T}: {scored} scored rows of {2 * B * T}; "
-                       "PreferenceLoss fwd+bwd, fp32 hidden/weight, reference-free (trainer variant)",
-           "scored_rows": scored, "rows": 2 * B * T}
-    for name, fn in (("compacted", compact_step), ("all_rows", full_step)):
+    def timeit(fn, iters=10):
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(10):
-            loss = fn()
+        for _ in range(iters):
+            r = fn()
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 10
-        out[name] = {"ms_per_step": ms, "valid_pair_tokens_per_s": 0.5 * scored / (ms * 1e-3), "loss": loss.item()}
-    out["speedup"] = out["all_rows"]["ms_per_step"] / out["compacted"]["ms_per_step"]
+        return e0.elapsed_time(e1) / iters, r
+
+    for lo, hi in ((10, 20), (40, 60), (T, T)):
+        lens = torch.randint(lo, hi + 1, (2, B), generator=g)
+        mw, ml = ((torch.arange(T)[None] < lens[i][:, None]).long().to(dev) for i in range(2))
+        scored = int(mw[:, 1:].sum() + ml[:, 1:].sum())
+        gs = [torch.full((B,), 0.01, device=dev), torch.full((B,), -0.01, device=dev)]
+
+        def module_step():
+            W.grad = hw.grad = hl.grad = None
+            loss = pl(LazyLogits(hw, W), LazyLogits(hl, W), yw, yl, mw, ml)
+            loss.backward()
+            return loss
+
+        def kernels_only():  # the C-ABI calls of the same step without autograd / module overhead
+            seqs, ctx = F.lmhead_compact_fwd([hw.detach(), hl.detach()], Wb, [yw, yl], [mw, ml], True)
+            return F.lmhead_compact_bwd(ctx, Wb, gs)
+
+        ms_mod, loss = timeit(module_step)
+        ms_ker, _ = timeit(kernels_only)
+        rec = {"caption_tokens": [lo, hi], "scored_rows": scored, "module_ms_per_step": ms_mod,
+               "c_abi_ms_per_step": ms_ker, "valid_pair_tokens_per_s": 0.5 * scored / (ms_mod * 1e-3), "loss": loss.item()}
+        if lo == 10:
+            def full_step():
+                W.grad = hw.grad = hl.grad = None
+                lw = ops.lmhead_seq_logprob(hw, W, yw, mw, True)[0]
+                ll = ops.lmhead_seq_logprob(hl, W, yl, ml, True)[0]
+                loss = ops.dpo_loss(lw, ll, None, None, CFG["beta"], 0.0, B)[0]
+                loss.backward()
+                return loss
+            ms_full, loss_f = timeit(full_step)
+            rec["all_rows_module_ms_per_step"] = ms_full
+            rec["all_rows_loss"] = loss_f.item()
+            out["scored_rows"] = scored
+            out["speedup"] = ms_full / ms_mod
+        out["sweep"].append(rec)
     return out
 
 

@@ -366,6 +366,38 @@ int pgica_grad_norm_clip(const void* const* grads_host, const int64_t* numels_ho
                          int n_tensors, float max_norm, int clip, float* stats, void* workspace,
                          size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * SURVEY 8(f) row 4 — the caption decoder's cross-attention over ONE key/value token (pkg/models/model.py:528-535,
+ * 594-601: nn.MultiheadAttention(query = token embeddings, key = value = the projected image) followed by
+ * attention_norm(text + attended)).  With a single key the softmax is identically 1, so
+ *     y[b,t,:] = LayerNorm(x[b,t,:] + out_bias + sum_h w[b,t,h] * u[b,h,:]),   u[b,h,:] = W_o[:, head h] v_h[b]
+ * where w is NULL (all ones: evaluation; pass heads = 1 and the head-summed u) or the attention-dropout weights
+ * keep[b,t,h] / (1 - p) in training.  x, y, dx: fp32 [batch][seqlen][dim]; u, du: [batch][heads][dim]; w:
+ * [batch][seqlen][heads]; mean, rstd: [batch*seqlen].  The backward owns one sequence per block (deterministic) and
+ * returns per-sequence partials [batch][dim] of dgamma, dbeta and sum_t dpre (= d out_bias) for the caller to add up.
+ * HBM-bound: x read and y written once forward; dy, x read and dx written once backward.
+ * ---------------------------------------------------------------------------------------------- */
+int pgica_xattn_ln_fwd(const float* x, const float* u, const float* w, const float* out_bias, const float* gamma,
+                       const float* beta, int64_t batch, int64_t seqlen, int64_t dim, int64_t heads, float eps, float* y,
+                       float* mean, float* rstd, void* stream);
+int pgica_xattn_ln_bwd(const float* dy, const float* x, const float* u, const float* w, const float* out_bias,
+                       const float* gamma, const float* mean, const float* rstd, int64_t batch, int64_t seqlen,
+                       int64_t dim, int64_t heads, float* dx, float* du, float* dgamma_part, float* dbeta_part,
+                       float* dpre_sum_part, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SURVEY 8(f) row 3 — tail of the projection heads that feed the contrastive head (pkg/models/model.py:136-142,
+ * 338-344: ... Linear -> LayerNorm; :826-829: F.normalize): e = LayerNorm(z) (the model also hands it to the decoder),
+ * n = e / max(||e||, eps_norm) (the NT-Xent operand), one launch; the backward takes the gradients of both outputs
+ * (either may be NULL).  stats: [rows][3] = mean, rstd, 1/max(||e||, eps).  dgamma_part / dbeta_part: one row of
+ * `dim` floats per block of 8 input rows (ceil(rows / 8) rows), summed by the caller.
+ * ---------------------------------------------------------------------------------------------- */
+int pgica_ln_l2norm_fwd(const float* z, const float* gamma, const float* beta, int64_t rows, int64_t dim, float eps_ln,
+                        float eps_norm, float* e, float* n, float* stats, void* stream);
+int pgica_ln_l2norm_bwd(const float* z, const float* gamma, const float* beta, const float* stats, const float* de,
+                        const float* dn, int64_t rows, int64_t dim, float* dz, float* dgamma_part, float* dbeta_part,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,10 +18,11 @@ from . import _lib  # noqa: F401  (ctypes binding; the library itself is loaded 
 from .components import (DPOPreferenceLoss, FusedDPOHead, NaNSafeGradientNorm, TemperatureScaledSimilarity,  # noqa: F401
                          compute_sequence_logprobs, lmhead_sequence_logprobs)
 from .graphs import GraphedContrastiveStep, GraphedDPOStep  # noqa: F401
-from .install import install, uninstall  # noqa: F401
+from .install import fuse_model, install, unfuse_model, uninstall  # noqa: F401
+from .prologue import collapsed_cross_attention_ln, ln_l2norm  # noqa: F401
 from .losses import ContrastiveLoss, DeferredLoss, LazyLogits, PreferenceLoss  # noqa: F401
 from .scoring import compute_similarity, paired_scores, retrieval_ranks  # noqa: F401
 
 __all__ = ["ContrastiveLoss", "PreferenceLoss", "DPOPreferenceLoss", "FusedDPOHead", "TemperatureScaledSimilarity",
            "compute_sequence_logprobs", "lmhead_sequence_logprobs", "LazyLogits", "GraphedDPOStep", "GraphedContrastiveStep", "NaNSafeGradientNorm",
-           "install", "uninstall", "DeferredLoss", "compute_similarity", "paired_scores", "retrieval_ranks"]
+           "install", "uninstall", "fuse_model", "unfuse_model", "collapsed_cross_attention_ln", "ln_l2norm", "DeferredLoss", "compute_similarity", "paired_scores", "retrieval_ranks"]

@@ -160,7 +160,7 @@ class OverlappedDWAllReduce:
     dW lives in torch symmetric memory; the buffer must not be rewritten (next backward) before `done` has fired on
     every rank — `backward` itself orders that."""
 
-    def __init__(self, vocab: int, d: int, device, group=None, segments: int = 8, max_ctas: int = 0):
+    def __init__(self, vocab: int, d: int, device, group=None, segments: int = 8, max_ctas: int = -1):
         import torch.distributed._symmetric_memory as symm
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = _world(group)
@@ -192,7 +192,10 @@ class OverlappedDWAllReduce:
         self.seg_pairs = [(min((s + 1) * self.rows_per_seg, self.rows) - s * self.rows_per_seg) // 256
                           for s in range(self.nseg)]
         self.stream = torch.cuda.Stream(device=device)
-        self.max_ctas = int(max_ctas)
+        # Grid of the all-reduce kernel.  Measured on 8 B200s (profiles/r2_n8_overlap_tuning.jsonl): one CTA per SM slows
+        # the co-resident backward kernel by 22 % (1.32 vs 1.08 ms), one per two SMs by 9 % with the same exposed tail
+        # (0.125 ms), one per four SMs no longer keeps up with NVLink (0.34 ms exposed).  Default: half the SMs.
+        self.max_ctas = int(max_ctas) if int(max_ctas) >= 0 else max(1, F._lib.load().pgica_sm_count() // 2)
         self.epoch = 0
         self.done = torch.cuda.Event()
         self.done.record()

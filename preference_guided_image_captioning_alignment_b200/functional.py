@@ -602,6 +602,60 @@ def lmhead_compact_bwd(ctx, weight_bf16, grad_seqs, need_dhidden=True, need_dwei
     return dhs, dw
 
 
+# ----------------------------------------------------------------------------------------- SURVEY 8(f) rows 3, 4
+def xattn_ln_fwd(x, u, w, out_bias, gamma, beta, eps):
+    """y = LayerNorm(x + out_bias + sum_h w[..., h] * u[:, h]) (pgica_xattn_ln_fwd).  -> (y, mean, rstd)"""
+    _need_cuda(x, u, w, out_bias, gamma, beta)
+    lib = _lib.load()
+    B, T, E = x.shape
+    H = u.shape[1]
+    y = torch.empty_like(x)
+    mean = torch.empty(B * T, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(B * T, dtype=torch.float32, device=x.device)
+    _lib.check(lib.pgica_xattn_ln_fwd(_p(x), _p(u), _p(w), _p(out_bias), _p(gamma), _p(beta), B, T, E, H, float(eps), _p(y),
+                                      _p(mean), _p(rstd), _stream()))
+    return y, mean, rstd
+
+
+def xattn_ln_bwd(dy, x, u, w, out_bias, gamma, mean, rstd):
+    """-> (dx, du, dgamma_part [B, E], dbeta_part [B, E], dpre_sum_part [B, E])"""
+    lib = _lib.load()
+    B, T, E = x.shape
+    H = u.shape[1]
+    f32 = dict(dtype=torch.float32, device=x.device)
+    dx = torch.empty_like(x)
+    du = torch.empty(B, H, E, **f32)
+    dg, db, dp = torch.empty(B, E, **f32), torch.empty(B, E, **f32), torch.empty(B, E, **f32)
+    _lib.check(lib.pgica_xattn_ln_bwd(_p(dy), _p(x), _p(u), _p(w), _p(out_bias), _p(gamma), _p(mean), _p(rstd), B, T, E, H,
+                                      _p(dx), _p(du), _p(dg), _p(db), _p(dp), _stream()))
+    return dx, du, dg, db, dp
+
+
+def ln_l2norm_fwd(z, gamma, beta, eps_ln, eps_norm):
+    """e = LayerNorm(z), n = e / max(||e||, eps_norm) in one launch.  -> (e, n, stats [rows, 3])"""
+    _need_cuda(z, gamma, beta)
+    lib = _lib.load()
+    rows, D = z.shape
+    e, n = torch.empty_like(z), torch.empty_like(z)
+    stats = torch.empty(rows, 3, dtype=torch.float32, device=z.device)
+    _lib.check(lib.pgica_ln_l2norm_fwd(_p(z), _p(gamma), _p(beta), rows, D, float(eps_ln), float(eps_norm), _p(e), _p(n),
+                                       _p(stats), _stream()))
+    return e, n, stats
+
+
+def ln_l2norm_bwd(z, gamma, beta, stats, de, dn):
+    """-> (dz, dgamma_part [ceil(rows / 8), D], dbeta_part)"""
+    lib = _lib.load()
+    rows, D = z.shape
+    nb = (rows + 7) // 8
+    dz = torch.empty_like(z)
+    dg = torch.empty(nb, D, dtype=torch.float32, device=z.device)
+    db = torch.empty(nb, D, dtype=torch.float32, device=z.device)
+    _lib.check(lib.pgica_ln_l2norm_bwd(_p(z), _p(gamma), _p(beta), _p(stats), _p(de), _p(dn), rows, D, _p(dz), _p(dg),
+                                       _p(db), _stream()))
+    return dz, dg, db
+
+
 # ----------------------------------------------------------------------------------------- device guard
 def _device_guard(fn):
     """Run `fn` with the device of its first CUDA tensor argument current: the stream handed to the C ABI

@@ -30,7 +30,7 @@ import weakref
 import torch
 import torch.nn as nn
 
-from . import components, losses, ops, scoring
+from . import components, losses, ops, prologue, scoring
 
 REFERENCE_PACKAGE = "preference_guided_image_captioning_alignment"
 _originals = {}
@@ -90,9 +90,31 @@ def resolve_causal_lm(lm):
     return lm
 
 
-def fuse_decoder(decoder):
+def fuse_model(model, cross_attention: bool = True, projection_tails: bool = True):
+    """Everything install() can fuse on an already-built PreferenceGuidedCaptioningModel: the lazy LM head, the one-key
+    cross-attention and the LayerNorm + L2-normalise tail of both projection heads (row 3).  All as
+    instance-level forward patches: the module tree and every state_dict key stay as they are."""
+    fuse_decoder(model.caption_decoder, cross_attention=cross_attention)
+    if projection_tails:
+        for enc in (getattr(model, "vision_encoder", None), getattr(model, "text_encoder", None)):
+            if enc is not None and hasattr(enc, "projection"):
+                prologue.fuse_projection_tail(enc)
+    return model
+
+
+def unfuse_model(model):
+    unfuse_decoder(model.caption_decoder)
+    for enc in (getattr(model, "vision_encoder", None), getattr(model, "text_encoder", None)):
+        if enc is not None and hasattr(enc, "projection"):
+            prologue.unfuse_projection_tail(enc)
+    return model
+
+
+def fuse_decoder(decoder, cross_attention: bool = False):
     """Make `decoder.lm_model`'s LM head lazy in place (idempotent).  `decoder` is a CaptionDecoder.  Nothing is added
     to or renamed in the module tree: checkpoints written before and after install() are interchangeable."""
+    if cross_attention and hasattr(decoder, "cross_attention") and hasattr(decoder, "attention_norm"):
+        prologue.fuse_cross_attention(decoder)
     lm = resolve_causal_lm(decoder.lm_model)
     head = lm.get_output_embeddings() if hasattr(lm, "get_output_embeddings") else lm.lm_head
     if head is None or not isinstance(head, nn.Linear):
@@ -109,6 +131,8 @@ def fuse_decoder(decoder):
 
 
 def unfuse_decoder(decoder):
+    if hasattr(decoder, "cross_attention") and hasattr(decoder, "attention_norm"):
+        prologue.unfuse_cross_attention(decoder)
     lm = resolve_causal_lm(decoder.lm_model)
     head = lm.get_output_embeddings() if hasattr(lm, "get_output_embeddings") else lm.lm_head
     head.__dict__.pop("forward", None)

@@ -281,3 +281,36 @@ def test_cfg5_stage2_step_patched_vs_unpatched(cuda_device):
     assert abs(n1 - n0) <= 1e-2 * n0, (n1, n0)
     assert _rel(w1, w0) < 1e-2
     assert abs(gen1 - gen0) <= 1e-4 * abs(gen0), (gen1, gen0)
+
+    # Everything install() can fuse (SURVEY 8(f) rows 3 and 4 on top of the LM head): the one-key cross-attention and
+    # the LayerNorm + normalise tails draw their own dropout masks, so the comparison runs with dropout off (eval mode,
+    # gradients on) — the Stage-2 step and a Stage-1 contrastive step.
+    model.eval()
+    l0, gen0, n0, w0, _ = run(mm.PreferenceLoss(0.1))
+    cap = {"ids": batch["preferred_ids"], "mask": batch["preferred_mask"]}
+
+    def stage1(cl):
+        model.zero_grad(set_to_none=True)
+        out = model(images=batch["image"], caption_ids=cap["ids"], caption_mask=cap["mask"], mode="contrastive")
+        loss = cl(out["image_embeddings"], out["text_embeddings"])
+        loss.backward()
+        g = model.vision_encoder.projection[0].weight.grad.clone()
+        return loss.item(), g, out
+
+    c0, gc0, _ = stage1(mm.ContrastiveLoss(0.07))
+    try:
+        pg.install()
+        pg.fuse_model(model)
+        l1, gen1, n1, w1, pref = run(mm.PreferenceLoss(0.1))
+        c1, gc1, out1 = stage1(mm.ContrastiveLoss(0.07))
+        assert isinstance(pref["logits"], losses.LazyLogits)
+        assert "forward" in model.caption_decoder.cross_attention.__dict__
+        assert "forward" in model.vision_encoder.projection[-1].__dict__
+    finally:
+        pg.unfuse_model(model)
+        pg.uninstall()
+    assert abs(l1 - l0) <= 1e-4 * abs(l0), (l1, l0)
+    assert abs(n1 - n0) <= 1e-2 * n0 and _rel(w1, w0) < 1e-2
+    assert abs(c1 - c0) <= 1e-4 * abs(c0), (c1, c0)
+    assert _rel(gc1, gc0) < 1e-2
+    assert "forward" not in model.caption_decoder.cross_attention.__dict__

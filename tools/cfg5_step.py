@@ -71,19 +71,31 @@ def run(batch=8, steps=5, warmup=2, seq_len=128, log=print):
     state = {k: v.clone() for k, v in model.state_dict().items()}
     ref = arm(lambda: mm.PreferenceLoss(0.1), "reference step:")
     model.load_state_dict(state)
+    def eval_loss(make_loss):  # dropout off: the two arms must agree (the fused cross-attention draws its own masks)
+        model.eval()
+        with torch.no_grad():
+            val = ref_model.stage2_micro_step(model, make_loss(), data)[0].item()
+        model.train()
+        return val
+
+    ref_eval = eval_loss(lambda: mm.PreferenceLoss(0.1))
     try:
         pg.install()
-        inst.fuse_decoder(model.caption_decoder)
+        pg.fuse_model(model)   # lazy LM head + one-key cross-attention + LayerNorm/normalise tails
+        ours_eval = eval_loss(lambda: mm.PreferenceLoss(0.1))
         ours = arm(lambda: mm.PreferenceLoss(0.1), "patched step:  ")
     finally:
-        inst.unfuse_decoder(model.caption_decoder)
+        pg.unfuse_model(model)
         pg.uninstall()
     return {"workload": f"cfg5: Stage-2 micro-step (2 forwards, PreferenceLoss, backward, clip, AdamW), batch {batch}, "
                         f"seq {seq_len}, right-padded captions U[10,20] ({valid} scored rows of {2 * batch * seq_len}), "
                         "fp32, TF32 off, random-init 867 M reference model",
             "reference": ref, "patched": ours,
             "speedup": ref["ms_per_step_median"] / ours["ms_per_step_median"],
-            "first_loss_rel_diff": abs(ours["first_loss"] - ref["first_loss"]) / abs(ref["first_loss"])}
+            "patched_with": "install() + fuse_model(): lazy LM head + compacted pair-stacked PreferenceLoss, one-key "
+                            "cross-attention + LayerNorm fused, LayerNorm + L2-normalise tails fused",
+            "eval_loss_reference": ref_eval, "eval_loss_patched": ours_eval,
+            "first_loss_rel_diff": abs(ours_eval - ref_eval) / abs(ref_eval)}
 
 
 if __name__ == "__main__":
