@@ -469,9 +469,44 @@ def run_ours(args, rank, world, local_rank):
         t = torch.tensor([n0.elapsed_time(n1) / 10], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         Bg = bl * world
+
+        # phase split of the same step, issued piece by piece (same building blocks as distributed._GlobalNTXent)
+        def nt_phases(ev):
+            off = rank * bl
+            ev[0].record()
+            a_op, b_op = F.as_bf16(a_l.detach()), F.as_bf16(b_l.detach())
+            b_all = D.all_gather_rows(b_op)
+            ev[1].record()
+            lse_row, diag, lse_col_part = F.ntxent_fwd(a_op, b_all, 2.0, off)
+            ev[2].record()
+            parts = D.all_gather_rows(lse_col_part.reshape(1, Bg))
+            lse_col = F.lse_combine(parts)
+            loss = F.ntxent_loss(lse_row, diag, lse_col[off:off + bl].contiguous(), 1.0 / Bg)
+            dist.all_reduce(loss)
+            ev[3].record()
+            da, db_part = F.ntxent_bwd(a_op, b_all, 2.0, off, lse_row, lse_col, one, 1.0 / (2.0 * Bg))
+            ev[4].record()
+            D.reduce_scatter_rows(db_part)
+            ev[5].record()
+
+        names = ["cast + all-gather of text rows (bf16)", "forward: row LSE / diagonal / column-LSE partials",
+                 "column-LSE all-gather + merge + loss all-reduce", "backward: dA and dB partial (recompute)",
+                 "reduce-scatter of dB (fp32)"]
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(8)]
+        for e in evs[:3]:
+            nt_phases(e)
+        barrier()
+        for e in evs[3:]:
+            nt_phases(e)
+        barrier()
+        ph = torch.tensor([sum(e[i].elapsed_time(e[i + 1]) for e in evs[3:]) / 5 for i in range(5)], device=dev)
+        dist.all_reduce(ph, op=dist.ReduceOp.MAX)
         dist_ntxent = {"global_batch": Bg, "rows_per_gpu": bl, "ms_per_step": t.item(),
                        "pairs_per_s": Bg / (t.item() * 1e-3), "algorithmic_tflops": 6.0 * Bg * Bg * 512 / t.item() / 1e9,
+                       "algorithmic_tflops_per_gpu": 6.0 * bl * Bg * 512 / t.item() / 1e9,
+                       "frac_of_measured_bf16_peak_per_gpu": 6.0 * bl * Bg * 512 / t.item() / 1e9 / peaks()["burst"],
                        "loss": nt_loss.item(),
+                       "phase_ms_max_over_ranks": dict(zip(names, [round(v, 4) for v in ph.tolist()])),
                        "collectives": "all-gather of text rows, all-gather of column-LSE partials, reduce-scatter of dB"}
     # ------------------------------------------------------------------ BASELINE config 4, this GPU's share
     cfg4 = cfg4_extra(torch, dist, F, dev, rank, world, W, Wr, barrier)

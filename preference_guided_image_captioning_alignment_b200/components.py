@@ -244,7 +244,19 @@ class NaNSafeGradientNorm(nn.Module):
         grads = [p.grad for p in parameters if p.grad is not None]
         if len(grads) == 0:
             return torch.tensor(0.0), True
-        stats = F.grad_norm_clip(grads, self.max_norm, clip=True)
+        native = all(g.is_contiguous() and g.dtype in (torch.float32, torch.bfloat16) for g in grads)
+        if native:
+            stats = F.grad_norm_clip(grads, self.max_norm, clip=True)
+        else:
+            # gradient layouts the multi-tensor kernel does not take in place (non-contiguous views, fp16 / fp64): the
+            # norm is taken over contiguous fp32 copies of those, and the clip coefficient — still on the device, no
+            # host round trip — is applied to every gradient in place
+            views = [g if (g.is_contiguous() and g.dtype in (torch.float32, torch.bfloat16)) else
+                     g.detach().float().contiguous() for g in grads]
+            stats = F.grad_norm_clip(views, self.max_norm, clip=False)
+            scale = torch.where((stats[2] != 0) & (stats[1] < 1), stats[1], torch.ones_like(stats[1]))
+            for g in grads:
+                g.mul_(scale.to(g.dtype))
         total_norm = stats[0]
         is_finite = bool(stats[2].item() != 0.0)  # the one host read the reference makes too (components.py:307)
         if not is_finite and self.error_if_nonfinite:

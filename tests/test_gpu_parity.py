@@ -1346,3 +1346,24 @@ def test_ln_l2norm_matches_layernorm_then_normalize(pg, cuda_device, rows, D):
     assert rel(torch.nn.functional.normalize(out, p=2, dim=0), torch.nn.functional.normalize(ref_e, p=2, dim=0)) < 1e-6
     prologue.unfuse_projection_tail(enc)
     assert type(enc.projection(x)) is torch.Tensor
+
+
+def test_grad_norm_clip_odd_layouts(pg, cuda_device):
+    """NaNSafeGradientNorm on gradients the multi-tensor kernel cannot take in place (a transposed view, fp16, fp64):
+    same norm and the same clipped values as torch.nn.utils.clip_grad_norm_ (do not raise)."""
+    g = torch.Generator().manual_seed(21)
+    shapes = [(33, 65), (128,), (7, 9, 5), (40, 24)]
+    ps = [torch.nn.Parameter(torch.zeros(*s, device=cuda_device)) for s in shapes]
+    ps[3] = torch.nn.Parameter(torch.zeros(40, 24, device=cuda_device, dtype=torch.float16))
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    for p, r in zip(ps, ref):
+        gr = torch.randn(*p.shape, generator=g).to(cuda_device) * 3
+        p.grad = gr.to(p.dtype)
+        r.grad = gr.to(p.dtype).clone()
+    ps[0].grad = ps[0].grad.t().contiguous().t()          # same values, non-contiguous layout
+    assert not ps[0].grad.is_contiguous()
+    norm_ref = torch.nn.utils.clip_grad_norm_(ref, 1.0)
+    total, finite = pg.NaNSafeGradientNorm(max_norm=1.0)(ps)
+    assert finite and abs(total.item() - norm_ref.item()) <= 1e-4 * norm_ref.item()
+    for p, r in zip(ps, ref):
+        assert rel(p.grad.float(), r.grad.float()) < 2e-3
