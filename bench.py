@@ -373,7 +373,7 @@ def run_ours(args, rank, world, local_rank):
     # N > 1 the same all-reduce (fp32 dW + the packed scalars), as the resident arm above
     Wp = W.float().requires_grad_(True)
     h2d = sum(t.numel() * t.element_size() for t in (H_host, Hr_host, y_host, m_host))
-    use_graph = os.environ.get("PGICA_BENCH_E2E_GRAPH", "1") != "0"
+    use_graph = os.environ.get("PGICA_BENCH_E2E_GRAPH", "1") != "0" and overlap is None
     copy_stream = torch.cuda.Stream(device=dev)
     copied = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
@@ -400,7 +400,37 @@ def run_ours(args, rank, world, local_rank):
         ev.record()
     issue_copy(0)
 
+    # N > 1 with the overlapped all-reduce: the step is issued through the functional wrappers + the reducer (the public
+    # multi-GPU entry point, distributed.OverlappedDWAllReduce.backward), same copies in, same loss read out.  The loss
+    # goes to pinned memory right after the forward; the host reads it while the backward + all-reduce are running.
+    loss_pinned = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    fwd_done = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_step_overlapped():
+        slot = state["k"] & 1
+        state["k"] += 1
+        issue_copy(slot ^ 1)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(copied[slot])
+        Hd, Hrd, yd, md = bufs[slot]
+        Hd = Hd.detach()
+        seq_p, lse_p, _, rl, rw, _ = F.lmhead_logprob_fwd(Hd, W, yd, md, False)
+        seq_r = F.lmhead_logprob_fwd(Hrd, Wr, yd, md, False)[0]
+        loss, metrics, dpc = F.dpo_loss_fwd(seq_p[:B], seq_p[B:], seq_r[:B], seq_r[B:], beta, 0.0, n_global)
+        loss_pinned[slot].copy_(loss, non_blocking=True)
+        fwd_done[slot].record()
+        gseq = F.dpo_grad_seq(dpc, one)
+        dh, dw, done, packed = overlap.backward(Hd, W, rl, rw, lse_p, gseq, False,
+                                                scalars=torch.cat([loss.reshape(1), metrics]))
+        cur.wait_event(done)
+        state["packed"] = packed
+        consumed[slot].record()
+        fwd_done[slot].synchronize()
+        return loss_pinned[slot].item()
+
     def e2e_step():
+        if overlap is not None:
+            return e2e_step_overlapped()
         slot = state["k"] & 1
         state["k"] += 1
         issue_copy(slot ^ 1)  # prefetch the next step's inputs
@@ -568,7 +598,10 @@ def run_ours(args, rank, world, local_rank):
                 "ms_per_step": e2e_ms / args.steps,
                 "last_loss": last_loss if world == 1 else float(state["packed"][0].item()),
                 "last_loss_read_in_step": last_loss,  # what the step's D2H read returned (this rank's share when N > 1)
-                "api": "GraphedDPOStep.launch + loss_value (CUDA graphs of FusedDPOHead.forward_stacked and its backward)" if use_graph
+                "api": "functional.lmhead_logprob_fwd / dpo_loss_fwd + distributed.OverlappedDWAllReduce.backward (dW and the "
+                       "scalars summed over the ranks by the co-resident peer-memory all-reduce), loss read from pinned "
+                       "memory after the forward" if overlap is not None else
+                       "GraphedDPOStep.launch + loss_value (CUDA graphs of FusedDPOHead.forward_stacked and its backward)" if use_graph
                        else "FusedDPOHead.forward_stacked + backward, eager"},
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -194,8 +194,10 @@ class OverlappedDWAllReduce:
         self.stream = torch.cuda.Stream(device=device)
         # Grid of the all-reduce kernel.  Measured on 8 B200s (profiles/r2_n8_overlap_tuning.jsonl): one CTA per SM slows
         # the co-resident backward kernel by 22 % (1.32 vs 1.08 ms), one per two SMs by 9 % with the same exposed tail
-        # (0.125 ms), one per four SMs no longer keeps up with NVLink (0.34 ms exposed).  Default: half the SMs.
-        self.max_ctas = int(max_ctas) if int(max_ctas) >= 0 else max(1, F._lib.load().pgica_sm_count() // 2)
+        # (0.125 ms), one per four SMs no longer keeps up with NVLink (0.34 ms exposed).  With 2 ranks a rank moves half
+        # as much and the full grid is the faster one (1.75 vs 1.80 ms).  Default: every SM up to 2 ranks, half beyond.
+        sms = F._lib.load().pgica_sm_count()
+        self.max_ctas = int(max_ctas) if int(max_ctas) >= 0 else (sms if self.world <= 2 else max(1, sms // 2))
         self.epoch = 0
         self.done = torch.cuda.Event()
         self.done.record()
