@@ -39,7 +39,7 @@ def run():
     from preference_guided_image_captioning_alignment_b200 import _lib
     from preference_guided_image_captioning_alignment_b200 import functional as F
     lib = _lib.load()
-    dsmem = os.environ.get("PGICA_SGG_EXCHANGE", "").startswith("d")
+    dsmem = False  # the DSMEM-exchange kernel was retired in round 2
     setter = lib.pgica_debug_set_sgg_trace if dsmem else lib.pgica_debug_set_sggx_trace
     setter.argtypes = [ctypes.c_void_p]
     names = NAMES_DSMEM if dsmem else NAMES
