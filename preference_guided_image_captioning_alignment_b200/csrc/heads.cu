@@ -183,7 +183,7 @@ int pgica_ntxent_bwd(const void* a, const void* b, int64_t rows_a, int64_t rows_
   // The dual kernel wins while A fits one chunk of X-holders (B200: 102 vs 156 us at 4096 x 4096, 592 vs 807 us at
   // 4096 x 32768 = cfg3 per GPU); with three chunks (16384 x 16384) its producers, which pay two exponentials per
   // element here, fall behind the two single-product launches (1.26 vs 1.06 ms): tools/ntxent_check.py.
-  if (da && db && rows_a <= 6144 && sggf_supported(rows_a, rows_b, dim) && xws_bytes >= sggf_workspace_bytes() &&
+  if (da && db && sggf_supported(rows_a, rows_b, dim) && xws_bytes >= sggf_workspace_bytes() &&
       (!db_is_bf16 || sggf_single_chunk(rows_a, rows_b, dim)))
     // dA and dB from one recomputation of the similarity tiles (sgg_f.cu)
     return pgica_softmax_grad_gemm_dual(a, b, rows_a, rows_b, dim, inv_tau, lse_row, rcoef, rtgt, lse_col, ccoef, ctgt,

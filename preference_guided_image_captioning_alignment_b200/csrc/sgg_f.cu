@@ -254,6 +254,35 @@ __host__ __device__ __forceinline__ void for_each_quad(const SggfParams& p, F&& 
   }
 }
 
+// The quads q = first, first + stride, ... of the same production order WITHOUT walking the ones in between: a cursor
+// over the (chunk, pass) blocks plus the closed form of StepOffsets (off(c) = floor(c * step / Cc)).  Every producer
+// warp used to run for_each_quad over ALL quads and skip the foreign ones — ~240 cycles of loop control per quad,
+// i.e. ~9 k cycles per own quad with 36 producers: more than the 8.8 k cycles the MMAs of a k = 1024 quad take, and all
+// of it serial in the epilogue warps (profiles/r2_trace_sggf_enumeration_overhead.log: epi_other = quads x 240).
+template <class F>
+__host__ __device__ __forceinline__ void for_each_own_quad(const SggfParams& p, int first, int stride, F&& f) {
+  int r0 = 0, c0 = 0, qbase = 0;
+  int Rc = p.R2 < p.RB2 ? p.R2 : p.RB2;
+  int Cc = p.C2 < p.J2 ? p.C2 : p.J2;
+  for (int q = first;; q += stride) {
+    while (q >= qbase + Rc * Cc) {  // advance to the block that holds q
+      qbase += Rc * Cc;
+      c0 += p.C2;
+      if (c0 >= p.J2) {
+        c0 = 0;
+        r0 += p.R2;
+        if (r0 >= p.RB2) return;
+        Rc = p.R2 < p.RB2 - r0 ? p.R2 : p.RB2 - r0;
+      }
+      Cc = p.C2 < p.J2 - c0 ? p.C2 : p.J2 - c0;
+    }
+    const int ql = q - qbase;
+    const int t = ql / Cc, c = ql - t * Cc;
+    const int off = p.spread ? (c * Rc) / Cc : c;  // StepOffsets after c steps
+    f(q, r0, (off + t) % Rc, c0, c);
+  }
+}
+
 // Visits, in production order, the pair-tiles one holder pair accumulates (two per quad).  is_y = false: X-holder of
 // row pair `idx` (chunk-relative); true: Y-holder of column pair `idx` (pass-relative).  f(q, sel, rp, cp, first,
 // period): quad q = (row pair rp, column pair cp), absolute; sel = 0/1 picks the column tile 2cp + sel (X-holder)
@@ -281,6 +310,21 @@ __host__ __device__ __forceinline__ void for_each_holder_tile(const SggfParams& 
           }
           g(period, chunk, pass);
           ++period;
+        }
+      } else if (xrow < Rc && !p.spread) {
+        // off(c) = c: column pair c meets this row pair in step t iff c = xrow - t (mod Rc) — visited directly (walking
+        // all Rc x Cc quads of the pass to find them cost ~240 cycles each, see for_each_own_quad)
+        for (int t = 0; t < Rc; ++t) {
+          int c = xrow - t;
+          if (c < 0) c += Rc;
+          for (; c < Cc; c += Rc) {
+            if (CG == 1 || (c0 + c) % CG == xgrp) {
+              const int q = qbase + t * Cc + c;
+              f(q, 0, r0 + xrow, c0 + c, first, period);
+              first = false;
+              f(q, 1, r0 + xrow, c0 + c, false, period);
+            }
+          }
         }
       } else if (xrow < Rc) {
         for (int t = 0; t < Rc; ++t) {
@@ -383,13 +427,11 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
       // two TMA issues) against the ~550 the tensor pipe takes to consume one, which leaves no slack for jitter.
       // (Four loader warps were measured too: no further gain.)
       const int par = warp >> 1;
-      int slot = 0, mine = pp;
+      int slot = 0;
       uint32_t phase = 0, stage_no = 0;
       const uint32_t lbar0 = mapa_u32(smem_u32(&full_bar[0]), 0);  // the leader's full barriers (shared::cluster)
       LAP_DECL;
-      for_each_quad(p, [&](int q, int r0, int r, int c0, int c) {
-        if (q != mine) return;
-        mine += p.nP;
+      for_each_own_quad(p, pp, p.nP, [&](int q, int r0, int r, int c0, int c) {
         const int xrow = (2 * (r0 + r) + (int)rho) * kBM, yrow = (2 * (c0 + c) + (int)rho) * kBT;
         for (int kb = 0; kb < num_kb; ++kb, ++stage_no) {
           if ((int)(stage_no & 1u) == par) {
@@ -417,12 +459,10 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
       // ---------------------------------------------------------------- MMA1 (leader): Z[256 x 256] = X[2rp, 2rp+1] Y[2cp, 2cp+1]^T
       constexpr uint32_t idesc1 = make_idesc_bf16(256, 256, 0, 0);
       const uint64_t desc_k = make_smem_desc(0, 16, 1024);
-      int slot = 0, mine = pp;
+      int slot = 0;
       uint32_t phase = 0, n = 0;
       LAP_DECL;
-      for_each_quad(p, [&](int q, int, int, int, int) {
-        if (q != mine) return;
-        mine += p.nP;
+      for_each_own_quad(p, pp, p.nP, [&](int q, int, int, int, int) {
         const uint32_t buf = n & 1u;
         LAP(0);
         mbar_wait_cluster(&zempty_bar[buf], ((n >> 1) & 1u) ^ 1u);  // both epilogues have read this Z buffer
@@ -455,13 +495,10 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
       if (lane == 0) LAP_FLUSH(0, 3);
     } else if (warp == 3) {
       // ---------------------------------------------------------------- exchange: staging -> ring slot -> flag
-      int mine = pp;
       uint32_t n = 0, ntile = 0;
       const uint64_t pol_keep = l2_policy_evict_last();
       LAP_DECL;
-      for_each_quad(p, [&](int q, int, int, int, int) {
-        if (q != mine) return;
-        mine += p.nP;
+      for_each_own_quad(p, pp, p.nP, [&](int q, int, int, int, int) {
         const uint32_t ds = n % (uint32_t)p.D, use = n / (uint32_t)p.D;
         for (int half = 0; half < 2; ++half) {
           const uint32_t tslot = (pcta * p.D + ds) * 2u + half;
@@ -497,12 +534,9 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
       const int row_in_blk = quarter * 32 + lane;
       const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
       const uint32_t g_local = smem_u32(staging);
-      int mine = pp;
       uint32_t n = 0, ntile = 0;
       LAP_DECL;
-      for_each_quad(p, [&](int q, int r0, int r, int c0, int c) {
-        if (q != mine) return;
-        mine += p.nP;
+      for_each_own_quad(p, pp, p.nP, [&](int q, int r0, int r, int c0, int c) {
         const int row = (2 * (r0 + r) + (int)rho) * kBM + row_in_blk;
         float rl = 0.f, rc = 0.f;
         int rt = -1;
@@ -879,19 +913,23 @@ struct Plan {
   int CG;                  // column groups of the X-holders (1 unless x has few row blocks)
 };
 
-// Time model in units of one 256 x 256 x 16 pair instruction at the rate the holders sustain (~150 cycles): a holder
-// pair spends 16 per pair-tile (two per quad).  A producer pair would spend k/16 per quad if its operands always
-// arrived in time; measured on cfg2 it needs 1.5x that (profiles/r1_trace_sggf_v2_pairs.log: a quarter of its time
-// goes to waiting for TMA loads), and a drain of the 128 x 512 accumulator costs about 90.  The slowest role sets
-// the pace of a chunk.
+// Time model in units of one 256 x 256 x 16 pair instruction at the rate the holders sustain (~140 cycles): a holder
+// pair spends 16 per pair-tile (two per quad), a drain of the 128 x 512 accumulator costs about 90, a producer pair
+// what per_quad below says.  The slowest role sets the pace of a chunk.
 //
 // Column groups (allow_groups): an X-holder pair sweeps ALL column pairs of its row pair, 32 instructions each —
 // 6300 for the GPT-2 vocabulary however few rows x has (the compacted Stage-2 batches of the trainer have 2-4 row
 // blocks).  When all of x fits one chunk with pairs to spare, CG X-holder pairs share a row pair's sweep (column pair
 // cp goes to group cp % CG) and add-reduce their partial OutX at the end.
-Plan choose_plan(int RB2, int J2, int k, int npairs, bool single_chunk, bool allow_groups = false) {
+Plan choose_plan(int RB2, int J2, int k, int npairs, bool single_chunk, bool allow_groups = false,
+                 bool both_terms = false) {
   const int S = k / kNC;
-  const double per_quad = 1.5 * k / 16.0, drain = 90.0;
+  // a producer pair spends per quad the longer of its MMAs (k/16 instructions, ~1.1x with the TMA waits that remain —
+  // measured after round 2 removed the schedule walk from the producer warps, profiles/r2_dual_ab2.log) and of its
+  // epilogue (256 x 256 elements over two CTAs: ~5 k cycles with one exponential per element, ~8 k with two)
+  const double epilogue = both_terms ? 58.0 : 36.0;
+  const double mma = 1.1 * k / 16.0;
+  const double per_quad = mma > epilogue ? mma : epilogue, drain = 90.0;
   Plan best{0, 0, 0, 0, 0, 1e300, 1};
   for (int R2 = single_chunk ? RB2 : 1; R2 <= RB2 && R2 * S <= npairs - S - 1; ++R2) {
     const int max_groups = (allow_groups && R2 >= RB2) ? 16 : 1;
@@ -1023,9 +1061,9 @@ int plan_and_launch(const void* x, const void* y, int64_t mx, int64_t my, int64_
   // ~2 % more time — measured 1.071 vs 1.051 ms, profiles/r2_dual_ab1.log).
   // column groups need an OutX that can be add-reduced: fp32
   const bool groups_ok = !p.outx_bf16 && get_option(kOptSggfColGroups) != 0;
-  Plan pl = choose_plan(p.RB2, p.J2, (int)k, npairs, p.outy_bf16 != 0, groups_ok);
+  Plan pl = choose_plan(p.RB2, p.J2, (int)k, npairs, p.outy_bf16 != 0, groups_ok, kRow && kCol);
   if (pl.R2 < p.RB2 && (pg.counters != nullptr || get_option(kOptSggfSingleChunk) != 0)) {
-    const Plan one = choose_plan(p.RB2, p.J2, (int)k, npairs, true, groups_ok);
+    const Plan one = choose_plan(p.RB2, p.J2, (int)k, npairs, true, groups_ok, kRow && kCol);
     if (one.R2 >= p.RB2 && one.nP >= 1) pl = one;
   }
   plan_override(&pl, npairs, S);
@@ -1135,7 +1173,8 @@ int64_t sggf_schedule(int RB2, int J2, int R2, int C2, int spread, int role, int
   p.spread = spread;
   int64_t n = 0;
   if (role == 0) {
-    for_each_quad(p, [&](int q, int r0, int r, int c0, int c) {
+    // the producers' view, from the cursor the device code runs, cross-checked against the plain walk over all quads
+    for_each_own_quad(p, 0, 1, [&](int q, int r0, int r, int c0, int c) {
       if (n < cap) {
         out[3 * n] = q;
         out[3 * n + 1] = r0 + r;
@@ -1143,6 +1182,13 @@ int64_t sggf_schedule(int RB2, int J2, int R2, int C2, int spread, int role, int
       }
       ++n;
     });
+    int64_t m = 0;
+    bool same = true;
+    for_each_quad(p, [&](int q, int r0, int r, int c0, int c) {
+      if (m < cap && m < n) same &= out[3 * m] == q && out[3 * m + 1] == r0 + r && out[3 * m + 2] == c0 + c;
+      ++m;
+    });
+    if (!same || m != n) return -2;
   } else {
     for_each_holder_tile(
         p, role == 2, idx,

@@ -38,20 +38,27 @@ def timed(iters=10):
 
 
 plans = sys.argv[4].split(";") if len(sys.argv) > 4 else ["", "8,11", "16,8", "16,9", "16,10", "16,11"]
+best = {}
 ref = None
-for plan in plans:
-    for drain in (0, 1):
+for rnd in range(3):  # round-robin over the configurations: the clock drifts over a run, the minimum per plan is kept
+    for plan in plans:
         set_plan(plan or None)
-        _lib.set_option("sggf_direct_drain", drain)
         try:
-            ms, ox, oy = timed()
+            ms, ox, oy = timed(6)
         except Exception as e:
-            print(f"plan {plan or 'auto':6s} direct_drain {drain}: {e}")
+            best[plan] = str(e)
             continue
         if ref is None:
             ref = (ox.float(), oy)
         ex = ((ox.float() - ref[0]).norm() / ref[0].norm()).item()
         ey = ((oy - ref[1]).norm() / ref[1].norm()).item()
-        flops = 4.0 * mx * my * k
-        print(f"plan {plan or 'auto':6s} direct_drain {drain}: {ms:.4f} ms  {flops / ms / 1e9:7.1f} TF/s algorithmic   "
-              f"rel diff vs first: dX {ex:.2e} dY {ey:.2e}", flush=True)
+        old = best.get(plan)
+        if not isinstance(old, tuple) or ms < old[0]:
+            best[plan] = (ms, ex, ey)
+flops = 4.0 * mx * my * k
+for plan in plans:
+    b = best[plan]
+    if isinstance(b, tuple):
+        print(f"plan {plan or 'auto':6s}: {b[0]:.4f} ms  {flops / b[0] / 1e9:7.1f} TF/s algorithmic   rel diff vs first: dX {b[1]:.2e} dY {b[2]:.2e}")
+    else:
+        print(f"plan {plan or 'auto':6s}: {b}")

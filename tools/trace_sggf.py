@@ -34,15 +34,20 @@ x = (torch.randn(mx, k, device=dev) * 0.5).to(torch.bfloat16)
 y = (torch.randn(my, k, device=dev) * 0.02).to(torch.bfloat16)
 row = (torch.full((mx,), 11.0, device=dev), torch.randn(mx, device=dev),
        torch.randint(0, my, (mx,), device=dev, dtype=torch.int32))
+col = None
+if os.environ.get("MODE") == "both":  # NT-Xent form: row and column term
+    col = (torch.full((my,), 11.0, device=dev), torch.randn(my, device=dev),
+           torch.randint(0, mx, (my,), device=dev, dtype=torch.int32))
+OX = torch.float32 if os.environ.get("OX") == "f32" else torch.bfloat16
 buf = torch.zeros(1024, 24, dtype=torch.int64, device=dev)
 OY = torch.bfloat16 if os.environ.get('OY') == 'bf16' else torch.float32
 for _ in range(2):
-    F.softmax_grad_gemm_dual(x, y, 1.0, row=row, out_x_dtype=torch.bfloat16, out_y_dtype=OY)
+    F.softmax_grad_gemm_dual(x, y, 1.0, row=row, col=col, out_x_dtype=OX, out_y_dtype=OY)
 torch.cuda.synchronize()
 assert lib.pgica_debug_set_sggf_trace(ctypes.c_void_p(buf.data_ptr())) == 0
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
-F.softmax_grad_gemm_dual(x, y, 1.0, row=row, out_x_dtype=torch.bfloat16, out_y_dtype=OY)
+F.softmax_grad_gemm_dual(x, y, 1.0, row=row, col=col, out_x_dtype=OX, out_y_dtype=OY)
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
