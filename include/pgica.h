@@ -81,6 +81,18 @@ int pgica_gemm_lse(const void* a, const void* b, int64_t rows, int64_t cols, int
                    const int32_t* labels, int64_t diag_offset, float* lse, float* tgt, void* workspace,
                    size_t workspace_bytes, void* stream);
 
+/* Row AND column log-sum-exp from ONE pass over the tiles (the symmetric cross-entropy of NT-Xent needs both:
+ * pkg/models/model.py:994-995, pkg/models/components.py:135-136): lse_col[j] = log sum_i exp(scale*<a_i, b_j>) next to
+ * lse_row / tgt as in pgica_gemm_lse.  Every 32-row group of the epilogue publishes, per 32-column chunk, the column
+ * sums of exp2(t - shift) with shift = the largest running row maximum in the group; a merge kernel folds the groups.
+ * PRECONDITION: bounded logits — 2 * scale * log2(e) * max|<a_i, b_j>| < 100 (unit-norm embeddings with
+ * temperature >= 0.03), so that no term can underflow against its group's shift; callers that cannot promise that use
+ * two pgica_gemm_lse launches (exact for any input).  Workspace: pgica_gemm_lse_rowcol_workspace_bytes(). */
+int pgica_gemm_lse_rowcol_workspace_bytes(int64_t rows, int64_t cols, int64_t k, size_t* bytes_host);
+int pgica_gemm_lse_rowcol(const void* a, const void* b, int64_t rows, int64_t cols, int64_t k, float scale,
+                          const int32_t* labels, int64_t diag_offset, float* lse_row, float* tgt, float* lse_col,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* Dense scaled similarity sim[i][j] = scale*<a_i, b_j> (fp32 [rows][cols]) for retrieval-style scoring —
  * TemperatureScaledSimilarity.forward, pkg/models/components.py:61-83 after normalisation — plus the row
  * log-sum-exp.  Same kernel as pgica_gemm_lse with the store epilogue enabled; workspace as for gemm_lse. */
@@ -278,6 +290,11 @@ int pgica_ntxent_workspace_bytes(int64_t rows_a, int64_t rows_b, int64_t dim, si
 int pgica_ntxent_fwd(const void* a, const void* b, int64_t rows_a, int64_t rows_b, int64_t dim, float inv_tau,
                      int64_t diag_offset, float* lse_row, float* diag, float* lse_col_part, void* workspace,
                      size_t workspace_bytes, void* stream);
+/* The same from ONE pass over the similarity tiles (pgica_gemm_lse_rowcol) for callers that guarantee unit-norm rows
+ * (|<a_i, b_j>| <= 1); falls back to the two-pass form by itself when inv_tau is too large for the bounded scheme. */
+int pgica_ntxent_fwd_bounded(const void* a, const void* b, int64_t rows_a, int64_t rows_b, int64_t dim, float inv_tau,
+                             int64_t diag_offset, float* lse_row, float* diag, float* lse_col_part, void* workspace,
+                             size_t workspace_bytes, void* stream);
 int pgica_ntxent_bwd(const void* a, const void* b, int64_t rows_a, int64_t rows_b, int64_t dim, float inv_tau,
                      int64_t diag_offset, const float* lse_row, const float* lse_col, const float* grad_loss,
                      float grad_mult, void* da, int da_is_bf16, void* db, int db_is_bf16, void* workspace,

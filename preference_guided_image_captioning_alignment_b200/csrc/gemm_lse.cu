@@ -45,6 +45,13 @@ struct GemmLseParams {
   float* part_sum;  // [num_n_tiles][rows_pad]  sum of exp2(. - max)
   float* part_tgt;  // [num_n_tiles][rows_pad]  scale*z at the label column, -inf if it is not in this tile
   float* z_out;     // optional dense [rows][cols] copy of scale*z (similarity-matrix API only)
+  // optional COLUMN statistics from the same tiles (NT-Xent with bounded logits: S is computed once instead of twice).
+  // Every warp of the epilogue owns 32 rows; per 32-column chunk it publishes the column sums of exp2(t - shift) over
+  // its rows (col_sum[group][column]) and the shift it used (col_shift[group][tile * 8 + chunk] = the largest running
+  // row maximum among its rows).  col_merge_kernel folds the groups of a column.
+  float* col_sum;   // [rows_pad / 32][cols_pad]
+  float* col_shift; // [rows_pad / 32][num_n_tiles * 8]
+  int cols_pad;
 };
 
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tmap, uint32_t bar_cluster, int c0, int c1) {
@@ -71,6 +78,7 @@ __device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
 
 constexpr size_t kSmemBytes = 1024 /*align slack*/ + kStages * (kABytes + kBBytes) + 256 /*barriers*/;
 
+template <bool kCols>  // kCols: also publish the column statistics (a separate instantiation: the plain forward keeps its code)
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_lse_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                 const GemmLseParams p) {
@@ -228,10 +236,46 @@ gemm_lse_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const float m_new = fmaxf(run_m, cm * c);
         const float corr = fast_exp2(run_m - m_new);
         float s0 = 0.f, s1 = 0.f;
+        if (!kCols) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          s0 += fast_exp2(fmaf(v[j], c, -m_new));
-          s1 += fast_exp2(fmaf(v[j + 1], c, -m_new));
+          for (int j = 0; j < 32; j += 2) {
+            s0 += fast_exp2(fmaf(v[j], c, -m_new));
+            s1 += fast_exp2(fmaf(v[j + 1], c, -m_new));
+          }
+        } else {
+          // the same exponentials, kept: rescaled to the warp's common shift and summed DOWN the 32 rows of the warp
+          // (butterfly: 31 shuffles, lane l ends up with the sum of column l of the chunk)
+          float e[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            e[j] = fast_exp2(fmaf(v[j], c, -m_new));
+            e[j + 1] = fast_exp2(fmaf(v[j + 1], c, -m_new));
+            s0 += e[j];
+            s1 += e[j + 1];
+          }
+          const bool rvalid = row < p.rows;
+          float sh = rvalid ? m_new : -INFINITY;
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) sh = fmaxf(sh, __shfl_xor_sync(0xffffffffu, sh, o));
+          const float f = rvalid ? fast_exp2(m_new - sh) : 0.f;  // <= 1; rows past the end contribute nothing
+#pragma unroll
+          for (int j = 0; j < 32; ++j) e[j] *= f;
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) {
+            const bool upper = (lane & o) != 0;
+#pragma unroll
+            for (int kk = 0; kk < o; ++kk) {
+              const float send = upper ? e[kk] : e[kk + o];
+              const float keep = upper ? e[kk + o] : e[kk];
+              e[kk] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+          }
+          if (m_blk < p.num_m_blocks) {
+            const size_t g = static_cast<size_t>(m_blk) * 4 + quarter;
+            const int col = n0 + ch * 32 + lane;
+            if (col < p.cols) p.col_sum[g * p.cols_pad + col] = e[0];
+            if (lane == 0) p.col_shift[g * (static_cast<size_t>(p.num_n_tiles) * 8) + n_tile * 8 + ch] = sh;
+          }
         }
         run_s = fmaf(run_s, corr, s0 + s1);
         run_m = m_new;
@@ -312,6 +356,46 @@ lse_merge_kernel(const GemmLseParams p, float* __restrict__ lse, float* __restri
   }
 }
 
+// Fold the row groups of every column: lse_col[j] = ln sum_g col_sum[g][j] * exp2(shift[g][chunk(j)])  (log2 domain in).
+// One thread per column (loads coalesced across columns); groups that hold no valid row carry shift = -inf, sum = 0.
+__global__ void __launch_bounds__(512) col_merge_kernel(const GemmLseParams p, int groups, float* __restrict__ lse_col) {
+  // block = 32 columns x 16 group lanes: coalesced 128-byte reads of col_sum, the groups of a column folded by 16 threads
+  __shared__ float sm_m[16][33], sm_s[16][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
+  const size_t shift_pitch = static_cast<size_t>(p.num_n_tiles) * 8;
+  const int slot = blockIdx.x;  // 32 columns share a shift; kBlockN is a multiple of 32, so slot == j / 32 for every tile
+  float M = -INFINITY, S = 0.f;
+  if (j < p.cols) {
+#pragma unroll 4
+    for (int g = ty; g < groups; g += 16) {
+      const float sh = p.col_shift[g * shift_pitch + slot];
+      const float v = p.col_sum[static_cast<size_t>(g) * p.cols_pad + j];
+      if (sh > -INFINITY) {
+        if (sh > M) {
+          S = S * exp2f(M - sh) + v;
+          M = sh;
+        } else {
+          S += v * exp2f(sh - M);
+        }
+      }
+    }
+  }
+  sm_m[ty][tx] = M;
+  sm_s[ty][tx] = S;
+  __syncthreads();
+  if (ty == 0 && j < p.cols) {
+    float Mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) Mx = fmaxf(Mx, sm_m[t][tx]);
+    float Sx = 0.f;
+#pragma unroll
+    for (int t = 0; t < 16; ++t)
+      if (sm_m[t][tx] > -INFINITY) Sx += sm_s[t][tx] * exp2f(sm_m[t][tx] - Mx);
+    lse_col[j] = (Mx + log2f(Sx)) * kLn2;
+  }
+}
+
 int plan(int64_t rows, int64_t cols, int64_t k, GemmLseParams* p, int* grid, size_t* ws_bytes) {
   PGICA_REQUIRE(rows > 0 && cols > 0 && k > 0, "gemm_lse: empty problem (rows %lld cols %lld k %lld)", (long long)rows,
                 (long long)cols, (long long)k);
@@ -332,6 +416,13 @@ int plan(int64_t rows, int64_t cols, int64_t k, GemmLseParams* p, int* grid, siz
   return PGICA_OK;
 }
 
+size_t col_stats_bytes(const GemmLseParams& p, size_t* sum_bytes) {
+  const size_t groups = static_cast<size_t>(p.rows_pad) / 32;
+  const size_t cols_pad = align_up((size_t)p.cols, 32);
+  *sum_bytes = align_up(groups * cols_pad * sizeof(float), 256);
+  return *sum_bytes + align_up(groups * (size_t)p.num_n_tiles * 8 * sizeof(float), 256);
+}
+
 }  // namespace
 }  // namespace pgica
 
@@ -345,7 +436,7 @@ int pgica_gemm_lse_workspace_bytes(int64_t rows, int64_t cols, int64_t k, size_t
 
 static int gemm_lse_impl(const void* a, const void* b, int64_t rows, int64_t cols, int64_t k, float scale,
                          const int32_t* labels, int64_t diag_offset, float* lse, float* tgt, float* z_out,
-                         void* workspace, size_t workspace_bytes, void* stream) {
+                         void* workspace, size_t workspace_bytes, void* stream, float* lse_col = nullptr) {
   using namespace pgica;
   int rc = pgica_device_check();
   if (rc != PGICA_OK) return rc;
@@ -356,9 +447,16 @@ static int gemm_lse_impl(const void* a, const void* b, int64_t rows, int64_t col
   if (rc != PGICA_OK) return rc;
   PGICA_REQUIRE(a && b && lse, "gemm_lse: null operand");
   PGICA_REQUIRE(scale > 0.f && scale == scale, "gemm_lse: scale must be positive (got %g)", (double)scale);
-  if (workspace_bytes < need || !workspace) {
-    set_error("gemm_lse: workspace too small (%zu < %zu)", workspace_bytes, need);
+  size_t col_sum_bytes = 0;
+  const size_t col_bytes = lse_col ? col_stats_bytes(p, &col_sum_bytes) : 0;
+  if (workspace_bytes < need + col_bytes || !workspace) {
+    set_error("gemm_lse: workspace too small (%zu < %zu)", workspace_bytes, need + col_bytes);
     return PGICA_ERR_WORKSPACE_TOO_SMALL;
+  }
+  if (lse_col) {
+    p.col_sum = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + need);
+    p.col_shift = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + need + col_sum_bytes);
+    p.cols_pad = (int)align_up((size_t)cols, 32);
   }
   const size_t seg = need / 3;
   p.part_max = reinterpret_cast<float*>(workspace);
@@ -376,7 +474,8 @@ static int gemm_lse_impl(const void* a, const void* b, int64_t rows, int64_t col
   if (rc != PGICA_OK) return rc;
 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  PGICA_CUDA_OK(cudaFuncSetAttribute(gemm_lse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  auto kern = lse_col ? gemm_lse_kernel<true> : gemm_lse_kernel<false>;
+  PGICA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kThreads);
@@ -389,12 +488,37 @@ static int gemm_lse_impl(const void* a, const void* b, int64_t rows, int64_t col
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PGICA_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_lse_kernel, tm_a, tm_b, p));
+  PGICA_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tm_a, tm_b, p));
   count_launches(1);
   lse_merge_kernel<<<(unsigned)ceil_div(rows, kMergeRows), kMergeRows * kMergeGroups, 0, st>>>(p, lse, tgt);
   PGICA_CUDA_OK(cudaGetLastError());
   count_launches(1);
+  if (lse_col) {
+    col_merge_kernel<<<(unsigned)ceil_div(cols, 32), 512, 0, st>>>(p, p.rows_pad / 32, lse_col);
+    PGICA_CUDA_OK(cudaGetLastError());
+    count_launches(1);
+  }
   return PGICA_OK;
+}
+
+int pgica_gemm_lse_rowcol_workspace_bytes(int64_t rows, int64_t cols, int64_t k, size_t* bytes_host) {
+  pgica::GemmLseParams p{};
+  int grid = 0;
+  size_t need = 0;
+  int rc = pgica::plan(rows, cols, k, &p, &grid, &need);
+  if (rc != PGICA_OK) return rc;
+  PGICA_REQUIRE(bytes_host, "workspace query: null result pointer");
+  size_t sum_bytes = 0;
+  *bytes_host = need + pgica::col_stats_bytes(p, &sum_bytes);
+  return PGICA_OK;
+}
+
+int pgica_gemm_lse_rowcol(const void* a, const void* b, int64_t rows, int64_t cols, int64_t k, float scale,
+                          const int32_t* labels, int64_t diag_offset, float* lse_row, float* tgt, float* lse_col,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  PGICA_REQUIRE(lse_col, "gemm_lse_rowcol: null column output");
+  return gemm_lse_impl(a, b, rows, cols, k, scale, labels, diag_offset, lse_row, tgt, nullptr, workspace,
+                       workspace_bytes, stream, lse_col);
 }
 
 int pgica_gemm_lse(const void* a, const void* b, int64_t rows, int64_t cols, int64_t k, float scale,

@@ -132,7 +132,11 @@ int pgica_ntxent_workspace_bytes(int64_t rows_a, int64_t rows_b, int64_t dim, si
   if (rc != PGICA_OK) return rc;
   rc = pgica_gemm_lse_workspace_bytes(rows_b, rows_a, dim, &g2);
   if (rc != PGICA_OK) return rc;
-  const size_t fwd = g1 > g2 ? g1 : g2;
+  size_t g3 = 0;
+  rc = pgica_gemm_lse_rowcol_workspace_bytes(rows_a, rows_b, dim, &g3);
+  if (rc != PGICA_OK) return rc;
+  size_t fwd = g1 > g2 ? g1 : g2;
+  if (g3 > fwd) fwd = g3;
   size_t x = 0;
   rc = pgica_softmax_grad_gemm_workspace_bytes(rows_a, rows_b, dim, &x);
   if (rc != PGICA_OK) return rc;
@@ -154,6 +158,21 @@ int pgica_ntxent_fwd(const void* a, const void* b, int64_t rows_a, int64_t rows_
   if (rc != PGICA_OK) return rc;
   return pgica_gemm_lse(b, a, rows_b, rows_a, dim, inv_tau, nullptr, -diag_offset, lse_col_part, nullptr, workspace,
                         workspace_bytes, stream);
+}
+
+int pgica_ntxent_fwd_bounded(const void* a, const void* b, int64_t rows_a, int64_t rows_b, int64_t dim, float inv_tau,
+                             int64_t diag_offset, float* lse_row, float* diag, float* lse_col_part, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  // bounded scheme: |t| <= inv_tau * log2(e) for unit-norm rows; keep 2 * that well inside the fp32 exponent range
+  if (!(inv_tau * 1.4426950408889634f * 2.0f < 100.0f))
+    return pgica_ntxent_fwd(a, b, rows_a, rows_b, dim, inv_tau, diag_offset, lse_row, diag, lse_col_part, workspace,
+                            workspace_bytes, stream);
+  PGICA_REQUIRE(a && b && lse_row && diag && lse_col_part, "ntxent_fwd_bounded: null pointer");
+  PGICA_REQUIRE(diag_offset >= 0 && diag_offset + rows_a <= rows_b,
+                "ntxent_fwd_bounded: positives (i, i + %lld) fall outside the %lld columns", (long long)diag_offset,
+                (long long)rows_b);
+  return pgica_gemm_lse_rowcol(a, b, rows_a, rows_b, dim, inv_tau, nullptr, diag_offset, lse_row, diag, lse_col_part,
+                               workspace, workspace_bytes, stream);
 }
 
 int pgica_ntxent_bwd(const void* a, const void* b, int64_t rows_a, int64_t rows_b, int64_t dim, float inv_tau,

@@ -32,8 +32,13 @@ class CudaCompute:
     def to_operand(self, x):
         return F.as_bf16(x)
 
+    def __init__(self, assume_normalized: bool = False):
+        # unit-norm rows (what the reference model hands its loss, pkg/models/model.py:826-829): row and column
+        # log-sum-exp from one pass over the similarity tiles instead of two
+        self.assume_normalized = bool(assume_normalized)
+
     def ntxent_fwd(self, a, b_all, inv_tau, diag_offset):
-        return F.ntxent_fwd(a, b_all, inv_tau, diag_offset)
+        return F.ntxent_fwd(a, b_all, inv_tau, diag_offset, bounded=self.assume_normalized)
 
     def lse_combine(self, parts):
         return F.lse_combine(parts)
@@ -101,23 +106,27 @@ class _GlobalNTXent(torch.autograd.Function):
 
 
 def global_ntxent(a: torch.Tensor, b: torch.Tensor, temperature: float, reduce_mean: bool = True, group=None,
-                  compute=None) -> torch.Tensor:
+                  compute=None, assume_normalized: bool = False) -> torch.Tensor:
     """NT-Xent over the GLOBAL batch; a, b are this rank's (b, D) rows, used as given (normalise first if needed).
+    assume_normalized=True promises unit-norm rows and lets the forward make one pass instead of two.
     Returns the global loss (identical on every rank)."""
-    return _GlobalNTXent.apply(a, b, 1.0 / float(temperature), reduce_mean, group, compute or CudaCompute())
+    return _GlobalNTXent.apply(a, b, 1.0 / float(temperature), reduce_mean, group,
+                               compute or CudaCompute(assume_normalized))
 
 
 class GlobalContrastiveLoss(torch.nn.Module):
     """ContrastiveLoss (pkg/models/model.py:957-1000 semantics) with negatives from every rank."""
 
-    def __init__(self, temperature: float = 0.07, group=None, compute=None):
+    def __init__(self, temperature: float = 0.07, group=None, compute=None, assume_normalized: bool = False):
         super().__init__()
         self.temperature = temperature
         self.group = group
         self.compute = compute
+        self.assume_normalized = assume_normalized
 
     def forward(self, image_embeddings, text_embeddings):
-        return global_ntxent(image_embeddings, text_embeddings, self.temperature, True, self.group, self.compute)
+        return global_ntxent(image_embeddings, text_embeddings, self.temperature, True, self.group, self.compute,
+                             self.assume_normalized)
 
 
 # ------------------------------------------------------------------------------------------------ DPO

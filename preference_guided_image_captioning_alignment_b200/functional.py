@@ -228,7 +228,10 @@ def dpo_grad_seq(dpc, grad_loss):
 
 
 # ----------------------------------------------------------------------------------------- Stage-1 head
-def ntxent_fwd(a, b, inv_tau, diag_offset=0):
+def ntxent_fwd(a, b, inv_tau, diag_offset=0, bounded=False):
+    """Row LSE, diagonal and column-LSE (partial) of the (rows_a x rows_b) similarity slice.  bounded=True: the caller
+    guarantees unit-norm rows (|<a_i, b_j>| <= 1) — both LSEs then come from ONE pass over the tiles
+    (pgica_ntxent_fwd_bounded) instead of two."""
     _need_cuda(a, b)
     lib = _lib.load()
     ra, dim = a.shape
@@ -238,8 +241,9 @@ def ntxent_fwd(a, b, inv_tau, diag_offset=0):
     ws = _ws(need.value, a.device)
     f32 = dict(dtype=torch.float32, device=a.device)
     lse_row, diag, lse_col = torch.empty(ra, **f32), torch.empty(ra, **f32), torch.empty(rb, **f32)
-    _lib.check(lib.pgica_ntxent_fwd(_p(a), _p(b), ra, rb, dim, float(inv_tau), int(diag_offset), _p(lse_row),
-                                    _p(diag), _p(lse_col), _p(ws), need.value, _stream()))
+    fn = lib.pgica_ntxent_fwd_bounded if bounded else lib.pgica_ntxent_fwd
+    _lib.check(fn(_p(a), _p(b), ra, rb, dim, float(inv_tau), int(diag_offset), _p(lse_row), _p(diag), _p(lse_col), _p(ws),
+                  need.value, _stream()))
     return lse_row, diag, lse_col
 
 

@@ -164,8 +164,8 @@ def ntxent_cosine(x: Tensor, y: Tensor, inv_tau: float, reduce_mean: bool,
         raise ValueError(f"ntxent_cosine expects two (B, D) tensors of equal shape, got {tuple(x.shape)} {tuple(y.shape)}")
     _, inv_x, _, xl, xr = F.rownorm_fwd(x, eps, split=True)
     _, inv_y, _, yl, yr = F.rownorm_fwd(y, eps, split=True)
-    lse_row, diag = F.gemm_lse(xl, yr, inv_tau, None, 0)
-    lse_col, _ = F.gemm_lse(yl, xr, inv_tau, None, 0, want_tgt=False)
+    # the rows were normalised right here: logits are bounded by inv_tau, so one pass gives both log-sum-exps
+    lse_row, diag, lse_col = F.ntxent_fwd(xl, yr, inv_tau, 0, bounded=True)
     n = x.shape[0]
     loss = F.ntxent_loss(lse_row, diag, lse_col, 1.0 / n if reduce_mean else 1.0)
     return loss, lse_row, lse_col, xl, xr, yl, yr, inv_x, inv_y

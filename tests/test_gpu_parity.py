@@ -1367,3 +1367,26 @@ def test_grad_norm_clip_odd_layouts(pg, cuda_device):
     assert finite and abs(total.item() - norm_ref.item()) <= 1e-4 * norm_ref.item()
     for p, r in zip(ps, ref):
         assert rel(p.grad.float(), r.grad.float()) < 2e-3
+
+
+@pytest.mark.parametrize("ra,rb,D,tau,off", [(64, 64, 512, 0.5, 0), (300, 1000, 256, 0.07, 200), (4096, 4096, 512, 0.5, 0),
+                                             (1000, 3001, 128, 0.1, 1500), (4096, 32768, 512, 0.5, 8192)])
+def test_ntxent_forward_one_pass_matches_two_pass(pg, cuda_device, ra, rb, D, tau, off):
+    """Row and column log-sum-exp from ONE pass over the similarity tiles (unit-norm rows: bounded logits) against the
+    exact two-pass forward and fp64 torch; ragged shapes, a diagonal offset (one rank's slice), tau down to 0.07; with
+    tau too small for the bounded scheme the call falls back to the two-pass form by itself."""
+    from preference_guided_image_captioning_alignment_b200 import functional as F
+    g = torch.Generator().manual_seed(ra + rb)
+    b = torch.nn.functional.normalize(torch.randn(rb, D, generator=g), dim=-1).bfloat16().to(cuda_device)
+    a = torch.nn.functional.normalize(b[off:off + ra].float().cpu() + 0.7 * torch.randn(ra, D, generator=g), dim=-1) \
+        .bfloat16().to(cuda_device)
+    lr2, dg2, lc2 = F.ntxent_fwd(a, b, 1.0 / tau, off)
+    lr1, dg1, lc1 = F.ntxent_fwd(a, b, 1.0 / tau, off, bounded=True)
+    assert torch.equal(lr1, lr2) and torch.equal(dg1, dg2)          # the row side is the same arithmetic
+    assert rel(lc1, lc2) < 2e-6 and float((lc1 - lc2).abs().max()) < 2e-5 * max(1.0, 1.0 / tau)
+    if ra * rb <= 5_000_000:
+        S = a.double() @ b.double().T / tau
+        assert rel(lc1, torch.logsumexp(S, 0)) < 1e-6 and rel(lr1, torch.logsumexp(S, 1)) < 1e-6
+    lr3, _, lc3 = F.ntxent_fwd(a, b, 1.0 / 0.01, off, bounded=True)   # 2 * 144 binades: exact path taken
+    lr4, _, lc4 = F.ntxent_fwd(a, b, 1.0 / 0.01, off)
+    assert torch.equal(lc3, lc4) and torch.equal(lr3, lr4)
