@@ -56,7 +56,9 @@ constexpr uint32_t kCStageBytes = 4 * kBox64Bytes;    // holder ring slot: 64 op
 constexpr int kCRing = 4;
 constexpr uint32_t kDrainBytes = 32768;                // holder: 4 drain warps x two 4 KB TMA-store buffers
 constexpr int kStagesPerTile = kBT / 64;              // 2
-constexpr int kThreads = 256;
+constexpr int kEpiThreads = 256;                      // producer epilogue: 8 warps, two per scheduler (a lone warp issues ~0.3 instructions
+                                                      // per cycle on dependent FFMA / MUFU chains — ncu stall samples, profiles/)
+constexpr int kThreads = 128 + kEpiThreads;
 constexpr float kLog2e = 1.4426950408889634f;
 // No slack for aligning the dynamic window by hand: the array is declared __align__(1024) (checked on the device),
 // which keeps 1.5 KB of the SM's 228 KB free — enough for the 1 KB the hardware reserves per resident CTA, so that a
@@ -407,9 +409,9 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&zfull_bar[i], 1);
-        mbar_init(&zempty_bar[i], 256);
+        mbar_init(&zempty_bar[i], 2 * kEpiThreads);
       }
-      mbar_init(stfull_bar, 128);
+      mbar_init(stfull_bar, kEpiThreads);
       mbar_init(stfree_bar, 1);
       fence_mbar_init();
     }
@@ -527,13 +529,15 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
       });
       LAP(0);
       if (lane == 0) LAP_FLUSH(6, 4);
-    } else if (warp >= 4 && warp < 8) {
+    } else if (warp >= 4) {
       // ---------------------------------------------------------------- epilogue: this CTA's Z rows -> two G tiles
-      const int quarter = warp & 3;
+      // Eight warps: warp w reads the TMEM lanes of quarter w & 3 (the hardware's lane window of a warp) and, of every
+      // 128-column tile, the 64 columns of its group (w - 4) >> 2 — one [128][64] box of the staging tile each.
+      const int quarter = warp & 3, wg = (warp - 4) >> 2;
       const int et = threadIdx.x - 128;
       const int row_in_blk = quarter * 32 + lane;
       const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-      const uint32_t g_local = smem_u32(staging);
+      const uint32_t g_local = smem_u32(staging) + (uint32_t)wg * kChunkBytes;
       uint32_t n = 0, ntile = 0;
       LAP_DECL;
       for_each_own_quad(p, pp, p.nP, [&](int q, int r0, int r, int c0, int c) {
@@ -553,23 +557,26 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
         for (int half = 0; half < 2; ++half) {
           const int col0 = (2 * (c0 + c) + half) * kBT;
           if (kCol) {
-            const int col = col0 + et;
-            float l = 0.f, cf = 0.f;
-            int tg = -1;
-            if (col < p.my) {
-              l = p.c_lse[col] * kLog2e;
-              cf = p.c_coef[col];
-              tg = p.c_tgt ? p.c_tgt[col] : -1;
+            if (et < kBT) {
+              const int col = col0 + et;
+              float l = 0.f, cf = 0.f;
+              int tg = -1;
+              if (col < p.my) {
+                l = p.c_lse[col] * kLog2e;
+                cf = p.c_coef[col];
+                tg = p.c_tgt ? p.c_tgt[col] : -1;
+              }
+              s_cl[et] = l;
+              s_cc[et] = cf;
+              s_ct[et] = tg;
             }
-            s_cl[et] = l;
-            s_cc[et] = cf;
-            s_ct[et] = tg;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
           }
           const int rrel = rt - col0;
-          uint32_t gp[kBT / 2];
+          uint32_t gp[kBT / 4];
 #pragma unroll
-          for (int ch = 0; ch < kBT / 32; ++ch) {
+          for (int cl = 0; cl < 2; ++cl) {
+            const int ch = wg * 2 + cl;  // 32-column chunk of the tile
             uint32_t rr[32];
             tmem_ld_32x32(tmem_base + lane_addr + buf * 256u + half * kBT + ch * 32, rr);
             tmem_ld_wait();
@@ -594,29 +601,28 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
                 if (jj == jj0) g[jj] -= rc;
             }
 #pragma unroll
-            for (int i = 0; i < 16; ++i) gp[ch * 16 + i] = pack_bf16x2(g[2 * i], g[2 * i + 1]);
+            for (int i = 0; i < 16; ++i) gp[cl * 16 + i] = pack_bf16x2(g[2 * i], g[2 * i + 1]);
           }
           if (half == 1) {
             tc_fence_before_sync();
-            mbar_arrive_cluster(&zempty_bar[buf], 0);  // tell the leader: this CTA has read the Z buffer
+            mbar_arrive_cluster(&zempty_bar[buf], 0);  // tell the leader: this thread has read the Z buffer
           }
           LAP(2);
           mbar_wait(stfree_bar, (ntile & 1u) ^ 1u);  // the exchange warp's TMA store has read the previous tile
           LAP(3);
 #pragma unroll
-          for (int ch = 0; ch < kBT / 32; ++ch) {
-            const uint32_t chunk_off = (ch >> 1) * kChunkBytes;
+          for (int cl = 0; cl < 2; ++cl) {
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
-              const uint32_t off = chunk_off + sw128_offset(row_in_blk, (ch & 1) * 4 + c4);
-              st_smem_v4(g_local + off, gp[ch * 16 + c4 * 4 + 0], gp[ch * 16 + c4 * 4 + 1], gp[ch * 16 + c4 * 4 + 2],
-                         gp[ch * 16 + c4 * 4 + 3]);
+              const uint32_t off = sw128_offset(row_in_blk, cl * 4 + c4);
+              st_smem_v4(g_local + off, gp[cl * 16 + c4 * 4 + 0], gp[cl * 16 + c4 * 4 + 1], gp[cl * 16 + c4 * 4 + 2],
+                         gp[cl * 16 + c4 * 4 + 3]);
             }
           }
           fence_proxy_async_smem();
           mbar_arrive(stfull_bar);
           ++ntile;
-          if (kCol) asm volatile("bar.sync 3, 128;" ::: "memory");  // the column statistics may be overwritten
+          if (kCol) asm volatile("bar.sync 3, 256;" ::: "memory");  // the column statistics may be overwritten
           LAP(4);
         }
         ++n;
