@@ -514,7 +514,7 @@ def run_ours(args, rank, world, local_rank):
             loss = F.ntxent_loss(lse_row, diag, lse_col[off:off + bl].contiguous(), 1.0 / Bg)
             dist.all_reduce(loss)
             ev[3].record()
-            da, db_part = F.ntxent_bwd(a_op, b_all, 2.0, off, lse_row, lse_col, one, 1.0 / (2.0 * Bg))
+            da, db_part = F.ntxent_bwd(a_op, b_all, 2.0, off, lse_row, lse_col, one, 1.0 / (2.0 * Bg), bounded=True)
             ev[4].record()
             D.reduce_scatter_rows(db_part)
             ev[5].record()
@@ -828,7 +828,7 @@ def ntxent_extras(torch, F, dev):
                 return F.ntxent_small(a, b, 2.0, True)[0]
             lr, dg, lc = F.ntxent_fwd(a, b, 2.0, bounded=True)  # unit-norm rows: one pass for both log-sum-exps
             loss = F.ntxent_loss(lr, dg, lc, 1.0 / B)
-            F.ntxent_bwd(a, b, 2.0, 0, lr, lc, one, 1.0 / (2 * B))
+            F.ntxent_bwd(a, b, 2.0, 0, lr, lc, one, 1.0 / (2 * B), bounded=True)
             return loss
 
         for _ in range(3):

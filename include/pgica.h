@@ -299,6 +299,12 @@ int pgica_ntxent_bwd(const void* a, const void* b, int64_t rows_a, int64_t rows_
                      int64_t diag_offset, const float* lse_row, const float* lse_col, const float* grad_loss,
                      float grad_mult, void* da, int da_is_bf16, void* db, int db_is_bf16, void* workspace,
                      size_t workspace_bytes, void* stream);
+/* The same for unit-norm rows: the dual backward kernel then takes ONE exponential per element for both softmax terms
+ * (2^(z c - c) times a per-row and a per-column factor); falls back like pgica_ntxent_fwd_bounded. */
+int pgica_ntxent_bwd_bounded(const void* a, const void* b, int64_t rows_a, int64_t rows_b, int64_t dim, float inv_tau,
+                             int64_t diag_offset, const float* lse_row, const float* lse_col, const float* grad_loss,
+                             float grad_mult, void* da, int da_is_bf16, void* db, int db_is_bf16, void* workspace,
+                             size_t workspace_bytes, void* stream);
 /* loss = 0.5 * inv_denom * sum_i [(lse_row[i]-diag[i]) + (lse_col_owned[i]-diag[i])]   (model.py:994-998) */
 int pgica_ntxent_loss(const float* lse_row, const float* diag, const float* lse_col_owned, int64_t n,
                       float inv_denom, float* loss, void* stream);

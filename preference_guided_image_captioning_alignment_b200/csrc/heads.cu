@@ -11,6 +11,11 @@ namespace pgica {
 bool sggf_supported(int64_t mx, int64_t my, int64_t k);  // sgg_f.cu
 bool sggf_single_chunk(int64_t mx, int64_t my, int64_t k);
 size_t sggf_workspace_bytes();
+int sggf_dispatch(const void* x, const void* y, int64_t mx, int64_t my, int64_t k, float scale, const float* r_lse,
+                  const float* r_coef, const int32_t* r_tgt, const float* c_lse, const float* c_coef,
+                  const int32_t* c_tgt, void* out_x, int out_x_is_bf16, void* out_y, int out_y_is_bf16,
+                  void* workspace, size_t workspace_bytes, cudaStream_t st, uint32_t* progress,
+                  int64_t rows_per_segment, bool shared_exponential);
 }  // namespace pgica
 extern "C" {
 
@@ -175,10 +180,10 @@ int pgica_ntxent_fwd_bounded(const void* a, const void* b, int64_t rows_a, int64
                                workspace, workspace_bytes, stream);
 }
 
-int pgica_ntxent_bwd(const void* a, const void* b, int64_t rows_a, int64_t rows_b, int64_t dim, float inv_tau,
-                     int64_t diag_offset, const float* lse_row, const float* lse_col, const float* grad_loss,
-                     float grad_mult, void* da, int da_is_bf16, void* db, int db_is_bf16, void* workspace,
-                     size_t workspace_bytes, void* stream) {
+static int ntxent_bwd_impl(const void* a, const void* b, int64_t rows_a, int64_t rows_b, int64_t dim, float inv_tau,
+                           int64_t diag_offset, const float* lse_row, const float* lse_col, const float* grad_loss,
+                           float grad_mult, void* da, int da_is_bf16, void* db, int db_is_bf16, void* workspace,
+                           size_t workspace_bytes, void* stream, bool bounded) {
   PGICA_REQUIRE(a && b && lse_row && lse_col && grad_loss, "ntxent_bwd: null pointer");
   PGICA_REQUIRE(da || db, "ntxent_bwd: nothing to compute");
   const size_t sa = align_up((size_t)rows_a * 4, 256), sb = align_up((size_t)rows_b * 4, 256);
@@ -199,14 +204,17 @@ int pgica_ntxent_bwd(const void* a, const void* b, int64_t rows_a, int64_t rows_
   if (rc != PGICA_OK) return rc;
   rc = pgica_ntxent_coef(grad_loss, grad_mult * inv_tau, rows_b, -diag_offset, rows_a, ccoef, ctgt, stream);
   if (rc != PGICA_OK) return rc;
-  // The dual kernel wins while A fits one chunk of X-holders (B200: 102 vs 156 us at 4096 x 4096, 592 vs 807 us at
-  // 4096 x 32768 = cfg3 per GPU); with three chunks (16384 x 16384) its producers, which pay two exponentials per
-  // element here, fall behind the two single-product launches (1.26 vs 1.06 ms): tools/ntxent_check.py.
   if (da && db && sggf_supported(rows_a, rows_b, dim) && xws_bytes >= sggf_workspace_bytes() &&
-      (!db_is_bf16 || sggf_single_chunk(rows_a, rows_b, dim)))
-    // dA and dB from one recomputation of the similarity tiles (sgg_f.cu)
+      (!db_is_bf16 || sggf_single_chunk(rows_a, rows_b, dim))) {
+    // dA and dB from one recomputation of the similarity tiles (sgg_f.cu).  Unit-norm rows: |logit| <= inv_tau, and the
+    // column targets built above mirror the row targets, so ONE exponential per element serves both softmax terms.
+    if (bounded)
+      return sggf_dispatch(a, b, rows_a, rows_b, dim, inv_tau, lse_row, rcoef, rtgt, lse_col, ccoef, ctgt, da,
+                           da_is_bf16, db, db_is_bf16, xws, xws_bytes, static_cast<cudaStream_t>(stream), nullptr, 0,
+                           true);
     return pgica_softmax_grad_gemm_dual(a, b, rows_a, rows_b, dim, inv_tau, lse_row, rcoef, rtgt, lse_col, ccoef, ctgt,
                                         da, da_is_bf16, db, db_is_bf16, xws, xws_bytes, stream);
+  }
   if (da) {
     rc = pgica_softmax_grad_gemm(a, b, rows_a, rows_b, dim, inv_tau, lse_row, rcoef, rtgt, lse_col, ccoef, ctgt, da,
                                  da_is_bf16, xws, xws_bytes, stream);
@@ -218,6 +226,24 @@ int pgica_ntxent_bwd(const void* a, const void* b, int64_t rows_a, int64_t rows_
     if (rc != PGICA_OK) return rc;
   }
   return PGICA_OK;
+}
+
+int pgica_ntxent_bwd(const void* a, const void* b, int64_t rows_a, int64_t rows_b, int64_t dim, float inv_tau,
+                     int64_t diag_offset, const float* lse_row, const float* lse_col, const float* grad_loss,
+                     float grad_mult, void* da, int da_is_bf16, void* db, int db_is_bf16, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  return ntxent_bwd_impl(a, b, rows_a, rows_b, dim, inv_tau, diag_offset, lse_row, lse_col, grad_loss, grad_mult, da,
+                         da_is_bf16, db, db_is_bf16, workspace, workspace_bytes, stream, false);
+}
+
+int pgica_ntxent_bwd_bounded(const void* a, const void* b, int64_t rows_a, int64_t rows_b, int64_t dim, float inv_tau,
+                             int64_t diag_offset, const float* lse_row, const float* lse_col, const float* grad_loss,
+                             float grad_mult, void* da, int da_is_bf16, void* db, int db_is_bf16, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  // same bound as pgica_ntxent_fwd_bounded; a temperature too small for it takes the two-exponential form
+  const bool ok = inv_tau > 0.f && inv_tau * 1.4426950408889634f * 2.0f < 100.0f;
+  return ntxent_bwd_impl(a, b, rows_a, rows_b, dim, inv_tau, diag_offset, lse_row, lse_col, grad_loss, grad_mult, da,
+                         da_is_bf16, db, db_is_bf16, workspace, workspace_bytes, stream, ok);
 }
 
 }  // extern "C"

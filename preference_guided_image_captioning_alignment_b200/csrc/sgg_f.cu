@@ -351,7 +351,11 @@ __host__ __device__ __forceinline__ void for_each_holder_tile(const SggfParams& 
   }
 }
 
-template <bool kRow, bool kCol>
+// kShared (both terms only): the caller guarantees |logit| <= scale (unit-norm rows) and column targets that mirror the
+// row targets (NT-Xent).  One exponential e = 2^(z c - c) then serves both softmax terms, P_row = e 2^(c - lse_row) and
+// P_col = e 2^(c - lse_col), each factor finite in fp32 because 2 c < 100; and the two one-hots fall on the same
+// element, handled outside the inner loop.
+template <bool kRow, bool kCol, bool kShared = false>
 __global__ void __launch_bounds__(kThreads, 1)
 sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__ CUtensorMap tm_y128,
             const __grid_constant__ CUtensorMap tm_x64, const __grid_constant__ CUtensorMap tm_y64,
@@ -549,6 +553,7 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
           rc = p.r_coef[row];
           rt = p.r_tgt ? p.r_tgt[row] : -1;
         }
+        const float rs = kShared ? rc * fast_exp2(p.c - rl) : 0.f;  // the row's factor of the shared exponential
         const uint32_t buf = n & 1u;
         LAP(0);
         mbar_wait(&zfull_bar[buf], (n >> 1) & 1u);
@@ -566,8 +571,8 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
                 cf = p.c_coef[col];
                 tg = p.c_tgt ? p.c_tgt[col] : -1;
               }
-              s_cl[et] = l;
-              s_cc[et] = cf;
+              s_cl[et] = kShared ? cf : l;                            // shared: the raw coefficient (one-hot fix-up)
+              s_cc[et] = kShared ? cf * fast_exp2(p.c - l) : cf;      //         the column's factor
               s_ct[et] = tg;
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -583,6 +588,10 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
             float g[32];
 #pragma unroll
             for (int jj = 0; jj < 32; ++jj) {
+              if (kShared) {
+                g[jj] = fast_exp2(fmaf(__uint_as_float(rr[jj]), p.c, -p.c)) * (rs + s_cc[ch * 32 + jj]);
+                continue;
+              }
               const float tz = __uint_as_float(rr[jj]) * p.c;
               float v = 0.f;
               if (kRow) v = rc * fast_exp2(tz - rl);
@@ -596,9 +605,10 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
             }
             if (kRow && rrel >= 0 && (rrel >> 5) == ch) {
               const int jj0 = rrel & 31;
+              const float hot = kShared ? rc + s_cl[ch * 32 + jj0] : rc;  // mirrored targets: both one-hots sit here
 #pragma unroll
               for (int jj = 0; jj < 32; ++jj)
-                if (jj == jj0) g[jj] -= rc;
+                if (jj == jj0) g[jj] -= hot;
             }
 #pragma unroll
             for (int i = 0; i < 16; ++i) gp[cl * 16 + i] = pack_bf16x2(g[2 * i], g[2 * i + 1]);
@@ -978,7 +988,7 @@ int plan_override(Plan* pl, int npairs, int S) {
 
 constexpr int kSlotsPerProducer = 4;  // double slots (two G tiles each) per producer CTA
 
-template <bool kRow, bool kCol>
+template <bool kRow, bool kCol, bool kShared = false>
 int resident_pairs(int* out) {
   // the shared-memory opt-in is a per-device attribute of the function, the occupancy a per-device number
   static int cached[64] = {0};
@@ -988,7 +998,7 @@ int resident_pairs(int* out) {
   PGICA_REQUIRE(dev >= 0 && dev < 64, "softmax_grad_gemm_dual: device ordinal %d out of range", dev);
   std::lock_guard<std::mutex> lock(mu);
   if (cached[dev] == 0) {
-    auto kern = sggf_kernel<kRow, kCol>;
+    auto kern = sggf_kernel<kRow, kCol, kShared>;
     PGICA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * 64);
@@ -1013,11 +1023,11 @@ int resident_pairs(int* out) {
   return PGICA_OK;
 }
 
-template <bool kRow, bool kCol>
+template <bool kRow, bool kCol, bool kShared = false>
 int launch(const CUtensorMap& tm_x128, const CUtensorMap& tm_y128, const CUtensorMap& tm_x64,
            const CUtensorMap& tm_y64, const CUtensorMap& tm_s, const CUtensorMap& tm_ox, const CUtensorMap& tm_oy,
            const SggfParams& p, cudaStream_t st) {
-  auto kern = sggf_kernel<kRow, kCol>;
+  auto kern = sggf_kernel<kRow, kCol, kShared>;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(2 * (p.nH + p.nW + p.nP)));
   cfg.blockDim = dim3(kThreads);
@@ -1053,11 +1063,11 @@ struct ProgressSpec {
   int64_t rows_per_segment = 0;  // multiple of 256 (a column pair)
 };
 
-template <bool kRow, bool kCol>
+template <bool kRow, bool kCol, bool kShared = false>
 int plan_and_launch(const void* x, const void* y, int64_t mx, int64_t my, int64_t k, SggfParams p, void* workspace,
                     size_t workspace_bytes, const ProgressSpec& pg, cudaStream_t st) {
   int npairs = 0;
-  int rc = resident_pairs<kRow, kCol>(&npairs);
+  int rc = resident_pairs<kRow, kCol, kShared>(&npairs);
   if (rc != PGICA_OK) return rc;
   const int S = p.S;
   // a bf16 OutY cannot be accumulated over chunks: all of X must then fit one chunk of X-holders.  One chunk is also
@@ -1133,7 +1143,7 @@ int plan_and_launch(const void* x, const void* y, int64_t mx, int64_t my, int64_
   if (rc != PGICA_OK) return rc;
   rc = p.outy_bf16 ? make_tmap_bf16(&tm_oy, p.out_y, my, k, k, 32) : make_tmap_f32(&tm_oy, p.out_y, my, k, k, 32);
   if (rc != PGICA_OK) return rc;
-  return launch<kRow, kCol>(tm_x128, tm_y128, tm_x64, tm_y64, tm_s, tm_ox, tm_oy, p, st);
+  return launch<kRow, kCol, kShared>(tm_x128, tm_y128, tm_x64, tm_y64, tm_s, tm_ox, tm_oy, p, st);
 }
 
 }  // namespace
@@ -1225,7 +1235,7 @@ int sggf_dispatch(const void* x, const void* y, int64_t mx, int64_t my, int64_t 
                   const float* r_coef, const int32_t* r_tgt, const float* c_lse, const float* c_coef,
                   const int32_t* c_tgt, void* out_x, int out_x_is_bf16, void* out_y, int out_y_is_bf16,
                   void* workspace, size_t workspace_bytes, cudaStream_t st, uint32_t* progress = nullptr,
-                  int64_t rows_per_segment = 0) {
+                  int64_t rows_per_segment = 0, bool shared_exponential = false) {
   PGICA_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0,
                 "softmax_grad_gemm_dual: workspace missing or not 256-byte aligned");
   ProgressSpec sc;
@@ -1252,6 +1262,11 @@ int sggf_dispatch(const void* x, const void* y, int64_t mx, int64_t my, int64_t 
   p.out_x = out_x;
   p.out_y = out_y;
   const bool row = r_lse != nullptr, col = c_lse != nullptr;
+  if (shared_exponential) {
+    // see sggf_kernel: |logit| <= scale, 2 scale log2(e) < 100, mirrored targets — promised by the caller (heads.cu)
+    PGICA_REQUIRE(row && col && r_tgt && c_tgt && 2.f * p.c < 100.f, "softmax_grad_gemm_dual: shared exponential misused");
+    return plan_and_launch<true, true, true>(x, y, mx, my, k, p, workspace, workspace_bytes, sc, st);
+  }
   if (row && col) return plan_and_launch<true, true>(x, y, mx, my, k, p, workspace, workspace_bytes, sc, st);
   if (row) return plan_and_launch<true, false>(x, y, mx, my, k, p, workspace, workspace_bytes, sc, st);
   return plan_and_launch<false, true>(x, y, mx, my, k, p, workspace, workspace_bytes, sc, st);

@@ -34,7 +34,7 @@ class CudaCompute:
 
     def __init__(self, assume_normalized: bool = False):
         # unit-norm rows (what the reference model hands its loss, pkg/models/model.py:826-829): row and column
-        # log-sum-exp from one pass over the similarity tiles instead of two
+        # log-sum-exp from one pass over the similarity tiles instead of two, one exponential per element in the backward
         self.assume_normalized = bool(assume_normalized)
 
     def ntxent_fwd(self, a, b_all, inv_tau, diag_offset):
@@ -48,7 +48,7 @@ class CudaCompute:
 
     def ntxent_bwd(self, a, b_all, inv_tau, diag_offset, lse_row, lse_col, grad_loss, mult):
         return F.ntxent_bwd(a, b_all, inv_tau, diag_offset, lse_row, lse_col, grad_loss, mult,
-                            da_dtype=torch.float32, db_dtype=torch.float32)
+                            da_dtype=torch.float32, db_dtype=torch.float32, bounded=self.assume_normalized)
 
 
 def _world(group):

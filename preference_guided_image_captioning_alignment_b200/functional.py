@@ -265,7 +265,8 @@ def lse_combine(parts):
 
 
 def ntxent_bwd(a, b, inv_tau, diag_offset, lse_row, lse_col, grad_loss, grad_mult, need_da=True, need_db=True,
-               da_dtype=torch.float32, db_dtype=torch.float32):
+               da_dtype=torch.float32, db_dtype=torch.float32, bounded=False):
+    """bounded=True: unit-norm rows promised (as in ntxent_fwd) — one exponential per element instead of two."""
     _need_cuda(a, b, grad_loss)
     lib = _lib.load()
     ra, dim = a.shape
@@ -276,10 +277,10 @@ def ntxent_bwd(a, b, inv_tau, diag_offset, lse_row, lse_col, grad_loss, grad_mul
     da = torch.empty(ra, dim, dtype=da_dtype, device=a.device) if need_da else None
     db = torch.empty(rb, dim, dtype=db_dtype, device=a.device) if need_db else None
     grad_loss = grad_loss.reshape(1).float().contiguous()
-    _lib.check(lib.pgica_ntxent_bwd(_p(a), _p(b), ra, rb, dim, float(inv_tau), int(diag_offset), _p(lse_row),
-                                    _p(lse_col), _p(grad_loss), float(grad_mult), _p(da),
-                                    1 if da_dtype == torch.bfloat16 else 0, _p(db),
-                                    1 if db_dtype == torch.bfloat16 else 0, _p(ws), need.value, _stream()))
+    fn = lib.pgica_ntxent_bwd_bounded if bounded else lib.pgica_ntxent_bwd
+    _lib.check(fn(_p(a), _p(b), ra, rb, dim, float(inv_tau), int(diag_offset), _p(lse_row), _p(lse_col), _p(grad_loss),
+                  float(grad_mult), _p(da), 1 if da_dtype == torch.bfloat16 else 0, _p(db),
+                  1 if db_dtype == torch.bfloat16 else 0, _p(ws), need.value, _stream()))
     return da, db
 
 

@@ -1390,3 +1390,37 @@ def test_ntxent_forward_one_pass_matches_two_pass(pg, cuda_device, ra, rb, D, ta
     lr3, _, lc3 = F.ntxent_fwd(a, b, 1.0 / 0.01, off, bounded=True)   # 2 * 144 binades: exact path taken
     lr4, _, lc4 = F.ntxent_fwd(a, b, 1.0 / 0.01, off)
     assert torch.equal(lc3, lc4) and torch.equal(lr3, lr4)
+
+
+@pytest.mark.parametrize("ra,rb,D,tau,off", [(256, 256, 512, 0.5, 0), (300, 1000, 512, 0.07, 200), (4096, 4096, 512, 0.5, 0),
+                                             (1000, 3001, 512, 0.1, 1500), (4096, 32768, 512, 0.5, 8192)])
+def test_ntxent_backward_one_exponential_matches_two(pg, cuda_device, ra, rb, D, tau, off):
+    """Unit-norm rows: the backward with one shared exponential per element (bounded) against the two-exponential form
+    and, where the similarity matrix fits, fp64 torch autograd; ragged shapes, diagonal offsets, tau down to 0.07; a
+    temperature outside the bound takes the exact path."""
+    from preference_guided_image_captioning_alignment_b200 import functional as F
+    g = torch.Generator().manual_seed(ra * 3 + rb)
+    b = torch.nn.functional.normalize(torch.randn(rb, D, generator=g), dim=-1).bfloat16().to(cuda_device)
+    a = torch.nn.functional.normalize(b[off:off + ra].float().cpu() + 0.7 * torch.randn(ra, D, generator=g), dim=-1) \
+        .bfloat16().to(cuda_device)
+    lr, dg, lc = F.ntxent_fwd(a, b, 1.0 / tau, off, bounded=True)
+    gl = torch.full((1,), 1.7, device=cuda_device)
+    mult = 0.5 / rb
+    da2, db2 = F.ntxent_bwd(a, b, 1.0 / tau, off, lr, lc, gl, mult)
+    da1, db1 = F.ntxent_bwd(a, b, 1.0 / tau, off, lr, lc, gl, mult, bounded=True)
+    assert rel(da1, da2) < 2e-3 and rel(db1, db2) < 2e-3
+    if ra * rb <= 5_000_000:
+        A, B = a.double().requires_grad_(), b.double().requires_grad_()
+        S = A @ B.T / tau
+        idx = torch.arange(ra, device=cuda_device)
+        # the full column log-sum-exp is what lc holds here (one rank: rows_a may be fewer than rows_b, then the column
+        # term of the missing rows is simply absent, exactly as in the two-exponential kernel)
+        loss = (torch.logsumexp(S, 1) - S[idx, idx + off]).sum() + (torch.logsumexp(S, 0)[off:off + ra] - S[idx, idx + off]).sum()
+        if ra == rb:
+            (loss * 1.7 * mult).backward()
+            assert rel(da1, A.grad) < 5e-3 and rel(db1, B.grad) < 5e-3
+    lr9, _, lc9 = F.ntxent_fwd(a, b, 100.0, off)
+    da3, db3 = F.ntxent_bwd(a, b, 100.0, off, lr9, lc9, gl, mult, bounded=True)  # 2 * 144 binades: two-exponential path
+    da4, db4 = F.ntxent_bwd(a, b, 100.0, off, lr9, lc9, gl, mult)
+    # (dA of a few-row problem is add-reduced over column groups in arrival order: equal to rounding, not bit for bit)
+    assert rel(da3, da4) < 1e-6 and torch.equal(db3, db4) and bool(torch.isfinite(da3).all())
