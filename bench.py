@@ -281,7 +281,8 @@ def run_ours(args, rank, world, local_rank):
     if world > 1 and ar_mode == "overlap" and fused:
         from preference_guided_image_captioning_alignment_b200 import distributed as D
         overlap = D.OverlappedDWAllReduce(V, d, dev, segments=int(os.environ.get("PGICA_DW_SEGMENTS", "8")),
-                                          max_ctas=int(os.environ.get("PGICA_DW_AR_CTAS", "-1")))
+                                          max_ctas=int(os.environ.get("PGICA_DW_AR_CTAS", "-1")),
+                                          multicast={"0": False, "1": True}.get(os.environ.get("PGICA_DW_MULTICAST", ""), None))
     elif world > 1:
         ar_mode = "nccl"
 
@@ -358,7 +359,8 @@ def run_ours(args, rank, world, local_rank):
             emit({"lean": True, "metric": METRIC, "value": value, "n_gpus": world, "ms_per_step": elapsed_ms / args.steps,
                   "phase_ms": phase_ms, "dw_allreduce": ar_mode,
                   "segments": overlap.nseg if overlap is not None else None,
-                  "ar_ctas": overlap.max_ctas if overlap is not None else None})
+                  "ar_ctas": overlap.max_ctas if overlap is not None else None,
+                  "multicast": bool(overlap.multicast_ptr) if overlap is not None else None})
         return
 
     # ------------------------------------------------------------------ end-to-end step (public module API)
@@ -589,7 +591,9 @@ def run_ours(args, rank, world, local_rank):
                                else "one launch per product",
                    "dw_allreduce": ("none" if world == 1 else
                                     f"progress-gated peer-memory all-reduce kernel beside the backward kernel, fp32, "
-                                    f"{overlap.nseg} vocabulary segments; loss/metric scalars in the same buffer"
+                                    f"{overlap.nseg} vocabulary segments, {overlap.max_ctas} CTAs, "
+                                    f"{'summed in the NVSwitch (multimem.ld_reduce)' if overlap.multicast_ptr else 'unicast peer loads'}"
+                                    f"; loss/metric scalars in the same buffer"
                                     if overlap is not None else "nccl fp32 all-reduce after the backward + nccl scalars"),
                    "also_measured": also,
                    "l2": "inputs larger than L2: the step streams 2x103 MB of bf16 LM-head weights and writes a "

@@ -188,9 +188,13 @@ int pgica_softmax_grad_gemm_dual_progress(const void* x, const void* y, int64_t 
  * (its CTAs spin, and must not take SM resources a cooperative producer still needs to become resident).  `stream` must
  * therefore not be the stream the producer was launched on.  Replaces the NCCL all-reduce after the backward
  * (distributed.allreduce_dweight).
+ * multicast_buf: the same buffer through an NVSwitch multicast mapping of all `world` GPUs (NVLS; e.g. torch symmetric
+ * memory's multicast_ptr plus the buffer's offset), or NULL.  When given, the owner's sum is one multimem.ld_reduce
+ * (added inside the switch; the order of the fp32 additions is the switch's) and its result one multimem.st to every
+ * rank — a world-th of the SM work, which matters because the SMs are shared with the producer.
  * ---------------------------------------------------------------------------------------------- */
-int pgica_peer_allreduce_progress(const void* const* bufs_host, const void* const* flags_host, int world, int rank,
-                                  const uint32_t* progress, const uint32_t* progress_target_host,
+int pgica_peer_allreduce_progress(const void* const* bufs_host, const void* const* flags_host, void* multicast_buf,
+                                  int world, int rank, const uint32_t* progress, const uint32_t* progress_target_host,
                                   const int64_t* seg_begin_host, int nseg, uint32_t epoch, uint32_t* local_sync,
                                   int max_ctas, void* stream);
 

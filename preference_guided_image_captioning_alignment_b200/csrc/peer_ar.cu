@@ -11,6 +11,10 @@
 // Reduce-scatter and all-gather of a two-shot all-reduce in one pass; per GPU and direction it moves (world-1)/world of
 // the buffer, like a ring.  Only the last segment's share is exposed after the producer ends.
 //
+// With an NVSwitch multicast mapping of the buffer (NVLS) the slice is summed INSIDE the switch: one
+// multimem.ld_reduce returns the sum over all ranks, one multimem.st stores it into all of them — a `world`-th of
+// the loads, stores and adds on the SMs this kernel shares with the producer.
+//
 // What DDP's bucket all-reduce does for the reference (pkg/training/trainer.py:201,492,616: accelerator.prepare wraps
 // the model, gradients are averaged in backward) — here for the one gradient that dominates the Stage-2 head's traffic.
 #include "common.h"
@@ -47,6 +51,7 @@ struct PeerArParams {
   const uint32_t* progress;     // local producer's counters (may be null)
   uint32_t target[kMaxSeg];
   long long seg_begin4[kMaxSeg + 1];  // segment boundaries in float4 units
+  float4* mc;                   // multicast mapping of the same buffer (null: unicast loads / stores through bufs[])
   uint32_t* local_sync;         // [0] segments released to this rank's CTAs (monotonic), [1] CTAs finished (monotonic)
   int world, rank, nseg;
   uint32_t epoch;
@@ -78,6 +83,22 @@ __device__ __forceinline__ float4 ld_sys_v4(const float4* p) {
 }
 __device__ __forceinline__ void st_sys_v4(float4* p, const float4& v) {
   asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+// NVLS: the load is answered by the switch with the element-wise fp32 sum over every GPU of the multicast group, the
+// store is replicated to all of them.
+__device__ __forceinline__ float4 multimem_ld_reduce_v4(const float4* p) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st_v4(float4* p, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
                : "memory");
 }
 
@@ -126,6 +147,20 @@ __device__ __forceinline__ void reduce_slice(const PeerArParams& p, long long lo
   }
 }
 
+__device__ __forceinline__ void reduce_slice_multicast(const PeerArParams& p, long long lo, long long hi) {
+  constexpr int U = 8;  // loads in flight per thread (a round trip through the switch each): as many bytes as unicast at 8 ranks
+  const long long stride = (long long)gridDim.x * kArThreads;
+  for (long long i = lo + (long long)blockIdx.x * kArThreads + threadIdx.x; i < hi; i += U * stride) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (i + u * stride < hi) v[u] = multimem_ld_reduce_v4(p.mc + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (i + u * stride < hi) multimem_st_v4(p.mc + i + u * stride, v[u]);
+  }
+}
+
 __device__ __forceinline__ void reduce_slice_any(const PeerArParams& p, long long lo, long long hi) {
   for (long long i = lo + (long long)blockIdx.x * kArThreads + threadIdx.x; i < hi; i += (long long)gridDim.x * kArThreads) {
     float4 acc = ld_sys_v4(p.bufs[0] + i);
@@ -163,6 +198,10 @@ __global__ void __launch_bounds__(kArThreads) peer_allreduce_progress_kernel(con
     const long long b = p.seg_begin4[s], e = p.seg_begin4[s + 1];
     const long long len = (e - b) / p.world;
     const long long lo = b + (long long)p.rank * len, hi = lo + len;
+    if (p.mc != nullptr) {
+      reduce_slice_multicast(p, lo, hi);
+      continue;
+    }
     switch (p.world) {
       case 2: reduce_slice<2>(p, lo, hi); break;
       case 4: reduce_slice<4>(p, lo, hi); break;
@@ -190,8 +229,8 @@ __global__ void __launch_bounds__(kArThreads) peer_allreduce_progress_kernel(con
 }  // namespace
 }  // namespace pgica
 
-extern "C" int pgica_peer_allreduce_progress(const void* const* bufs_host, const void* const* flags_host, int world,
-                                             int rank, const uint32_t* progress, const uint32_t* progress_target_host,
+extern "C" int pgica_peer_allreduce_progress(const void* const* bufs_host, const void* const* flags_host,
+                                             void* multicast_buf, int world, int rank, const uint32_t* progress, const uint32_t* progress_target_host,
                                              const int64_t* seg_begin_host, int nseg, uint32_t epoch,
                                              uint32_t* local_sync, int max_ctas, void* stream) {
   using namespace pgica;
@@ -220,6 +259,8 @@ extern "C" int pgica_peer_allreduce_progress(const void* const* bufs_host, const
     p.seg_begin4[s] = seg_begin_host[s] / 4;
   }
   for (int s = 0; s < nseg; ++s) p.target[s] = progress ? progress_target_host[s] : 0u;
+  PGICA_REQUIRE((reinterpret_cast<uintptr_t>(multicast_buf) & 15u) == 0, "peer_allreduce_progress: multicast pointer unaligned");
+  p.mc = static_cast<float4*>(multicast_buf);
   p.progress = progress;
   p.local_sync = local_sync;
   p.world = world;

@@ -56,9 +56,13 @@ constexpr uint32_t kCStageBytes = 4 * kBox64Bytes;    // holder ring slot: 64 op
 constexpr int kCRing = 4;
 constexpr uint32_t kDrainBytes = 32768;                // holder: 4 drain warps x two 4 KB TMA-store buffers
 constexpr int kStagesPerTile = kBT / 64;              // 2
-constexpr int kEpiThreads = 256;                      // producer epilogue: 8 warps, two per scheduler (a lone warp issues ~0.3 instructions
-                                                      // per cycle on dependent FFMA / MUFU chains — ncu stall samples, profiles/)
-constexpr int kThreads = 128 + kEpiThreads;
+// Producer epilogue warps.  With both softmax terms (NT-Xent, k = 512) the epilogue is the producer's bottleneck and a
+// lone warp per scheduler issues only ~0.3 instructions per cycle on its dependent FFMA / MUFU chains (ncu stall
+// samples, profiles/r2_ncu_ntxent_bwd_stalls.txt): 8 warps, two per scheduler.  With the row term only (the LM head,
+// k = 1024) the tensor pipe is the bottleneck and the kernel stays at 4 — 256 threads x 168 registers leave room in
+// the register file for the all-reduce kernel that runs beside it (peer_ar.cu); 384 threads would fill it.
+constexpr int epi_warps(bool row, bool col) { return col ? 8 : (void(row), 4); }
+constexpr int block_threads(bool row, bool col) { return 128 + 32 * epi_warps(row, col); }
 constexpr float kLog2e = 1.4426950408889634f;
 // No slack for aligning the dynamic window by hand: the array is declared __align__(1024) (checked on the device),
 // which keeps 1.5 KB of the SM's 228 KB free — enough for the 1 KB the hardware reserves per resident CTA, so that a
@@ -356,11 +360,13 @@ __host__ __device__ __forceinline__ void for_each_holder_tile(const SggfParams& 
 // P_col = e 2^(c - lse_col), each factor finite in fp32 because 2 c < 100; and the two one-hots fall on the same
 // element, handled outside the inner loop.
 template <bool kRow, bool kCol, bool kShared = false>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(block_threads(kRow, kCol), 1)
 sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__ CUtensorMap tm_y128,
             const __grid_constant__ CUtensorMap tm_x64, const __grid_constant__ CUtensorMap tm_y64,
             const __grid_constant__ CUtensorMap tm_s, const __grid_constant__ CUtensorMap tm_ox,
             const __grid_constant__ CUtensorMap tm_oy, const SggfParams p) {
+  constexpr int kEpiWarps = epi_warps(kRow, kCol), kEpiThreads = 32 * kEpiWarps;
+  constexpr int kChunksPerWarp = 16 / kEpiWarps;  // 32-column chunks of a 128-column tile per epilogue warp (4 or 2)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) {
@@ -535,13 +541,13 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
       if (lane == 0) LAP_FLUSH(6, 4);
     } else if (warp >= 4) {
       // ---------------------------------------------------------------- epilogue: this CTA's Z rows -> two G tiles
-      // Eight warps: warp w reads the TMEM lanes of quarter w & 3 (the hardware's lane window of a warp) and, of every
-      // 128-column tile, the 64 columns of its group (w - 4) >> 2 — one [128][64] box of the staging tile each.
+      // Warp w reads the TMEM lanes of quarter w & 3 (the hardware's lane window of a warp) and, with eight warps, of
+      // every 128-column tile the 64 columns of its group (w - 4) >> 2 — one [128][64] box of the staging tile each.
       const int quarter = warp & 3, wg = (warp - 4) >> 2;
       const int et = threadIdx.x - 128;
       const int row_in_blk = quarter * 32 + lane;
       const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-      const uint32_t g_local = smem_u32(staging) + (uint32_t)wg * kChunkBytes;
+      const uint32_t g_local = smem_u32(staging);
       uint32_t n = 0, ntile = 0;
       LAP_DECL;
       for_each_own_quad(p, pp, p.nP, [&](int q, int r0, int r, int c0, int c) {
@@ -575,13 +581,13 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
               s_cc[et] = kShared ? cf * fast_exp2(p.c - l) : cf;      //         the column's factor
               s_ct[et] = tg;
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
           }
           const int rrel = rt - col0;
-          uint32_t gp[kBT / 4];
+          uint32_t gp[kChunksPerWarp * 16];
 #pragma unroll
-          for (int cl = 0; cl < 2; ++cl) {
-            const int ch = wg * 2 + cl;  // 32-column chunk of the tile
+          for (int cl = 0; cl < kChunksPerWarp; ++cl) {
+            const int ch = wg * kChunksPerWarp + cl;  // 32-column chunk of the tile
             uint32_t rr[32];
             tmem_ld_32x32(tmem_base + lane_addr + buf * 256u + half * kBT + ch * 32, rr);
             tmem_ld_wait();
@@ -621,10 +627,11 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
           mbar_wait(stfree_bar, (ntile & 1u) ^ 1u);  // the exchange warp's TMA store has read the previous tile
           LAP(3);
 #pragma unroll
-          for (int cl = 0; cl < 2; ++cl) {
+          for (int cl = 0; cl < kChunksPerWarp; ++cl) {
+            const int ch = wg * kChunksPerWarp + cl;
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
-              const uint32_t off = sw128_offset(row_in_blk, cl * 4 + c4);
+              const uint32_t off = (uint32_t)(ch >> 1) * kChunkBytes + sw128_offset(row_in_blk, (ch & 1) * 4 + c4);
               st_smem_v4(g_local + off, gp[cl * 16 + c4 * 4 + 0], gp[cl * 16 + c4 * 4 + 1], gp[cl * 16 + c4 * 4 + 2],
                          gp[cl * 16 + c4 * 4 + 3]);
             }
@@ -632,7 +639,7 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
           fence_proxy_async_smem();
           mbar_arrive(stfull_bar);
           ++ntile;
-          if (kCol) asm volatile("bar.sync 3, 256;" ::: "memory");  // the column statistics may be overwritten
+          if (kCol) asm volatile("bar.sync 3, %0;" ::"n"(kEpiThreads) : "memory");  // the column statistics may be overwritten
           LAP(4);
         }
         ++n;
@@ -1002,7 +1009,7 @@ int resident_pairs(int* out) {
     PGICA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * 64);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(block_threads(kRow, kCol));
     cfg.dynamicSmemBytes = kSmem;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1030,7 +1037,7 @@ int launch(const CUtensorMap& tm_x128, const CUtensorMap& tm_y128, const CUtenso
   auto kern = sggf_kernel<kRow, kCol, kShared>;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(2 * (p.nH + p.nW + p.nP)));
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(block_threads(kRow, kCol));
   cfg.dynamicSmemBytes = kSmem;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];

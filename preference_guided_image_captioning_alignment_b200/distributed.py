@@ -169,7 +169,8 @@ class OverlappedDWAllReduce:
     dW lives in torch symmetric memory; the buffer must not be rewritten (next backward) before `done` has fired on
     every rank — `backward` itself orders that."""
 
-    def __init__(self, vocab: int, d: int, device, group=None, segments: int = 8, max_ctas: int = -1):
+    def __init__(self, vocab: int, d: int, device, group=None, segments: int = 8, max_ctas: int = -1,
+                 multicast: Optional[bool] = None):
         import torch.distributed._symmetric_memory as symm
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = _world(group)
@@ -192,6 +193,16 @@ class OverlappedDWAllReduce:
         self.buf_ptrs = [f.data_ptr() for f in flat]
         self.flag_ptrs = [f.data_ptr() + 4 * self.flag_off for f in flat]
         self._flat = flat
+        # NVSwitch multicast mapping of the same allocation (NVLS), when the fabric offers one: the sum then happens
+        # inside the switch.  multicast=None: use it if available; False: never; True: require it.
+        mc_base = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+        if multicast is True and not mc_base:
+            raise RuntimeError("OverlappedDWAllReduce(multicast=True): this symmetric allocation has no multicast mapping")
+        self.multicast_ptr = 0
+        if multicast is None and self.world <= 2:
+            multicast = False  # two ranks: nothing to save (2 loads -> 1) and measured slower, 1.65-1.84 vs 1.60 ms per step
+        if mc_base and multicast is not False and self.world > 1:
+            self.multicast_ptr = mc_base + (flat[self.rank].data_ptr() - int(self.hdl.buffer_ptrs[self.rank]))
         self.local = flat[self.rank][:n].view(self.rows, self.d)
         self.progress = torch.zeros(self.nseg, dtype=torch.int32, device=device)
         self.local_sync = torch.zeros(2, dtype=torch.int32, device=device)
@@ -205,8 +216,12 @@ class OverlappedDWAllReduce:
         # the co-resident backward kernel by 22 % (1.32 vs 1.08 ms), one per two SMs by 9 % with the same exposed tail
         # (0.125 ms), one per four SMs no longer keeps up with NVLink (0.34 ms exposed).  With 2 ranks a rank moves half
         # as much and the full grid is the faster one (1.75 vs 1.80 ms).  Default: every SM up to 2 ranks, half beyond.
+        # Through the multicast mapping a CTA issues a `world`-th of the memory instructions; 8 B200s, same box:
+        # 74 CTAs 1.79 ms per step, 37: 1.71, 24: 1.69 (unicast with 74: 1.75) — profiles/r2_n8_multicast_tuning.jsonl.
         sms = F._lib.load().pgica_sm_count()
         self.max_ctas = int(max_ctas) if int(max_ctas) >= 0 else (sms if self.world <= 2 else max(1, sms // 2))
+        if int(max_ctas) < 0 and self.multicast_ptr:
+            self.max_ctas = max(1, sms // 6)
         self.epoch = 0
         self.done = torch.cuda.Event()
         self.done.record()
@@ -237,7 +252,8 @@ class OverlappedDWAllReduce:
                                                 self.progress, self.rows_per_seg, length_normalize, dhidden_dtype)
         targets = [self.epoch * inc * np_ for np_ in self.seg_pairs]
         F.peer_allreduce_progress(self.buf_ptrs, self.flag_ptrs, self.rank, self.progress, targets, self.seg_begin,
-                                  self.epoch, self.local_sync, self.max_ctas, stream=self.stream)
+                                  self.epoch, self.local_sync, self.max_ctas, stream=self.stream,
+                                  multicast_ptr=self.multicast_ptr)
         self.done = torch.cuda.Event()
         self.done.record(self.stream)
         if scalars is not None:

@@ -341,8 +341,9 @@ def lmhead_logprob_bwd_progress(hidden, weight, row_label, row_weight, lse, grad
 
 
 def peer_allreduce_progress(buf_ptrs, flag_ptrs, rank, progress, targets, seg_begin, epoch, local_sync, max_ctas=0,
-                            stream=None):
-    """Launch the progress-gated peer all-reduce (pgica_peer_allreduce_progress) on `stream` (default: current)."""
+                            stream=None, multicast_ptr=0):
+    """Launch the progress-gated peer all-reduce (pgica_peer_allreduce_progress) on `stream` (default: current).
+    multicast_ptr: the buffer through an NVSwitch multicast mapping (0: sums over unicast peer loads)."""
     lib = _lib.load()
     world, nseg = len(buf_ptrs), len(seg_begin) - 1
     bufs = (ctypes.c_void_p * world)(*[int(q) for q in buf_ptrs])
@@ -350,7 +351,8 @@ def peer_allreduce_progress(buf_ptrs, flag_ptrs, rank, progress, targets, seg_be
     tg = (ctypes.c_uint32 * nseg)(*[int(t) & 0xFFFFFFFF for t in targets]) if progress is not None else None
     sb = (ctypes.c_int64 * (nseg + 1))(*[int(v) for v in seg_begin])
     st = ctypes.c_void_p(stream.cuda_stream) if stream is not None else _stream()
-    _lib.check(lib.pgica_peer_allreduce_progress(bufs, flags, world, int(rank), _p(progress), tg, sb, nseg,
+    mc = ctypes.c_void_p(int(multicast_ptr)) if multicast_ptr else None
+    _lib.check(lib.pgica_peer_allreduce_progress(bufs, flags, mc, world, int(rank), _p(progress), tg, sb, nseg,
                                                  int(epoch) & 0xFFFFFFFF, _p(local_sync), int(max_ctas), st))
 
 

@@ -111,28 +111,34 @@ def main():
         dh_ref, dw_ref = Fn.lmhead_logprob_bwd(H2, W2, rl2, rw2, lse2, gs, False)
         dw_ref = dw_ref.clone()
         dist.all_reduce(dw_ref)
-        red = D2.OverlappedDWAllReduce(V2, d2, dev, segments=nseg)
-        for trial in range(3):
-            scal = torch.arange(6, device=dev, dtype=torch.float32) + rank + trial
-            dh2, dw2, done, scal_sum = red.backward(H2, W2, rl2, rw2, lse2, gs, False, scalars=scal)
-            torch.cuda.current_stream().wait_event(done)
-            torch.cuda.synchronize()
-            e_w = rel(dw2.cpu().numpy(), dw_ref.cpu().numpy())
-            e_h = rel(dh2.float().cpu().numpy(), dh_ref.float().cpu().numpy())
-            want_scal = sum(torch.arange(6, dtype=torch.float32) + q + trial for q in range(world))
-            e_s = float((scal_sum.cpu() - want_scal).abs().max())
-            # every rank must hold bit-identical sums (fixed rank order inside the kernel)
-            chk = dw2.double().sum().reshape(1)
-            allchk = [torch.empty_like(chk) for _ in range(world)]
-            dist.all_gather(allchk, chk)
-            same = all(bool(c.item() == allchk[0].item()) for c in allchk)
-            res = {"check": "overlapped_dw_allreduce", "world": world, "shape": [B2, T2, d2, V2], "segments": red.nseg,
-                   "trial": trial, "dw_rel": e_w, "dh_rel": e_h, "scalars_maxabs": e_s, "identical_on_all_ranks": same,
-                   "ok": bool(e_w < 1e-5 and e_h < 1e-5 and e_s < 1e-4 and same)}
-            ok &= res["ok"]
-            if rank == 0:
-                print(json.dumps(res), flush=True)
-        del red
+        for multicast in (False, None):  # unicast peer loads, then the NVSwitch multicast path where the fabric has one
+            red = D2.OverlappedDWAllReduce(V2, d2, dev, segments=nseg, multicast=multicast)
+            if multicast is None and not red.multicast_ptr:
+                if rank == 0:
+                    print(json.dumps({"check": "overlapped_dw_allreduce", "multicast": "not available"}), flush=True)
+                del red
+                continue
+            for trial in range(3):
+                scal = torch.arange(6, device=dev, dtype=torch.float32) + rank + trial
+                dh2, dw2, done, scal_sum = red.backward(H2, W2, rl2, rw2, lse2, gs, False, scalars=scal)
+                torch.cuda.current_stream().wait_event(done)
+                torch.cuda.synchronize()
+                e_w = rel(dw2.cpu().numpy(), dw_ref.cpu().numpy())
+                e_h = rel(dh2.float().cpu().numpy(), dh_ref.float().cpu().numpy())
+                want_scal = sum(torch.arange(6, dtype=torch.float32) + q + trial for q in range(world))
+                e_s = float((scal_sum.cpu() - want_scal).abs().max())
+                # every rank must hold bit-identical sums (fixed rank order inside the kernel)
+                chk = dw2.double().sum().reshape(1)
+                allchk = [torch.empty_like(chk) for _ in range(world)]
+                dist.all_gather(allchk, chk)
+                same = all(bool(c.item() == allchk[0].item()) for c in allchk)
+                res = {"check": "overlapped_dw_allreduce", "multicast": bool(red.multicast_ptr), "world": world,
+                       "shape": [B2, T2, d2, V2], "segments": red.nseg, "trial": trial, "dw_rel": e_w, "dh_rel": e_h, "scalars_maxabs": e_s, "identical_on_all_ranks": same,
+                       "ok": bool(e_w < 1e-5 and e_h < 1e-5 and e_s < 1e-4 and same)}
+                ok &= res["ok"]
+                if rank == 0:
+                    print(json.dumps(res), flush=True)
+            del red
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
