@@ -30,7 +30,15 @@ constexpr int kStages = 7;
 constexpr int kAccStages = 2;
 constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
 constexpr uint32_t kBBytes = (kBlockN / 2) * kBlockK * 2;  // this CTA's half of the B tile
-constexpr int kThreads = 256;
+// Epilogue: 8 warps = 2 per scheduler (a lone warp leaves its scheduler idle on every dependent FFMA / MUFU / shuffle; the
+// dual backward kernel's ncu stall samples showed 0.31 instructions per cycle with one).  Warp w reads TMEM lane quarter
+// w & 3 and column group (w - 4) >> 2 of the tile: each group publishes its own (max, sum, target) partial.
+// The one-pass NT-Xent forward (kCols: two exponentials per element and a butterfly sum) is epilogue-bound and takes two
+// groups; the plain forward (the LM head at k = 1024: tensor-bound, 0.94 of peak) keeps one — a second group doubles the
+// partials lse_merge_kernel has to fold, +1 % on that launch.
+constexpr int kMaxEpiGroups = 2;
+constexpr int epi_groups(bool cols) { return cols ? 2 : 1; }
+constexpr int block_threads(bool cols) { return 128 + 128 * epi_groups(cols); }
 constexpr int kEpilogueWarp0 = 4;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
@@ -38,12 +46,13 @@ constexpr float kLn2 = 0.6931471805599453f;
 struct GemmLseParams {
   int rows, cols, k;
   int num_m_blocks, num_m_pairs, num_n_tiles, rows_pad;
+  int num_parts;    // num_n_tiles * column groups of the launched kernel
   float scale;
   const int* labels;
   int diag_offset;
-  float* part_max;  // [num_n_tiles][rows_pad]  max of scale*log2e*z over the tile's columns
-  float* part_sum;  // [num_n_tiles][rows_pad]  sum of exp2(. - max)
-  float* part_tgt;  // [num_n_tiles][rows_pad]  scale*z at the label column, -inf if it is not in this tile
+  float* part_max;  // [num_parts][rows_pad]  max of scale*log2e*z over the columns of a tile's group
+  float* part_sum;  // [..][rows_pad]  sum of exp2(. - max);  max = -inf, sum = 0 when the group lies past the last column
+  float* part_tgt;  // [..][rows_pad]  scale*z at the label column, -inf if it is not among these columns
   float* z_out;     // optional dense [rows][cols] copy of scale*z (similarity-matrix API only)
   // optional COLUMN statistics from the same tiles (NT-Xent with bounded logits: S is computed once instead of twice).
   // Every warp of the epilogue owns 32 rows; per 32-column chunk it publishes the column sums of exp2(t - shift) over
@@ -79,9 +88,10 @@ __device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
 constexpr size_t kSmemBytes = 1024 /*align slack*/ + kStages * (kABytes + kBBytes) + 256 /*barriers*/;
 
 template <bool kCols>  // kCols: also publish the column statistics (a separate instantiation: the plain forward keeps its code)
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(block_threads(kCols), 1)
 gemm_lse_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                 const GemmLseParams p) {
+  constexpr int kEpiGroups = epi_groups(kCols);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* smem_a = smem;
@@ -110,7 +120,7 @@ gemm_lse_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     }
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 256);  // leader's: the epilogue threads of both CTAs
+      mbar_init(&tempty_bar[i], 2 * 128 * kEpiGroups);  // leader's: the epilogue threads of both CTAs
     }
     fence_mbar_init();
   }
@@ -190,6 +200,8 @@ gemm_lse_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     }
   } else if (warp >= kEpilogueWarp0) {
     const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    const int wg = (warp - kEpilogueWarp0) >> 2;  // column group of the tile
+    constexpr int kChunks = kBlockN / 32 / kEpiGroups;
     const int row_in_blk = quarter * 32 + lane;
     const float c = p.scale * kLog2e;
     int acc = 0;
@@ -209,7 +221,8 @@ gemm_lse_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       const int rel = label - n0;  // label column relative to this tile
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kBlockN;
 #pragma unroll 1
-      for (int ch = 0; ch < kBlockN / 32; ++ch) {
+      for (int cl = 0; cl < kChunks; ++cl) {
+        const int ch = wg * kChunks + cl;
         if (tail && n0 + ch * 32 >= p.cols) break;  // warp-uniform: nothing valid from here on
         uint32_t r[32];
         tmem_ld_32x32(taddr + ch * 32, r);
@@ -295,7 +308,7 @@ gemm_lse_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         acc_phase ^= 1;
       }
       if (m_blk < p.num_m_blocks) {
-        const size_t o = static_cast<size_t>(n_tile) * p.rows_pad + m_blk * kBlockM + row_in_blk;
+        const size_t o = (static_cast<size_t>(n_tile) * kEpiGroups + wg) * p.rows_pad + m_blk * kBlockM + row_in_blk;
         p.part_max[o] = run_m;
         p.part_sum[o] = run_s;
         p.part_tgt[o] = run_t;
@@ -322,11 +335,12 @@ lse_merge_kernel(const GemmLseParams p, float* __restrict__ lse, float* __restri
   const int row = blockIdx.x * kMergeRows + r;
   float m = -INFINITY, sum = 0.f, t = -INFINITY;
   if (row < p.rows) {
-    for (int s = g; s < p.num_n_tiles; s += kMergeGroups) {
+    for (int s = g; s < p.num_parts; s += kMergeGroups) {
       const size_t o = static_cast<size_t>(s) * p.rows_pad + row;
       const float pm = p.part_max[o], ps = p.part_sum[o];
+      if (pm == -INFINITY && ps == 0.f) continue;  // a column group past the last column; (-inf, NaN) — a NaN row, whose
+                                                   // maximum fmaxf leaves at -inf — falls through and poisons the sum
       const float mn = fmaxf(m, pm);
-      // (-inf) - (-inf) cannot occur: a tile always has at least one valid column, so pm is finite or NaN
       sum = sum * exp2f(m - mn) + ps * exp2f(pm - mn);
       m = mn;
       t = fmaxf(t, p.part_tgt[o]);
@@ -412,7 +426,7 @@ int plan(int64_t rows, int64_t cols, int64_t k, GemmLseParams* p, int* grid, siz
   PGICA_REQUIRE(total < (1ll << 30), "gemm_lse: too many tiles");
   const int pairs = device_sm_count() / 2;
   *grid = 2 * (int)(total < pairs ? total : pairs);
-  *ws_bytes = 3 * align_up((size_t)p->num_n_tiles * p->rows_pad * sizeof(float), 256);
+  *ws_bytes = 3 * align_up((size_t)p->num_n_tiles * kMaxEpiGroups * p->rows_pad * sizeof(float), 256);
   return PGICA_OK;
 }
 
@@ -462,6 +476,7 @@ static int gemm_lse_impl(const void* a, const void* b, int64_t rows, int64_t col
   p.part_max = reinterpret_cast<float*>(workspace);
   p.part_sum = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + seg);
   p.part_tgt = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + 2 * seg);
+  p.num_parts = p.num_n_tiles * epi_groups(lse_col != nullptr);
   p.scale = scale;
   p.labels = labels;
   p.diag_offset = (int)diag_offset;
@@ -478,7 +493,7 @@ static int gemm_lse_impl(const void* a, const void* b, int64_t rows, int64_t col
   PGICA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(lse_col ? block_threads(true) : block_threads(false));
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

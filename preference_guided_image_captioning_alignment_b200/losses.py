@@ -91,7 +91,14 @@ class DeferredLoss(torch.Tensor):
 
 class ContrastiveLoss(nn.Module):
     """Drop-in for pkg/models/model.py:957-1000: symmetric cross-entropy over I·Tᵀ/τ on inputs that are used
-    AS GIVEN (the model normalises them, model.py:826-829); temperature is not clamped."""
+    AS GIVEN (the model normalises them, model.py:826-829); temperature is not clamped.
+
+    The constructor is the reference's.  Setting the attribute `assume_normalized = True` afterwards promises
+    unit-norm rows, which lets large batches take the one-pass forward / one-exponential backward; embeddings that
+    come out of this package's fused LayerNorm + L2-normalise (prologue.fuse_projection_tail) carry that promise
+    themselves."""
+
+    assume_normalized = False
 
     def __init__(self, temperature: float = 0.07) -> None:
         super().__init__()
@@ -99,7 +106,9 @@ class ContrastiveLoss(nn.Module):
         self.logger = logging.getLogger(__name__)
 
     def forward(self, image_embeddings: torch.Tensor, text_embeddings: torch.Tensor) -> torch.Tensor:
-        loss, _, _ = ops.ntxent_auto(image_embeddings, text_embeddings, 1.0 / float(self.temperature), True)
+        unit = self.assume_normalized or (getattr(image_embeddings, "_pgica_unit_norm", False)
+                                          and getattr(text_embeddings, "_pgica_unit_norm", False))
+        loss, _, _ = ops.ntxent_auto(image_embeddings, text_embeddings, 1.0 / float(self.temperature), True, bool(unit))
         return loss.to(image_embeddings.dtype) if image_embeddings.dtype == torch.float64 else loss
 
 

@@ -24,25 +24,29 @@ def _grad_dtype(t):
 
 # ============================================================================================ NT-Xent
 @torch.library.custom_op("pgica::ntxent", mutates_args=())
-def ntxent(a: Tensor, b: Tensor, inv_tau: float, reduce_mean: bool) -> Tuple[Tensor, Tensor, Tensor]:
+def ntxent(a: Tensor, b: Tensor, inv_tau: float, reduce_mean: bool, bounded: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
     """Symmetric NT-Xent on (B, D) x (B, D) embeddings as given (no normalisation here).
+    bounded: the caller promises unit-norm rows — one pass over the similarity tiles gives both log-sum-exps.
     Returns (loss[], lse_row[B], lse_col[B])."""
     if a.shape != b.shape or a.dim() != 2:
         raise ValueError(f"ntxent expects two (B, D) tensors of equal shape, got {tuple(a.shape)} {tuple(b.shape)}")
     n = a.shape[0]
     if a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16:
-        lse_row, diag, lse_col = F.ntxent_fwd(a.contiguous(), b.contiguous(), inv_tau, 0)
+        lse_row, diag, lse_col = F.ntxent_fwd(a.contiguous(), b.contiguous(), inv_tau, 0, bounded=bounded)
     else:  # fp32 embeddings: two-term bf16 split, one GEMM of depth 3*D per direction (as ntxent_cosine does)
         al, ar = F.split3(a)
         bl, br = F.split3(b)
-        lse_row, diag = F.gemm_lse(al, br, inv_tau, None, 0)
-        lse_col, _ = F.gemm_lse(bl, ar, inv_tau, None, 0, want_tgt=False)
+        if bounded:  # a_left3 . b_right3 and b_left3 . a_right3 are the same three products: one pass serves both
+            lse_row, diag, lse_col = F.ntxent_fwd(al, br, inv_tau, 0, bounded=True)
+        else:
+            lse_row, diag = F.gemm_lse(al, br, inv_tau, None, 0)
+            lse_col, _ = F.gemm_lse(bl, ar, inv_tau, None, 0, want_tgt=False)
     loss = F.ntxent_loss(lse_row, diag, lse_col, 1.0 / n if reduce_mean else 1.0)
     return loss, lse_row, lse_col
 
 
 @ntxent.register_fake
-def _(a, b, inv_tau, reduce_mean):
+def _(a, b, inv_tau, reduce_mean, bounded=False):
     return a.new_empty((), dtype=torch.float32), _f32(a.shape[0], a), _f32(b.shape[0], a)
 
 
@@ -104,23 +108,24 @@ class _NTXentSmallEager(torch.autograd.Function):
         return (da * g_loss).to(ctx.dtypes[0]), (db * g_loss).to(ctx.dtypes[1]), None, None
 
 
-def ntxent_auto(a: Tensor, b: Tensor, inv_tau: float, reduce_mean: bool):
-    """`ntxent_small` when the batch fits one CTA, else the general kernels.  -> (loss, lse_row, lse_col)"""
+def ntxent_auto(a: Tensor, b: Tensor, inv_tau: float, reduce_mean: bool, bounded: bool = False):
+    """`ntxent_small` when the batch fits one CTA, else the general kernels (bounded: unit-norm rows promised, see
+    `ntxent`).  -> (loss, lse_row, lse_col)"""
     if a.dim() == 2 and a.shape == b.shape and a.is_cuda and F.ntxent_small_supported(a.shape[0], a.shape[1]):
         if torch.compiler.is_compiling():
             return ntxent_small(a, b, inv_tau, reduce_mean)[:3]
         return _NTXentSmallEager.apply(a, b, inv_tau, reduce_mean)
-    return ntxent(a, b, inv_tau, reduce_mean)
+    return ntxent(a, b, inv_tau, reduce_mean, bounded)
 
 
 @torch.library.custom_op("pgica::ntxent_bwd", mutates_args=())
 def ntxent_bwd(a: Tensor, b: Tensor, lse_row: Tensor, lse_col: Tensor, grad_loss: Tensor, inv_tau: float,
-               reduce_mean: bool) -> Tuple[Tensor, Tensor]:
+               reduce_mean: bool, bounded: bool = False) -> Tuple[Tensor, Tensor]:
     n, d = a.shape
     mult = 1.0 / (2.0 * n) if reduce_mean else 0.5
     if a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16:
         return F.ntxent_bwd(a.contiguous(), b.contiguous(), inv_tau, 0, lse_row, lse_col, grad_loss, mult,
-                            da_dtype=torch.bfloat16, db_dtype=torch.bfloat16)
+                            da_dtype=torch.bfloat16, db_dtype=torch.bfloat16, bounded=bounded)
     # the backward must recompute exactly the logits the forward saw: same split operands, depth 3*D; columns
     # [0, D) and [2D, 3D) of each product are G.hi and G.lo of the other side
     al, ar = F.split3(a)
@@ -131,22 +136,23 @@ def ntxent_bwd(a: Tensor, b: Tensor, lse_row: Tensor, lse_col: Tensor, grad_loss
 
 
 @ntxent_bwd.register_fake
-def _(a, b, lse_row, lse_col, grad_loss, inv_tau, reduce_mean):
+def _(a, b, lse_row, lse_col, grad_loss, inv_tau, reduce_mean, bounded=False):
     dt = torch.bfloat16 if (a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16) else torch.float32
     return torch.empty_like(a, dtype=dt), torch.empty_like(b, dtype=dt)
 
 
 def _ntxent_setup(ctx, inputs, output):
-    a, b, inv_tau, reduce_mean = inputs
+    a, b, inv_tau, reduce_mean = inputs[:4]
     _, lse_row, lse_col = output
     ctx.save_for_backward(a, b, lse_row, lse_col)
     ctx.inv_tau, ctx.reduce_mean = inv_tau, reduce_mean
+    ctx.bounded = bool(inputs[4]) if len(inputs) > 4 else False
 
 
 def _ntxent_backward(ctx, g_loss, g_lr, g_lc):
     a, b, lse_row, lse_col = ctx.saved_tensors
-    da, db = ntxent_bwd(a, b, lse_row, lse_col, g_loss.contiguous(), ctx.inv_tau, ctx.reduce_mean)
-    return da.to(a.dtype), db.to(b.dtype), None, None
+    da, db = ntxent_bwd(a, b, lse_row, lse_col, g_loss.contiguous(), ctx.inv_tau, ctx.reduce_mean, ctx.bounded)
+    return da.to(a.dtype), db.to(b.dtype), None, None, None
 
 
 ntxent.register_autograd(_ntxent_backward, setup_context=_ntxent_setup)

@@ -185,6 +185,7 @@ def _proj_norm_forward(self, z):
         return TF.layer_norm(z, self.normalized_shape, self.weight, self.bias, self.eps)
     e, n = ln_l2norm(z, self)
     out = e.as_subclass(NormalizedCarrier)
+    n._pgica_unit_norm = True  # read by losses.ContrastiveLoss: unit-norm rows by construction
     out._pgica_normalized = n
     return out
 

@@ -1424,3 +1424,33 @@ def test_ntxent_backward_one_exponential_matches_two(pg, cuda_device, ra, rb, D,
     da4, db4 = F.ntxent_bwd(a, b, 100.0, off, lr9, lc9, gl, mult)
     # (dA of a few-row problem is add-reduced over column groups in arrival order: equal to rounding, not bit for bit)
     assert rel(da3, da4) < 1e-6 and torch.equal(db3, db4) and bool(torch.isfinite(da3).all())
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_contrastive_loss_assume_normalized(pg, cuda_device, dtype):
+    """model-flavour ContrastiveLoss beyond the single-CTA batch: the unit-norm promise (one-pass forward, shared
+    exponential backward) gives the loss and gradients of the default path and of fp64 torch."""
+    B, D, tau = 1024, 512, 0.07
+    g = torch.Generator().manual_seed(9)
+    t = torch.nn.functional.normalize(torch.randn(B, D, generator=g), dim=-1)
+    i = torch.nn.functional.normalize(t + 0.5 * torch.randn(B, D, generator=g), dim=-1)
+    res = {}
+    for flag in (False, True):
+        a = i.to(dtype).to(cuda_device).requires_grad_()
+        b = t.to(dtype).to(cuda_device).requires_grad_()
+        head = pg.ContrastiveLoss(temperature=tau)
+        head.assume_normalized = flag
+        loss = head(a, b)
+        loss.backward()
+        res[flag] = (loss.detach().double(), a.grad.double(), b.grad.double())
+    A = i.to(dtype).double().to(cuda_device).requires_grad_()
+    Bm = t.to(dtype).double().to(cuda_device).requires_grad_()
+    S = A @ Bm.T / tau
+    idx = torch.arange(B, device=cuda_device)
+    ref = 0.5 * (torch.nn.functional.cross_entropy(S, idx) + torch.nn.functional.cross_entropy(S.T, idx))
+    ref.backward()
+    tol_l, tol_g = (1e-6, 8e-3) if dtype == torch.bfloat16 else (1e-6, 3e-3)
+    for flag in (False, True):
+        assert abs(res[flag][0] - ref.detach()) / abs(ref.detach()) < tol_l
+        assert rel(res[flag][1], A.grad) < tol_g and rel(res[flag][2], Bm.grad) < tol_g
+    assert abs(res[True][0] - res[False][0]) / abs(res[False][0]) < 1e-6

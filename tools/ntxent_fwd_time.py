@@ -17,3 +17,4 @@ for ra, rb in ((4096, 4096), (4096, 32768), (16384, 16384)):
         e1.record()
         torch.cuda.synchronize()
         print(ra, rb, "one-pass" if bounded else "two-pass", round(e0.elapsed_time(e1) / 10 * 1e3, 1), "us", flush=True)
+
