@@ -827,28 +827,36 @@ def ntxent_extras(torch, F, dev):
 
         small = F.ntxent_small_supported(B, 512)  # B <= 128: loss and both gradients from ONE single-CTA launch
 
-        def step():
+        def step(unit_norm=True):
             if small:
                 return F.ntxent_small(a, b, 2.0, True)[0]
-            lr, dg, lc = F.ntxent_fwd(a, b, 2.0, bounded=True)  # unit-norm rows: one pass for both log-sum-exps
+            # unit-norm rows (what the reference model feeds its loss): one pass for both log-sum-exps, one exponential
+            # per element in the backward; general inputs: two passes, two exponentials
+            lr, dg, lc = F.ntxent_fwd(a, b, 2.0, bounded=unit_norm)
             loss = F.ntxent_loss(lr, dg, lc, 1.0 / B)
-            F.ntxent_bwd(a, b, 2.0, 0, lr, lc, one, 1.0 / (2 * B), bounded=True)
+            F.ntxent_bwd(a, b, 2.0, 0, lr, lc, one, 1.0 / (2 * B), bounded=unit_norm)
             return loss
 
-        for _ in range(3):
-            step()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        iters = 20 if B <= 4096 else 5
-        e0.record()
-        for _ in range(iters):
-            step()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / iters
+        def timed(unit_norm):
+            for _ in range(3):
+                step(unit_norm)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            iters = 20 if B <= 4096 else 5
+            e0.record()
+            for _ in range(iters):
+                step(unit_norm)
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / iters
+
+        ms = timed(True)
         out[name] = {"pairs_per_s": B / (ms * 1e-3), "us_per_step": ms * 1e3,
                      "algorithmic_tflops": 6.0 * B * B * 512 / ms / 1e9,
                      "launches_per_step": 1 if small else None}
+        if not small:
+            out[name]["inputs"] = "unit-norm rows promised (one-pass forward, one exponential per element backward)"
+            out[name]["us_per_step_general_inputs"] = timed(False) * 1e3
     return out
 
 
