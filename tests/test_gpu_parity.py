@@ -1382,7 +1382,8 @@ def test_ntxent_forward_one_pass_matches_two_pass(pg, cuda_device, ra, rb, D, ta
         .bfloat16().to(cuda_device)
     lr2, dg2, lc2 = F.ntxent_fwd(a, b, 1.0 / tau, off)
     lr1, dg1, lc1 = F.ntxent_fwd(a, b, 1.0 / tau, off, bounded=True)
-    assert torch.equal(lr1, lr2) and torch.equal(dg1, dg2)          # the row side is the same arithmetic
+    # the row side is the same arithmetic up to the grouping of the column partials (two epilogue groups per tile)
+    assert rel(lr1, lr2) < 1e-6 and float((lr1 - lr2).abs().max()) < 1e-5 and torch.equal(dg1, dg2)
     assert rel(lc1, lc2) < 2e-6 and float((lc1 - lc2).abs().max()) < 2e-5 * max(1.0, 1.0 / tau)
     if ra * rb <= 5_000_000:
         S = a.double() @ b.double().T / tau
