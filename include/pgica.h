@@ -154,7 +154,8 @@ int pgica_softmax_grad_gemm_dual(const void* x, const void* y, int64_t mx, int64
  * weight gradient (what DDP's bucket reducer does for the reference, pkg/training/trainer.py:201,492,616)
  * can run over NVLink while the tensor cores are still computing the rest of the vocabulary.  out_y rows are cut into
  * segments of rows_per_segment (a multiple of 256); whenever a drain warp has seen the TMA stores of a final out_y tile
- * complete it adds 1 to progress[segment] with release semantics at SYSTEM scope.  A full segment has received
+ * complete it adds 1 to progress[segment] with release semantics at GPU scope (the consumer runs on this GPU and
+ * relays to its peers).  A full segment has received
  * (*increments_per_256_rows_host) * rows_per_segment / 256 increments (fewer for the ragged last one: count whole
  * 256-row pairs of ceil(my / 256)); the counters only ever grow — the caller compares against a per-launch target.
  * pgica_peer_allreduce_progress below is the consumer.  out_y is fp32 and x must fit one chunk of the kernel.

@@ -2,7 +2,7 @@
 // with the kernel that produces it.
 //
 // The dual backward kernel (sgg_f.cu) finishes dW in vocabulary order and publishes per-segment progress counters
-// (system-scope release).  This kernel is launched on a second stream next to it: one small CTA per SM (256 threads,
+// (release at GPU scope).  This kernel is launched on a second stream next to it: one small CTA per SM (256 threads,
 // ~60 registers, no shared memory — it fits beside the persistent CTA the dual kernel keeps on every SM).  For each
 // segment it waits for the local counter, meets the other ranks at a flag barrier in peer memory, and then every rank
 // reduces ITS 1/world slice of the segment: 16-byte loads of the slice from all `world` buffers (one outstanding load

@@ -123,7 +123,7 @@ struct SggfParams {
   const int* c_tgt;
   void* out_x;
   void* out_y;
-  uint32_t* progress;     // optional: progress[s] += 1 (release, system scope) whenever a drain warp's stores of a FINAL
+  uint32_t* progress;     // optional: progress[s] += 1 (release, gpu scope) whenever a drain warp's stores of a FINAL
   int cp_per_seg;         //   OutY tile of segment s = (column pair / cp_per_seg) are complete; a column pair (256 rows
                           //   of OutY) contributes 8 * S increments.  Lets a co-resident kernel or the host start
                           //   moving finished rows of OutY (the data-parallel all-reduce of dW) while the grid is
@@ -846,9 +846,11 @@ sggf_kernel(const __grid_constant__ CUtensorMap tm_x128, const __grid_constant__
     const int n_chunks = (p.RB2 + p.R2 - 1) / p.R2;
     int pending_seg = -1;  // segment of the OutY tile whose TMA stores this warp has issued but not yet seen complete
     auto signal_progress = [&](int seg) {
-      // TMA (async-proxy) stores complete -> generic-proxy release at SYSTEM scope: the reader may be another GPU
+      // TMA (async-proxy) stores complete -> generic-proxy release at GPU scope.  The consumer is a kernel on THIS GPU
+      // (peer_ar.cu acquires the counter and relays to the other ranks with its own system-scope release: causality
+      // order is transitive); a system-scope release here cost 1.8 us per drain on the Y-holders' critical path.
       asm volatile("fence.proxy.async.global;" ::: "memory");
-      asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p.progress + seg), "r"(1u) : "memory");
+      asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p.progress + seg), "r"(1u) : "memory");
     };
     LAP_DECL;
     for_each_holder_tile(
@@ -1066,7 +1068,7 @@ int launch(const CUtensorMap& tm_x128, const CUtensorMap& tm_y128, const CUtenso
 }
 
 struct ProgressSpec {
-  uint32_t* counters = nullptr;  // device, one uint32 per segment of OutY rows (system-scope visible)
+  uint32_t* counters = nullptr;  // device, one uint32 per segment of OutY rows
   int64_t rows_per_segment = 0;  // multiple of 256 (a column pair)
 };
 

@@ -154,7 +154,7 @@ class OverlappedDWAllReduce:
     """Data-parallel sum of the LM-head weight gradient that runs WHILE the backward kernel is still producing it.
 
     The dual backward kernel (csrc/sgg_f.cu) finalises dW in vocabulary order and bumps a per-segment progress counter
-    (system-scope release) whenever the stores of a finished tile have completed.  Next to it, on a second stream, runs
+    (release at GPU scope) whenever the stores of a finished tile have completed.  Next to it, on a second stream, runs
     `pgica_peer_allreduce_progress` (csrc/peer_ar.cu): one small CTA per SM that fits beside the persistent kernel.  Per
     segment it waits for the local counter, meets the other ranks at a flag barrier in peer memory, and every rank sums
     its 1/W slice of the segment straight out of all W symmetric buffers over NVLink and stores the result into all of
